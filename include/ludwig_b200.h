@@ -1,0 +1,186 @@
+/*
+ * ludwig_b200.h — C ABI of libludwig_b200.so
+ *
+ * Drop-in replacement for the KernelAbstractions launch sites of OPEN_Ludwig's
+ * per-timestep D3Q27 hot path.  Every entry point cites the reference call site
+ * (file:line under /root/reference/src) it replaces.  The reference has no FFI of
+ * its own (it is 100 % Julia); the binding a maintainer adds is the `ccall` glue
+ * in open_ludwig_b200/julia/LudwigB200.jl.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative LUDWIG_E* code on error and
+ *    never throws across the ABI; ludwig_last_error() returns the message.
+ *  - all index tables are passed EXACTLY as the reference builds them: 1-based,
+ *    0 = "none", Julia column-major.  Field arrays use the reference layout
+ *    f[x,y,z,b,k]  <=>  linear = x + 8*y + 64*z + 512*b + 512*n_blocks*k  (0-based).
+ *    The library converts to its own HBM layout internally.
+ *  - host pointers are borrowed for the duration of the call only.
+ *  - handles are opaque and owned by the library.
+ *  - step / force calls are asynchronous on the context's stream until
+ *    ludwig_sync() or a call that returns host scalars.
+ *  - one calling thread per context.
+ */
+#ifndef LUDWIG_B200_H
+#define LUDWIG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUDWIG_OK 0
+#define LUDWIG_EINVAL (-1)   /* bad argument */
+#define LUDWIG_ECUDA (-2)    /* CUDA runtime error */
+#define LUDWIG_ENOMEM (-3)   /* allocation failure */
+#define LUDWIG_ESTATE (-4)   /* call order violated */
+
+typedef struct ludwig_ctx ludwig_ctx;
+typedef struct ludwig_mesh ludwig_mesh;
+typedef struct ludwig_forces ludwig_forces;
+
+/* One refinement level as the reference's BlockLevel (blocks.jl:16-65) holds it on
+ * the host after setup_multilevel_domain (domain.jl:224-236). */
+typedef struct ludwig_level_desc {
+    int32_t level_id;              /* 1-based (blocks.jl:17) */
+    int32_t n_blocks;              /* length(active_block_coords) */
+    int32_t dim_x, dim_y, dim_z;   /* size(block_pointer) = max active block coord per axis (blocks.jl:104-115) */
+    float tau;                     /* blocks.jl:20 */
+    double dx;                     /* blocks.jl:18 (a Float64 holding a Float32 value) */
+    const int32_t* block_pointer;  /* [dim_x,dim_y,dim_z] col-major, 1-based block index, 0 = none */
+    const int32_t* neighbor_table; /* [n_blocks,27] col-major, dir = (dx+1)+(dy+1)*3+(dz+1)*9 (+1 in Julia) */
+    const int32_t* map_x;          /* [n_blocks] 1-based block coordinates */
+    const int32_t* map_y;
+    const int32_t* map_z;
+    const uint8_t* obstacle;       /* Bool[8,8,8,n_blocks] */
+    const float* sponge;           /* Float32[8,8,8,n_blocks] */
+    const float* wall_dist;        /* Float32[8,8,8,n_blocks] (metres; 100 = far) */
+    int32_t temporal_storage;      /* has_temporal_storage(level) (blocks.jl:208) */
+    int32_t bouzidi_enabled;       /* blocks.jl:156 */
+    int32_t n_boundary_cells;      /* blocks.jl:64 */
+    const uint16_t* q_map_f16;     /* Float16[8,8,8,n_blocks,27] bit patterns, or NULL if !bouzidi_enabled */
+    const int32_t* cell_block;     /* [n_boundary_cells] 1-based */
+    const int8_t* cell_x;          /* [n_boundary_cells] 1-based local coords */
+    const int8_t* cell_y;
+    const int8_t* cell_z;
+} ludwig_level_desc;
+
+/* Scalar arguments of perform_timestep_v2! (physics_v2.jl:26-41) that are constant
+ * across a batch (main.jl:60-66,176-180). */
+typedef struct ludwig_params {
+    float c_wale;
+    float nu_sgs_bg;
+    float inlet_turbulence;
+    float q_min_threshold;      /* Q_MIN_THRESHOLD (config_loader.jl:184) */
+    int32_t wall_model_active;
+    int32_t use_temporal;       /* TEMPORAL_INTERPOLATION */
+    int32_t sponge_blend;       /* SPONGE_BLEND_DISTRIBUTIONS */
+    int32_t symmetric;          /* SYMMETRIC_ANALYSIS */
+    int32_t domain_nx;          /* level-1 cell counts (main.jl:93) */
+    int32_t domain_ny;
+    int32_t domain_nz;
+    int32_t strict_fp;          /* 1: mirror the reference's FP32 operation order without FMA
+                                   contraction (parity build); 0: fast path (FMA, regrouped sums) */
+} ludwig_params;
+
+/* which-codes for ludwig_level_upload / ludwig_level_download: the BlockLevel field
+ * (blocks.jl:28-47) to move, always in the reference layout. */
+enum {
+    LUDWIG_F = 0,         /* Float32[8,8,8,nb,27] */
+    LUDWIG_F_TEMP = 1,
+    LUDWIG_F_POST = 2,    /* only if n_boundary_cells > 0 */
+    LUDWIG_F_OLD = 3,     /* only if temporal_storage */
+    LUDWIG_RHO = 4,       /* Float32[8,8,8,nb] */
+    LUDWIG_RHO_OLD = 5,
+    LUDWIG_VEL = 6,       /* Float32[8,8,8,nb,3] */
+    LUDWIG_VEL_TEMP = 7,
+    LUDWIG_VEL_OLD = 8,
+    LUDWIG_OBSTACLE = 9   /* uint8[8,8,8,nb] */
+};
+
+/* -- context ------------------------------------------------------------------- */
+
+/* main.jl:75 backend selection.  `device` is the CUDA ordinal. */
+int ludwig_ctx_create(ludwig_ctx** out, int device);
+/* main.jl:247-248 (grids = nothing; force_cleanup()) */
+int ludwig_ctx_destroy(ludwig_ctx* ctx);
+const char* ludwig_last_error(const ludwig_ctx* ctx);
+/* "cuda-sm100a" for the product library, "cpu-oracle" for the test oracle. */
+const char* ludwig_backend_name(void);
+/* main.jl:164, solver_control.jl:164, physics_v2.jl:85,95  KernelAbstractions.synchronize */
+int ludwig_sync(ludwig_ctx* ctx);
+
+/* -- data upload ---------------------------------------------------------------- */
+
+/* main.jl:98  grids = [adapt(backend, g) for g in cpu_grids]   (blocks.jl:67-87).
+ * Levels must be added in order 1..L; returns the 0-based level index in *out_index.
+ * Allocates f/f_temp/rho/vel/vel_temp (+ old/post storage as the reference's
+ * constructor does, blocks.jl:118-147) with the constructor's initial values. */
+int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* desc, int32_t* out_index);
+int ludwig_num_levels(const ludwig_ctx* ctx);
+
+/* adapt() also moves the state arrays; these two move a single field of a level.
+ * io_vtk.jl:55-57 / forces/io.jl:28-31 `Array(level.rho)` etc. are the download side. */
+int ludwig_level_upload(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src);
+int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst);
+
+/* main.jl:101  Geometry.upload_mesh_to_gpu (geometry.jl:60-84): Float32 SoA. */
+int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n_triangles,
+                       const float* cx, const float* cy, const float* cz,
+                       const float* nx, const float* ny, const float* nz,
+                       const float* area, ludwig_mesh** out);
+int ludwig_mesh_destroy(ludwig_mesh* mesh);
+
+/* main.jl:145  ForceData(n_triangles, backend; ...)  (forces/structs.jl:94-119) */
+int ludwig_forces_create(ludwig_ctx* ctx, const ludwig_mesh* mesh,
+                         double rho_ref, double u_ref, double area_ref, double chord_ref,
+                         const double moment_center[3], int32_t symmetric, ludwig_forces** out);
+int ludwig_forces_destroy(ludwig_forces* forces);
+
+/* -- time stepping ---------------------------------------------------------------- */
+
+/* main.jl:109-135  init_eq! on every level. */
+int ludwig_init_equilibrium(ludwig_ctx* ctx);
+
+/* solver_control.jl:145-165  execute_timestep_batch!: `batch_size` coarse steps
+ * t_start .. t_start+batch_size-1 with the whole recursive 2:1 sub-cycling
+ * (recursive_step!, solver_control.jl:21-143) scheduled by the library.  Returns
+ * without a host sync. */
+int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, float u_curr,
+                      const ludwig_params* params);
+
+/* Fine-grained entry points for a driver that keeps solver_control.jl verbatim.
+ * ludwig_level_step = one perform_timestep_v2! (physics_v2.jl:26-97): K1 (+K2) on
+ * `level` with buffer parity derived from t_sub exactly as solver_control.jl:35-41.
+ * The parent is level-1 (ignored for level 0); its "new" buffers are the ones its
+ * own last step (parity parent_t_sub) wrote, its "old" state the pre-step state
+ * (solver_control.jl:65-72). */
+int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t parent_t_sub,
+                      float temporal_weight, float u_curr, const ludwig_params* params);
+/* blocks.jl:199-205 copy_to_old!(level, f_in, vel_in), f_in chosen by parity of t_sub. */
+int ludwig_level_snapshot_old(ludwig_ctx* ctx, int32_t level, int64_t t_sub);
+
+/* -- diagnostics / forces ---------------------------------------------------------- */
+
+/* main.jl:197,223  compute_aerodynamics! (forces/surface.jl:592-601): K3 + K4 + the
+ * host math of integrate_surface_forces! (:467-572).
+ * out[18] = Fx,Fy,Fz, Mx,My,Mz, Fx_p,Fy_p,Fz_p, Fx_v,Fy_v,Fz_v, Cd,Cl,Cs, Cmx,Cmy,Cmz */
+int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* forces, int32_t level,
+                                const double mesh_offset[3], double velocity_scale,
+                                double rho_phys, int32_t search_radius, double out[18]);
+/* forces/io.jl:28-31  Array(force_data.pressure_map) etc.  Each dst is Float32[n_triangles]. */
+int ludwig_forces_download_maps(ludwig_ctx* ctx, const ludwig_forces* forces,
+                                float* p, float* sx, float* sy, float* sz);
+
+/* main.jl:186  compute_flow_stats(grids[1]) (diagnostics.jl:56-94).
+ * out[6] = n_fluid, rho_mean, rho_min, rho_max, v_max, kinetic_energy */
+int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]);
+
+/* Device-memory footprint of everything the context owns, in bytes
+ * (diagnostics_vram.jl:17 prints the reference's). */
+int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUDWIG_B200_H */

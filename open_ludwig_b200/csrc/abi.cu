@@ -1,0 +1,605 @@
+// abi.cu — the extern "C" entry points of libludwig_b200.so (include/ludwig_b200.h) and the host-side
+// schedule that replaces solver_control.jl:21-165 / physics_v2.jl:26-97.
+//
+// Differences from the reference's schedule that do NOT change results:
+//   * no host synchronisation between kernels (the reference blocks after every launch, physics_v2.jl:85,95);
+//   * no copy_to_old! (blocks.jl:199-205): after an A-B step the input buffers ARE the old state, so only the
+//     density is double-buffered on levels that have children (248 B/cell-update less traffic on parents);
+//   * no dense f_post_collision (K2 is two-phase, see k_misc.cu).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "ludwig_internal.h"
+
+using namespace ludwig;
+
+namespace {
+
+int fail(ludwig_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? LUDWIG_ENOMEM : LUDWIG_ECUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+// Every copy goes through the context's (non-blocking) stream: a plain cudaMemcpy on the legacy stream is
+// not ordered against kernels launched on ctx->stream.
+inline cudaError_t memcpy_sync(cudaStream_t s, void* dst, const void* src, size_t n, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, s);
+    return e == cudaSuccess ? cudaStreamSynchronize(s) : e;
+}
+
+template <typename T>
+cudaError_t dalloc(ludwig_ctx* ctx, T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e == cudaSuccess) ctx->bytes += (int64_t)(n * sizeof(T));
+    return e;
+}
+
+inline uint64_t spread3(uint32_t v) {   // 21 bits -> every third bit
+    uint64_t x = v & 0x1fffff;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
+
+void free_level(Level* L) {
+    if (!L) return;
+    void* ptrs[] = {L->d_ref2int, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_list_interior, L->d_list_boundary,
+                    L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
+                    L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old, L->d_bc_cell, L->d_bc_q, L->d_bc_tmp};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete L;
+}
+
+// Upload one reference-layout field [ncomp][nb_ref][512] into the internal layout [nb_int][ncomp][512],
+// one component at a time through a 2 KiB-per-block staging buffer.
+int upload_field(ludwig_ctx* ctx, Level& L, const float* h_src, float* d_dst, int ncomp) {
+    float* stage = nullptr;
+    size_t n = (size_t)L.nb * BS3;
+    CU(cudaMalloc((void**)&stage, n * 4));
+    for (int k = 0; k < ncomp; ++k) {
+        cudaError_t e = cudaMemcpyAsync(stage, h_src + n * k, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) { launch_ref_to_int(stage, d_dst, L.d_int2ref, L.nb, ncomp, k, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
+        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("upload_field: ") + cudaGetErrorString(e)); }
+    }
+    cudaFree(stage);
+    return LUDWIG_OK;
+}
+int download_field(ludwig_ctx* ctx, Level& L, const float* d_src, float* h_dst, int ncomp) {
+    float* stage = nullptr;
+    size_t n = (size_t)L.nb * BS3;
+    CU(cudaMalloc((void**)&stage, n * 4));
+    for (int k = 0; k < ncomp; ++k) {
+        launch_int_to_ref(d_src, stage, L.d_int2ref, L.nb, ncomp, k, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(h_dst + n * k, stage, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("download_field: ") + cudaGetErrorString(e)); }
+    }
+    cudaFree(stage);
+    return LUDWIG_OK;
+}
+
+int ensure_explicit_old(ludwig_ctx* ctx, Level& L) {
+    if (L.explicit_old) return LUDWIG_OK;
+    size_t nc = (size_t)L.nb * BS3;
+    CU(dalloc(ctx, &L.d_f_old, nc * Q));
+    CU(dalloc(ctx, &L.d_vel_old, nc * 3));
+    CU(dalloc(ctx, &L.d_rho_old, nc));
+    CU(cudaMemsetAsync(L.d_f_old, 0, nc * Q * 4, ctx->stream));
+    CU(cudaMemsetAsync(L.d_vel_old, 0, nc * 3 * 4, ctx->stream));
+    launch_fill(L.d_rho_old, 1.0f, nc, ctx->stream);
+    L.explicit_old = true;
+    return LUDWIG_OK;
+}
+
+struct ParentView {
+    const Level* P = nullptr;
+    const float *f_new = nullptr, *f_old = nullptr, *rho_new = nullptr, *rho_old = nullptr, *vel_new = nullptr, *vel_old = nullptr;
+};
+
+// The parent's buffers as recursive_step_temporal! receives them (solver_control.jl:65-72):
+// new = (f_out, level.rho, vel_out) of the parent's step `parent_t_sub`, old = its pre-step state.
+ParentView make_parent_view(const Level& P, int64_t parent_t_sub, bool explicit_old) {
+    ParentView v;
+    v.P = &P;
+    int in = (parent_t_sub % 2 == 0) ? 0 : 1, out = 1 - in;
+    v.f_new = P.d_f[out]; v.vel_new = P.d_vel[out]; v.rho_new = P.d_rho[P.rho_cur];
+    if (explicit_old && P.explicit_old) { v.f_old = P.d_f_old; v.vel_old = P.d_vel_old; v.rho_old = P.d_rho_old; }
+    else { v.f_old = P.d_f[in]; v.vel_old = P.d_vel[in]; v.rho_old = P.d_rho[1] ? P.d_rho[1 - P.rho_cur] : P.d_rho[P.rho_cur]; }
+    return v;
+}
+
+// perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2.
+int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p) {
+    const int in = (t_sub % 2 == 0) ? 0 : 1, out = 1 - in;   // solver_control.jl:35-41
+    int rho_out = L.rho_cur;
+    if (L.d_rho[1]) rho_out = 1 - L.rho_cur;   // keep the pre-step density for the children
+    K1Args a{};
+    a.f_in = L.d_f[in]; a.f_out = L.d_f[out];
+    a.vel_in = L.d_vel[in]; a.vel_out = L.d_vel[out];
+    a.rho_out = L.d_rho[rho_out];
+    a.obstacle = L.d_obstacle; a.sponge = L.d_sponge; a.wall_dist = L.d_wall_dist;
+    a.nbr = L.d_nbr; a.bcoord = L.d_bcoord;
+    if (pv) {
+        a.pf_new = pv->f_new; a.pf_old = pv->f_old; a.prho_new = pv->rho_new; a.prho_old = pv->rho_old;
+        a.pvel_new = pv->vel_new; a.pvel_old = pv->vel_old;
+        a.pptr = pv->P->d_ptr; a.pdimx = pv->P->dimx; a.pdimy = pv->P->dimy; a.pdimz = pv->P->dimz;
+        a.tau_parent = pv->P->tau; a.is_l1 = 0;
+    } else {
+        a.pdimx = a.pdimy = a.pdimz = 1; a.tau_parent = 0.5f; a.is_l1 = 1;
+    }
+    const int scale = 1 << (L.level_id - 1);   // physics_v2.jl:55-56
+    a.nxg = p.domain_nx * scale; a.nyg = p.domain_ny * scale; a.nzg = p.domain_nz * scale;
+    a.tau = L.tau; a.c_wale = p.c_wale; a.nu_bg = p.nu_sgs_bg; a.u_inlet = u_curr; a.inlet_turb = p.inlet_turbulence;
+    a.tw = tw; a.is_symmetric = p.symmetric; a.wm = p.wall_model_active;
+    a.seed = (int)(t_sub % 1000000);           // physics_v2.jl:76
+    a.use_temporal = p.use_temporal; a.sponge_blend = p.sponge_blend;
+
+    if (p.strict_fp) {
+        a.list = nullptr; a.n_list = L.nb;
+        launch_k1_generic_strict(a, ctx->stream);
+    } else {
+        a.list = L.d_list_interior; a.n_list = L.n_interior;
+        launch_k1_interior(a, ctx->stream);
+        a.list = L.d_list_boundary; a.n_list = L.n_boundary;
+        launch_k1_generic_fast(a, ctx->stream);
+    }
+    if (L.bouzidi && L.n_bc > 0) launch_bouzidi(L, L.d_f[out], p.q_min_threshold, p.strict_fp != 0, ctx->stream);
+    L.rho_cur = rho_out;
+    L.last_t_sub = t_sub;
+    CU(cudaGetLastError());
+    return LUDWIG_OK;
+}
+
+// recursive_step! / recursive_step_temporal! (solver_control.jl:21-143)
+int recursive_step(ludwig_ctx* ctx, size_t lvl, int64_t t_sub, const ParentView* pv, float tw, float u, const ludwig_params& p) {
+    if (lvl >= ctx->levels.size()) return LUDWIG_OK;
+    Level& L = *ctx->levels[lvl];
+    int rc = step_level(ctx, L, pv, t_sub, tw, u, p);
+    if (rc) return rc;
+    if (lvl + 1 < ctx->levels.size()) {
+        ParentView me = make_parent_view(L, t_sub, /*explicit_old=*/false);
+        if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub, &me, 0.0f, u, p))) return rc;
+        if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p))) return rc;
+    }
+    return LUDWIG_OK;
+}
+
+bool level_ok(const ludwig_ctx* ctx, int32_t level) { return ctx && level >= 0 && level < (int)ctx->levels.size(); }
+
+}  // namespace
+
+extern "C" {
+
+const char* ludwig_backend_name(void) { return "cuda-sm100a"; }
+
+int ludwig_ctx_create(ludwig_ctx** out, int device) {
+    if (!out) return LUDWIG_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LUDWIG_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return LUDWIG_ECUDA;
+    auto* ctx = new ludwig_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
+    if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
+        delete ctx;
+        return LUDWIG_ENOMEM;
+    }
+    *out = ctx;
+    return LUDWIG_OK;
+}
+
+int ludwig_ctx_destroy(ludwig_ctx* ctx) {
+    if (!ctx) return LUDWIG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (Level* L : ctx->levels) free_level(L);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return LUDWIG_OK;
+}
+
+const char* ludwig_last_error(const ludwig_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int ludwig_num_levels(const ludwig_ctx* ctx) { return ctx ? (int)ctx->levels.size() : LUDWIG_EINVAL; }
+int64_t ludwig_device_bytes(const ludwig_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+int ludwig_sync(ludwig_ctx* ctx) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LUDWIG_OK;
+}
+
+int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* out_index) {
+    if (!ctx || !d) return LUDWIG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (d->level_id != (int)ctx->levels.size() + 1) return fail(ctx, LUDWIG_ESTATE, "levels must be created in order 1..L");
+    if (d->n_blocks <= 0) return fail(ctx, LUDWIG_EINVAL, "n_blocks must be > 0");
+    if (d->dim_x <= 0 || d->dim_y <= 0 || d->dim_z <= 0) return fail(ctx, LUDWIG_EINVAL, "block_pointer extents must be > 0");
+    if (!d->block_pointer || !d->neighbor_table || !d->map_x || !d->map_y || !d->map_z || !d->obstacle || !d->sponge || !d->wall_dist)
+        return fail(ctx, LUDWIG_EINVAL, "null table pointer");
+    const int nb = d->n_blocks;
+    const size_t nc = (size_t)nb * BS3;
+
+    Level* Lp = new Level();
+    Level& L = *Lp;
+    struct Guard { Level* p; ~Guard() { if (p) free_level(p); } } guard{Lp};
+    L.level_id = d->level_id; L.nb = nb; L.dimx = d->dim_x; L.dimy = d->dim_y; L.dimz = d->dim_z;
+    L.tau = d->tau; L.dx = d->dx; L.temporal = d->temporal_storage != 0;
+
+    // --- permutation: Morton order of the block coordinates
+    std::vector<uint64_t> key(nb);
+    for (int i = 0; i < nb; ++i) {
+        int bx = d->map_x[i], by = d->map_y[i], bz = d->map_z[i];
+        if (bx < 1 || by < 1 || bz < 1 || bx > d->dim_x || by > d->dim_y || bz > d->dim_z)
+            return fail(ctx, LUDWIG_EINVAL, "block coordinate outside block_pointer extents");
+        key[i] = morton3((uint32_t)(bx - 1), (uint32_t)(by - 1), (uint32_t)(bz - 1));
+    }
+    L.int2ref.resize(nb);
+    std::iota(L.int2ref.begin(), L.int2ref.end(), 0);
+    std::sort(L.int2ref.begin(), L.int2ref.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    L.ref2int.resize(nb);
+    for (int i = 0; i < nb; ++i) L.ref2int[L.int2ref[i]] = i;
+
+    // --- topology tables in internal numbering
+    std::vector<int32_t> nbr((size_t)nb * 27), bcoord((size_t)nb * 4);
+    for (int bi = 0; bi < nb; ++bi) {
+        int br = L.int2ref[bi];
+        for (int dir = 0; dir < 27; ++dir) {
+            int32_t v = d->neighbor_table[br + (size_t)nb * dir];
+            if (v < 0 || v > nb) return fail(ctx, LUDWIG_EINVAL, "neighbor_table entry out of range");
+            nbr[(size_t)bi * 27 + dir] = v > 0 ? L.ref2int[v - 1] : -1;
+        }
+        bcoord[(size_t)bi * 4 + 0] = d->map_x[br] - 1;
+        bcoord[(size_t)bi * 4 + 1] = d->map_y[br] - 1;
+        bcoord[(size_t)bi * 4 + 2] = d->map_z[br] - 1;
+        bcoord[(size_t)bi * 4 + 3] = 0;
+    }
+    size_t nptr = (size_t)d->dim_x * d->dim_y * d->dim_z;
+    std::vector<int32_t> ptr(nptr);
+    for (size_t i = 0; i < nptr; ++i) {
+        int32_t v = d->block_pointer[i];
+        if (v < 0 || v > nb) return fail(ctx, LUDWIG_EINVAL, "block_pointer entry out of range");
+        ptr[i] = v > 0 ? L.ref2int[v - 1] : -1;
+    }
+    CU(dalloc(ctx, &L.d_ref2int, (size_t)nb)); CU(dalloc(ctx, &L.d_int2ref, (size_t)nb));
+    CU(dalloc(ctx, &L.d_nbr, (size_t)nb * 27)); CU(dalloc(ctx, &L.d_bcoord, (size_t)nb * 4)); CU(dalloc(ctx, &L.d_ptr, nptr));
+    CU(memcpy_sync(ctx->stream, L.d_ref2int, L.ref2int.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+    CU(memcpy_sync(ctx->stream, L.d_int2ref, L.int2ref.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+    CU(memcpy_sync(ctx->stream, L.d_nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
+    CU(memcpy_sync(ctx->stream, L.d_bcoord, bcoord.data(), bcoord.size() * 4, cudaMemcpyHostToDevice));
+    CU(memcpy_sync(ctx->stream, L.d_ptr, ptr.data(), nptr * 4, cudaMemcpyHostToDevice));
+
+    // --- static fields
+    CU(dalloc(ctx, &L.d_obstacle, nc)); CU(dalloc(ctx, &L.d_sponge, nc)); CU(dalloc(ctx, &L.d_wall_dist, nc));
+    {
+        uint8_t* stage = nullptr;
+        CU(cudaMalloc((void**)&stage, nc));
+        cudaError_t e = memcpy_sync(ctx->stream, stage, d->obstacle, nc, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { launch_ref_to_int_u8(stage, L.d_obstacle, L.d_int2ref, nb, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, std::string("obstacle upload: ") + cudaGetErrorString(e));
+    }
+    int rc;
+    if ((rc = upload_field(ctx, L, d->sponge, L.d_sponge, 1))) return rc;
+    if ((rc = upload_field(ctx, L, d->wall_dist, L.d_wall_dist, 1))) return rc;
+
+    // --- state, with the constructor's initial values (blocks.jl:118-147): rho = 1, vel = 0, f = 0
+    for (int i = 0; i < 2; ++i) {
+        CU(dalloc(ctx, &L.d_f[i], nc * Q)); CU(dalloc(ctx, &L.d_vel[i], nc * 3));
+        CU(cudaMemsetAsync(L.d_f[i], 0, nc * Q * 4, ctx->stream));
+        CU(cudaMemsetAsync(L.d_vel[i], 0, nc * 3 * 4, ctx->stream));
+    }
+    CU(dalloc(ctx, &L.d_rho[0], nc));
+    launch_fill(L.d_rho[0], 1.0f, nc, ctx->stream);
+
+    // --- Bouzidi: compact the dense FP16 q_map rows of the boundary cells
+    L.bouzidi = d->bouzidi_enabled != 0 && d->n_boundary_cells > 0 && d->q_map_f16 != nullptr;
+    L.n_bc = L.bouzidi ? d->n_boundary_cells : 0;
+    if (L.n_bc > 0) {
+        if (!d->cell_block || !d->cell_x || !d->cell_y || !d->cell_z) return fail(ctx, LUDWIG_EINVAL, "null boundary-cell list");
+        std::vector<int32_t> cells(L.n_bc);
+        std::vector<uint16_t> q((size_t)L.n_bc * 27);
+        for (int i = 0; i < L.n_bc; ++i) {
+            int br = d->cell_block[i] - 1, x = d->cell_x[i] - 1, y = d->cell_y[i] - 1, z = d->cell_z[i] - 1;
+            if (br < 0 || br >= nb || x < 0 || x > 7 || y < 0 || y > 7 || z < 0 || z > 7)
+                return fail(ctx, LUDWIG_EINVAL, "boundary cell out of range");
+            int loc = x + 8 * y + 64 * z;
+            cells[i] = L.ref2int[br] * BS3 + loc;
+            for (int k = 0; k < 27; ++k) q[(size_t)i * 27 + k] = d->q_map_f16[(size_t)br * BS3 + loc + nc * k];
+        }
+        CU(dalloc(ctx, &L.d_bc_cell, (size_t)L.n_bc)); CU(dalloc(ctx, &L.d_bc_q, (size_t)L.n_bc * 27)); CU(dalloc(ctx, &L.d_bc_tmp, (size_t)L.n_bc * 27));
+        CU(memcpy_sync(ctx->stream, L.d_bc_cell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
+        CU(memcpy_sync(ctx->stream, L.d_bc_q, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
+    }
+
+    // --- per-block flags and the interior / boundary work lists
+    launch_block_flags(L, ctx->stream);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(memcpy_sync(ctx->stream, bcoord.data(), L.d_bcoord, bcoord.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> li, lb;
+    for (int bi = 0; bi < nb; ++bi) ((bcoord[(size_t)bi * 4 + 3] & BF_INTERIOR) ? li : lb).push_back(bi);
+    L.n_interior = (int)li.size(); L.n_boundary = (int)lb.size();
+    CU(dalloc(ctx, &L.d_list_interior, li.size())); CU(dalloc(ctx, &L.d_list_boundary, lb.size()));
+    if (!li.empty()) CU(memcpy_sync(ctx->stream, L.d_list_interior, li.data(), li.size() * 4, cudaMemcpyHostToDevice));
+    if (!lb.empty()) CU(memcpy_sync(ctx->stream, L.d_list_boundary, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice));
+
+    // --- the previous level now has children: double-buffer its density (implicit rho_old)
+    if (!ctx->levels.empty()) {
+        Level& P = *ctx->levels.back();
+        P.has_children = true;
+        if (!P.d_rho[1]) {
+            size_t pnc = (size_t)P.nb * BS3;
+            CU(dalloc(ctx, &P.d_rho[1], pnc));
+            launch_fill(P.d_rho[1], 1.0f, pnc, ctx->stream);
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    guard.p = nullptr;
+    ctx->levels.push_back(Lp);
+    if (out_index) *out_index = (int32_t)ctx->levels.size() - 1;
+    return LUDWIG_OK;
+}
+
+static int resolve_field(ludwig_ctx* ctx, Level& L, int which, bool for_upload, float** p, int* ncomp) {
+    const int in = L.last_t_sub >= 0 ? ((L.last_t_sub % 2 == 0) ? 0 : 1) : 0;
+    *p = nullptr;
+    switch (which) {
+        case LUDWIG_F: *p = L.d_f[0]; *ncomp = Q; break;
+        case LUDWIG_F_TEMP: *p = L.d_f[1]; *ncomp = Q; break;
+        case LUDWIG_VEL: *p = L.d_vel[0]; *ncomp = 3; break;
+        case LUDWIG_VEL_TEMP: *p = L.d_vel[1]; *ncomp = 3; break;
+        case LUDWIG_RHO: *p = L.d_rho[L.rho_cur]; *ncomp = 1; break;
+        case LUDWIG_F_OLD: case LUDWIG_VEL_OLD: case LUDWIG_RHO_OLD: {
+            if (!L.temporal) return fail(ctx, LUDWIG_EINVAL, "level has no temporal storage");
+            if (for_upload) { int rc = ensure_explicit_old(ctx, L); if (rc) return rc; }
+            *ncomp = which == LUDWIG_F_OLD ? Q : which == LUDWIG_VEL_OLD ? 3 : 1;
+            if (L.explicit_old) *p = which == LUDWIG_F_OLD ? L.d_f_old : which == LUDWIG_VEL_OLD ? L.d_vel_old : L.d_rho_old;
+            else if (L.last_t_sub < 0) return fail(ctx, LUDWIG_ESTATE, "old state not materialised before the first step");
+            else *p = which == LUDWIG_F_OLD ? L.d_f[in] : which == LUDWIG_VEL_OLD ? L.d_vel[in] : (L.d_rho[1] ? L.d_rho[1 - L.rho_cur] : nullptr);
+            break;
+        }
+        case LUDWIG_F_POST:
+            return fail(ctx, LUDWIG_EINVAL, "f_post_collision is not materialised by this library (two-phase Bouzidi kernel)");
+        default: return fail(ctx, LUDWIG_EINVAL, "unknown field code");
+    }
+    if (!*p) return fail(ctx, LUDWIG_EINVAL, "field not allocated on this level");
+    return LUDWIG_OK;
+}
+
+int ludwig_level_upload(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src) {
+    if (!level_ok(ctx, level) || !src) return fail(ctx, LUDWIG_EINVAL, "bad level/src");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    if (which == LUDWIG_OBSTACLE) {
+        uint8_t* stage = nullptr;
+        size_t nc = (size_t)L.nb * BS3;
+        CU(cudaMalloc((void**)&stage, nc));
+        cudaError_t e = memcpy_sync(ctx->stream, stage, src, nc, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { launch_ref_to_int_u8(stage, L.d_obstacle, L.d_int2ref, L.nb, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, cudaGetErrorString(e));
+        return LUDWIG_OK;
+    }
+    float* p; int ncomp;
+    int rc = resolve_field(ctx, L, which, true, &p, &ncomp);
+    if (rc) return rc;
+    return upload_field(ctx, L, (const float*)src, p, ncomp);
+}
+
+int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst) {
+    if (!level_ok(ctx, level) || !dst) return fail(ctx, LUDWIG_EINVAL, "bad level/dst");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    if (which == LUDWIG_OBSTACLE) {
+        uint8_t* stage = nullptr;
+        size_t nc = (size_t)L.nb * BS3;
+        CU(cudaMalloc((void**)&stage, nc));
+        launch_int_to_ref_u8(L.d_obstacle, stage, L.d_int2ref, L.nb, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = memcpy_sync(ctx->stream, dst, stage, nc, cudaMemcpyDeviceToHost);
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, cudaGetErrorString(e));
+        return LUDWIG_OK;
+    }
+    float* p; int ncomp;
+    int rc = resolve_field(ctx, L, which, false, &p, &ncomp);
+    if (rc) return rc;
+    return download_field(ctx, L, p, (float*)dst, ncomp);
+}
+
+int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n, const float* cx, const float* cy, const float* cz, const float* nx, const float* ny,
+                       const float* nz, const float* area, ludwig_mesh** out) {
+    if (!ctx || n <= 0 || !out || !cx || !cy || !cz || !nx || !ny || !nz || !area) return fail(ctx, LUDWIG_EINVAL, "bad mesh args");
+    CU(cudaSetDevice(ctx->device));
+    auto* m = new ludwig_mesh();
+    m->n = n;
+    float** dst[7] = {&m->cx, &m->cy, &m->cz, &m->nx, &m->ny, &m->nz, &m->area};
+    const float* src[7] = {cx, cy, cz, nx, ny, nz, area};
+    for (int i = 0; i < 7; ++i) {
+        cudaError_t e = dalloc(ctx, dst[i], (size_t)n);
+        if (e == cudaSuccess) e = memcpy_sync(ctx->stream, *dst[i], src[i], (size_t)n * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ludwig_mesh_destroy(m); return fail(ctx, LUDWIG_ECUDA, cudaGetErrorString(e)); }
+    }
+    *out = m;
+    return LUDWIG_OK;
+}
+int ludwig_mesh_destroy(ludwig_mesh* m) {
+    if (!m) return LUDWIG_OK;
+    float* p[7] = {m->cx, m->cy, m->cz, m->nx, m->ny, m->nz, m->area};
+    for (float* q : p) if (q) cudaFree(q);
+    delete m;
+    return LUDWIG_OK;
+}
+
+int ludwig_forces_create(ludwig_ctx* ctx, const ludwig_mesh* mesh, double rho_ref, double u_ref, double area_ref, double chord_ref,
+                         const double mc[3], int32_t symmetric, ludwig_forces** out) {
+    if (!ctx || !mesh || !out || !mc) return fail(ctx, LUDWIG_EINVAL, "bad forces args");
+    CU(cudaSetDevice(ctx->device));
+    auto* f = new ludwig_forces();
+    f->mesh = mesh; f->rho_ref = rho_ref; f->u_ref = u_ref; f->area_ref = area_ref; f->chord_ref = chord_ref;
+    f->mc[0] = mc[0]; f->mc[1] = mc[1]; f->mc[2] = mc[2]; f->symmetric = symmetric;
+    float** dst[4] = {&f->p, &f->sx, &f->sy, &f->sz};
+    for (auto d : dst) {
+        cudaError_t e = dalloc(ctx, d, (size_t)mesh->n);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*d, 0, (size_t)mesh->n * 4, ctx->stream);
+        if (e != cudaSuccess) { ludwig_forces_destroy(f); return fail(ctx, LUDWIG_ECUDA, cudaGetErrorString(e)); }
+    }
+    if (cudaMalloc((void**)&f->d_acc, 9 * sizeof(double)) != cudaSuccess || cudaMallocHost((void**)&f->h_acc, 9 * sizeof(double)) != cudaSuccess) {
+        ludwig_forces_destroy(f);
+        return fail(ctx, LUDWIG_ENOMEM, "forces accumulators");
+    }
+    *out = f;
+    return LUDWIG_OK;
+}
+int ludwig_forces_destroy(ludwig_forces* f) {
+    if (!f) return LUDWIG_OK;
+    float* p[4] = {f->p, f->sx, f->sy, f->sz};
+    for (float* q : p) if (q) cudaFree(q);
+    if (f->d_acc) cudaFree(f->d_acc);
+    if (f->h_acc) cudaFreeHost(f->h_acc);
+    delete f;
+    return LUDWIG_OK;
+}
+
+// main.jl:109-135
+int ludwig_init_equilibrium(ludwig_ctx* ctx) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    for (Level* Lp : ctx->levels) {
+        Level& L = *Lp;
+        launch_init_eq(L.d_f[0], L.d_f[1], L.explicit_old ? L.d_f_old : nullptr, L.nb, ctx->stream);
+        if (L.explicit_old) {
+            launch_fill(L.d_rho_old, 1.0f, (size_t)L.nb * BS3, ctx->stream);
+            CU(cudaMemsetAsync(L.d_vel_old, 0, (size_t)L.nb * BS3 * 3 * 4, ctx->stream));
+        }
+    }
+    CU(cudaGetLastError());
+    return LUDWIG_OK;
+}
+
+// solver_control.jl:145-165
+int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params) {
+    if (!ctx || !params || ctx->levels.empty() || batch_size < 0) return fail(ctx, LUDWIG_EINVAL, "bad step args");
+    CU(cudaSetDevice(ctx->device));
+    for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
+        int rc = recursive_step(ctx, 0, t_start + t_offset, nullptr, 0.0f, u_curr, *params);
+        if (rc) return rc;
+    }
+    return LUDWIG_OK;
+}
+
+int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t parent_t_sub, float temporal_weight, float u_curr,
+                      const ludwig_params* params) {
+    if (!level_ok(ctx, level) || !params) return fail(ctx, LUDWIG_EINVAL, "bad level");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    if (level == 0) return step_level(ctx, L, nullptr, t_sub, temporal_weight, u_curr, *params);
+    Level& P = *ctx->levels[level - 1];
+    if (params->use_temporal && !P.temporal) return fail(ctx, LUDWIG_ESTATE, "parent has no temporal storage");
+    ParentView pv = make_parent_view(P, parent_t_sub, /*explicit_old=*/true);
+    return step_level(ctx, L, &pv, t_sub, temporal_weight, u_curr, *params);
+}
+
+// blocks.jl:199-205.  Only the fine-grained API needs real copies; ludwig_step_batch never calls this.
+int ludwig_level_snapshot_old(ludwig_ctx* ctx, int32_t level, int64_t t_sub) {
+    if (!level_ok(ctx, level)) return fail(ctx, LUDWIG_EINVAL, "bad level");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    if (!L.temporal) return LUDWIG_OK;   // length(level.f_old) <= 27: the reference's copy_to_old! is a no-op
+    int rc = ensure_explicit_old(ctx, L);
+    if (rc) return rc;
+    const int in = (t_sub % 2 == 0) ? 0 : 1;
+    size_t nc = (size_t)L.nb * BS3;
+    CU(cudaMemcpyAsync(L.d_f_old, L.d_f[in], nc * Q * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(L.d_rho_old, L.d_rho[L.rho_cur], nc * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(L.d_vel_old, L.d_vel[in], nc * 3 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LUDWIG_OK;
+}
+
+// forces/surface.jl:389-601
+int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* F, int32_t level, const double mesh_offset[3], double velocity_scale,
+                                double rho_phys, int32_t search_radius, double out[18]) {
+    if (!level_ok(ctx, level) || !F || !mesh_offset || !out) return fail(ctx, LUDWIG_EINVAL, "bad aero args");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    const ludwig_mesh& M = *F->mesh;
+    const float pscale = (float)(rho_phys * velocity_scale * velocity_scale);   // forces/surface.jl:402-403
+    const float offx = (float)mesh_offset[0], offy = (float)mesh_offset[1], offz = (float)mesh_offset[2];
+    // K3 reads level.rho and level.vel (NOT vel_temp) whatever the parity — forces/surface.jl:412
+    launch_map_stresses(L, L.d_rho[L.rho_cur], L.d_vel[0], M, *F, (float)L.dx, offx, offy, offz, pscale, pscale, search_radius, ctx->stream);
+    launch_integrate_forces(M, *F, offx, offy, offz, ctx->stream);
+    CU(cudaMemcpyAsync(F->h_acc, F->d_acc, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // FP64 sums of the FP32 per-triangle contributions (the reference's FP32 atomics lose ~1e-4 here)
+    double Fx_p = F->h_acc[0], Fy_p = F->h_acc[1], Fz_p = F->h_acc[2];
+    double Fx_v = F->h_acc[3], Fy_v = F->h_acc[4], Fz_v = F->h_acc[5];
+    double Mx = F->h_acc[6], My = F->h_acc[7], Mz = F->h_acc[8];
+    if (F->symmetric) {
+        Fx_p *= 2.0; Fz_p *= 2.0; Fx_v *= 2.0; Fz_v *= 2.0; My *= 2.0;
+        Fy_p = 0.0; Fy_v = 0.0; Mx = 0.0; Mz = 0.0;
+    }
+    double Fx = Fx_p + Fx_v, Fy = Fy_p + Fy_v, Fz = Fz_p + Fz_v;
+    double q_inf = 0.5 * F->rho_ref * F->u_ref * F->u_ref;
+    double F_ref = q_inf * F->area_ref, M_ref = F_ref * F->chord_ref;
+    double Cd = 0, Cl = 0, Cs = 0, Cmx = 0, Cmy = 0, Cmz = 0;
+    if (F_ref > 1e-10) { Cd = Fx / F_ref; Cl = Fz / F_ref; Cs = Fy / F_ref; }
+    if (M_ref > 1e-10) { Cmx = Mx / M_ref; Cmy = My / M_ref; Cmz = Mz / M_ref; }
+    double r[18] = {Fx, Fy, Fz, Mx, My, Mz, Fx_p, Fy_p, Fz_p, Fx_v, Fy_v, Fz_v, Cd, Cl, Cs, Cmx, Cmy, Cmz};
+    std::memcpy(out, r, sizeof(r));
+    return LUDWIG_OK;
+}
+
+int ludwig_forces_download_maps(ludwig_ctx* ctx, const ludwig_forces* F, float* p, float* sx, float* sy, float* sz) {
+    if (!ctx || !F) return fail(ctx, LUDWIG_EINVAL, "bad forces handle");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    size_t n = (size_t)F->mesh->n * 4;
+    if (p) CU(memcpy_sync(ctx->stream, p, F->p, n, cudaMemcpyDeviceToHost));
+    if (sx) CU(memcpy_sync(ctx->stream, sx, F->sx, n, cudaMemcpyDeviceToHost));
+    if (sy) CU(memcpy_sync(ctx->stream, sy, F->sy, n, cudaMemcpyDeviceToHost));
+    if (sz) CU(memcpy_sync(ctx->stream, sz, F->sz, n, cudaMemcpyDeviceToHost));
+    return LUDWIG_OK;
+}
+
+// diagnostics.jl:56-94
+int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
+    if (!level_ok(ctx, level) || !out) return fail(ctx, LUDWIG_EINVAL, "bad stats args");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    int nparts = std::min(4096, std::max(1, std::min(ctx->num_sms * 8, (L.nb * BS3 + 255) / 256)));
+    launch_flow_stats(L, L.d_rho[L.rho_cur], L.d_vel[0], ctx->d_stats, nparts, ctx->stream);
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, (size_t)nparts * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double n = 0, rs = 0, ke = 0, rmin = INFINITY, rmax = -INFINITY, vmax = 0;
+    for (int i = 0; i < nparts; ++i) {
+        const double* q = ctx->h_stats + (size_t)i * 6;
+        n += q[0]; rs += q[1]; ke += q[5];
+        rmin = std::min(rmin, q[2]); rmax = std::max(rmax, q[3]); vmax = std::max(vmax, q[4]);
+    }
+    if (n > 0) { out[0] = n; out[1] = rs / n; out[2] = rmin; out[3] = rmax; out[4] = vmax; out[5] = 0.5 * ke; }
+    else { out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 1; out[4] = 0; out[5] = 0; }
+    return LUDWIG_OK;
+}
+
+}  // extern "C"

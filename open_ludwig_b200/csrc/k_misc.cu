@@ -1,0 +1,341 @@
+// k_misc.cu — the small kernels around K1:
+//   K0  init_eq!                          main.jl:109-124
+//   K2  bouzidi_correction_kernel_fixed!  bouzidi_kernel.jl:13-92   (two-phase, no dense f_post_collision)
+//   K3  map_stresses_kernel!              forces/surface.jl:138-266
+//   K4  integrate_forces_kernel!          forces/surface.jl:282-366 (deterministic FP64 tree, no atomics)
+//   R1  compute_flow_stats                diagnostics.jl:56-94      (one fused masked min/max/sum pass)
+//   layout conversion reference <-> internal (the device side of adapt(), main.jl:98)
+#include "ludwig_internal.h"
+
+#include <cuda_fp16.h>
+
+namespace ludwig {
+
+// ---------------------------------------------------------------------------------------------
+// K0
+__global__ void init_eq_kernel(float* __restrict__ f0, float* __restrict__ f1, float* __restrict__ f_old, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per float4 of a (b,k) row
+    if (i >= n) return;
+    int k = (int)((i / (BS3 / 4)) % Q);
+    int cx = k % 3 - 1, cy = (k / 3) % 3 - 1, cz = k / 9 - 1;
+    int d2 = cx * cx + cy * cy + cz * cz;
+    float w = d2 == 0 ? 8.0f / 27.0f : d2 == 1 ? 2.0f / 27.0f : d2 == 2 ? 1.0f / 54.0f : 1.0f / 216.0f;
+    float4 v = make_float4(w, w, w, w);
+    reinterpret_cast<float4*>(f0)[i] = v;
+    reinterpret_cast<float4*>(f1)[i] = v;
+    if (f_old) reinterpret_cast<float4*>(f_old)[i] = v;
+}
+void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s) {
+    size_t n = (size_t)nb * Q * BS3 / 4;
+    init_eq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f0, f1, f_old, n);
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+void launch_fill(float* p, float v, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    fill_kernel<<<grid, 256, 0, s>>>(p, v, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion.  Reference: field[x,y,z,b_ref,k] (direction-major); internal: field[b_int][k][512].
+// One (b,k) row = 512 floats = 128 float4; one thread per float4.
+__global__ void ref_to_int_kernel(const float4* __restrict__ src_k, float4* __restrict__ dst, const int32_t* __restrict__ int2ref,
+                                  int nb, int ncomp, int k) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nb * 128) return;
+    int b = (int)(i >> 7), q = (int)(i & 127);
+    dst[((size_t)b * ncomp + k) * 128 + q] = src_k[(size_t)int2ref[b] * 128 + q];
+}
+__global__ void int_to_ref_kernel(const float4* __restrict__ src, float4* __restrict__ dst_k, const int32_t* __restrict__ int2ref,
+                                  int nb, int ncomp, int k) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nb * 128) return;
+    int b = (int)(i >> 7), q = (int)(i & 127);
+    dst_k[(size_t)int2ref[b] * 128 + q] = src[((size_t)b * ncomp + k) * 128 + q];
+}
+void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s) {
+    size_t n = (size_t)nb * 128;
+    ref_to_int_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)src_ref_k, (float4*)dst, int2ref, nb, ncomp, k);
+}
+void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s) {
+    size_t n = (size_t)nb * 128;
+    int_to_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)src, (float4*)dst_ref_k, int2ref, nb, ncomp, k);
+}
+__global__ void ref_to_int_u8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int32_t* __restrict__ int2ref, int nb, int fwd) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 512 B per block = 32 uint4
+    if (i >= (size_t)nb * 32) return;
+    int b = (int)(i >> 5), q = (int)(i & 31);
+    if (fwd) dst[(size_t)b * 32 + q] = src[(size_t)int2ref[b] * 32 + q];
+    else dst[(size_t)int2ref[b] * 32 + q] = src[(size_t)b * 32 + q];
+}
+void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s) {
+    size_t n = (size_t)nb * 32;
+    ref_to_int_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint4*)src_ref, (uint4*)dst, int2ref, nb, 1);
+}
+void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s) {
+    size_t n = (size_t)nb * 32;
+    ref_to_int_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint4*)src, (uint4*)dst_ref, int2ref, nb, 0);
+}
+
+// per-block flag word: lets K1 skip the obstacle / sponge / wall_dist loads for blocks that have none
+__global__ void block_flags_kernel(const uint8_t* __restrict__ obstacle, const float* __restrict__ sponge,
+                                   const float* __restrict__ wall_dist, const int32_t* __restrict__ nbr, int32_t* __restrict__ bcoord, int nb) {
+    int b = blockIdx.x;
+    __shared__ unsigned s_flags;
+    if (threadIdx.x == 0) s_flags = 0;
+    __syncthreads();
+    unsigned fl = 0;
+    for (int c = threadIdx.x; c < BS3; c += blockDim.x) {
+        size_t i = (size_t)b * BS3 + c;
+        if (obstacle[i]) fl |= BF_OBSTACLE;
+        if (sponge[i] > 0.0f) fl |= BF_SPONGE;
+        float d = wall_dist[i];
+        if (d > 0.0f && d < 10.0f) fl |= BF_WALLDIST;
+    }
+    if (threadIdx.x < 27 && nbr[(size_t)b * 27 + threadIdx.x] < 0) fl |= 0x80000000u;   // some neighbour missing
+    if (fl) atomicOr(&s_flags, fl);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned f = s_flags;
+        unsigned out = f & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
+        if (!(f & 0x80000000u)) out |= BF_INTERIOR;
+        bcoord[(size_t)b * 4 + 3] = (int32_t)out;
+    }
+}
+void launch_block_flags(Level& L, cudaStream_t s) {
+    block_flags_kernel<<<L.nb, 128, 0, s>>>(L.d_obstacle, L.d_sponge, L.d_wall_dist, L.d_nbr, L.d_bcoord, L.nb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  Bouzidi.  The reference reads a dense post-collision copy f_post_collision (+108 B/cell written by
+// K1) and overwrites f_out in place.  Before K2 runs, f_post_collision == f_out bit for bit
+// (physics_kernels.jl:350-353), so here phase A gathers every correction from f_out into a compact
+// [n_bc][27] buffer and phase B scatters them — same values, no dense array, no read/write hazard.
+template <bool STRICT>
+__global__ void bouzidi_gather_kernel(const float* __restrict__ f_out, const int32_t* __restrict__ bc_cell,
+                                      const uint16_t* __restrict__ bc_q, const int32_t* __restrict__ nbr,
+                                      float* __restrict__ tmp, int n_bc, float q_min) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bc * 27) return;
+    int ci = i / 27, k = i - ci * 27;
+    float q = __half2float(__ushort_as_half(bc_q[i]));
+    float res = __int_as_float(0x7fc00000);   // NaN = "link inactive"
+    if (q > q_min && q <= 1.0f) {
+        int cell = bc_cell[ci];
+        int b = cell >> 9, c = cell & 511;
+        int x = c & 7, y = (c >> 3) & 7, z = c >> 6;
+        int opp_k = 26 - k;
+        const float* fb = f_out + (size_t)b * Q * BS3;
+        float f_k = fb[k * BS3 + c];
+        if (q < 0.5f) {
+            int cx = k % 3 - 1, cy = (k / 3) % 3 - 1, cz = k / 9 - 1;
+            int nx = x - cx, ny = y - cy, nz = z - cz;   // x + c_opp(k)
+            float f_ff = f_k;
+            if (((nx | ny | nz) & ~7) == 0) {
+                f_ff = fb[k * BS3 + nz * 64 + ny * 8 + nx];
+            } else {
+                int ox = nx < 0 ? -1 : (nx > 7 ? 1 : 0), oy = ny < 0 ? -1 : (ny > 7 ? 1 : 0), oz = nz < 0 ? -1 : (nz > 7 ? 1 : 0);
+                int nbi = nbr[(size_t)b * 27 + (ox + 1) + (oy + 1) * 3 + (oz + 1) * 9];
+                if (nbi >= 0) f_ff = f_out[((size_t)nbi * Q + k) * BS3 + (nz & 7) * 64 + (ny & 7) * 8 + (nx & 7)];
+            }
+            float coeff1 = 2.0f * q;
+            if (STRICT) res = __fadd_rn(__fmul_rn(coeff1, f_k), __fmul_rn(__fsub_rn(1.0f, coeff1), f_ff));
+            else res = coeff1 * f_k + (1.0f - coeff1) * f_ff;
+        } else {
+            float f_opp_post = fb[opp_k * BS3 + c];
+            float inv_2q = 1.0f / (2.0f * q);
+            float coeff2 = __fmul_rn(__fsub_rn(__fmul_rn(2.0f, q), 1.0f), inv_2q);
+            if (STRICT) res = __fadd_rn(__fmul_rn(inv_2q, f_k), __fmul_rn(coeff2, f_opp_post));
+            else res = inv_2q * f_k + coeff2 * f_opp_post;
+        }
+    }
+    tmp[i] = res;
+}
+__global__ void bouzidi_scatter_kernel(float* __restrict__ f_out, const int32_t* __restrict__ bc_cell, const float* __restrict__ tmp, int n_bc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bc * 27) return;
+    float v = tmp[i];
+    if (v != v) return;
+    int ci = i / 27, k = i - ci * 27;
+    int cell = bc_cell[ci];
+    f_out[((size_t)(cell >> 9) * Q + (26 - k)) * BS3 + (cell & 511)] = v;
+}
+void launch_bouzidi(const Level& L, float* f_out, float q_min, bool strict, cudaStream_t s) {
+    if (!L.bouzidi || L.n_bc == 0) return;
+    int n = L.n_bc * 27;
+    unsigned grid = (n + 255) / 256;
+    if (strict) bouzidi_gather_kernel<true><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, L.d_bc_tmp, L.n_bc, q_min);
+    else bouzidi_gather_kernel<false><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, L.d_bc_tmp, L.n_bc, q_min);
+    bouzidi_scatter_kernel<<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_tmp, L.n_bc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  nearest-fluid-cell search per triangle + pressure / shear (forces/surface.jl:32-124,138-266).
+// The arithmetic is written with explicit _rn intrinsics so that it matches the oracle without FMA.
+__global__ void map_stresses_kernel(const float* __restrict__ rho, const float* __restrict__ vel, const uint8_t* __restrict__ obstacle,
+                                    const int32_t* __restrict__ ptr, int dimx, int dimy, int dimz,
+                                    const float* __restrict__ tcx, const float* __restrict__ tcy, const float* __restrict__ tcz,
+                                    const float* __restrict__ tnx, const float* __restrict__ tny, const float* __restrict__ tnz,
+                                    float* __restrict__ p_map, float* __restrict__ sx_map, float* __restrict__ sy_map, float* __restrict__ sz_map,
+                                    int n_tri, float dx, float offx, float offy, float offz, float pscale, float sscale,
+                                    float tau_molecular, int search_radius) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tri) return;
+    float tx = __fadd_rn(tcx[i], offx), ty = __fadd_rn(tcy[i], offy), tz = __fadd_rn(tcz[i], offz);
+    float n_x = tnx[i], n_y = tny[i], n_z = tnz[i];
+    int g_x = (int)floorf(__fdiv_rn(tx, dx)) + 1, g_y = (int)floorf(__fdiv_rn(ty, dx)) + 1, g_z = (int)floorf(__fdiv_rn(tz, dx)) + 1;
+    float best_dist_sq = 1e10f, best_rho = 1.0f, best_ux = 0.f, best_uy = 0.f, best_uz = 0.f, best_wall_dist = 0.5f;
+    bool found = false;
+    for (int radius = 0; radius <= search_radius; ++radius) {
+        if (found && radius > 1) break;
+        for (int dz = -radius; dz <= radius; ++dz)
+            for (int dy = -radius; dy <= radius; ++dy)
+                for (int ddx = -radius; ddx <= radius; ++ddx) {
+                    if (radius > 0 && !(abs(ddx) == radius || abs(dy) == radius || abs(dz) == radius)) continue;
+                    int cgx = g_x + ddx, cgy = g_y + dy, cgz = g_z + dz;
+                    if (cgx < 1 || cgy < 1 || cgz < 1) continue;
+                    int bx = (cgx - 1) >> 3, by = (cgy - 1) >> 3, bz = (cgz - 1) >> 3;
+                    if (bx >= dimx || by >= dimy || bz >= dimz) continue;
+                    int bi = ptr[bx + dimx * (by + dimy * bz)];
+                    if (bi < 0) continue;
+                    int loc = ((cgx - 1) & 7) + 8 * ((cgy - 1) & 7) + 64 * ((cgz - 1) & 7);
+                    size_t c = (size_t)bi * BS3 + loc;
+                    if (obstacle[c]) continue;
+                    float ccx = __fmul_rn(__fsub_rn((float)cgx, 0.5f), dx), ccy = __fmul_rn(__fsub_rn((float)cgy, 0.5f), dx),
+                          ccz = __fmul_rn(__fsub_rn((float)cgz, 0.5f), dx);
+                    float ex = __fsub_rn(tx, ccx), ey = __fsub_rn(ty, ccy), ez = __fsub_rn(tz, ccz);
+                    float dist_sq = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+                    if (dist_sq < best_dist_sq) {
+                        best_dist_sq = dist_sq;
+                        best_rho = rho[c];
+                        size_t vi = (size_t)bi * 3 * BS3 + loc;
+                        best_ux = vel[vi]; best_uy = vel[vi + BS3]; best_uz = vel[vi + 2 * BS3];
+                        best_wall_dist = __fdiv_rn(__fsqrt_rn(dist_sq), dx);
+                        found = true;
+                    }
+                }
+    }
+    float p_val = 0.f, tau_x = 0.f, tau_y = 0.f, tau_z = 0.f;
+    if (found) {
+        float wall_dist = fmaxf(best_wall_dist, 0.5f);
+        float p_gauge_lat = __fdiv_rn(__fsub_rn(best_rho, 1.0f), 3.0f);
+        p_val = __fmul_rn(p_gauge_lat, pscale);
+        float u_dot_n = __fadd_rn(__fadd_rn(__fmul_rn(best_ux, n_x), __fmul_rn(best_uy, n_y)), __fmul_rn(best_uz, n_z));
+        float ut_x = __fsub_rn(best_ux, __fmul_rn(u_dot_n, n_x)), ut_y = __fsub_rn(best_uy, __fmul_rn(u_dot_n, n_y)),
+              ut_z = __fsub_rn(best_uz, __fmul_rn(u_dot_n, n_z));
+        float u_tan_mag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ut_x, ut_x), __fmul_rn(ut_y, ut_y)), __fmul_rn(ut_z, ut_z)));
+        float nu_lat = __fdiv_rn(__fsub_rn(tau_molecular, 0.5f), 3.0f);
+        if (u_tan_mag > 1.0e-10f && wall_dist > 0.01f) {
+            float tau_lat_mag = __fdiv_rn(__fmul_rn(__fmul_rn(best_rho, nu_lat), u_tan_mag), wall_dist);
+            float tau_phys_mag = __fmul_rn(tau_lat_mag, sscale);
+            tau_x = __fmul_rn(__fdiv_rn(ut_x, u_tan_mag), tau_phys_mag);
+            tau_y = __fmul_rn(__fdiv_rn(ut_y, u_tan_mag), tau_phys_mag);
+            tau_z = __fmul_rn(__fdiv_rn(ut_z, u_tan_mag), tau_phys_mag);
+        }
+    }
+    p_map[i] = p_val; sx_map[i] = tau_x; sy_map[i] = tau_y; sz_map[i] = tau_z;
+}
+void launch_map_stresses(const Level& L, const float* rho, const float* vel, const ludwig_mesh& M, ludwig_forces& F, float dx,
+                         float offx, float offy, float offz, float pscale, float sscale, int radius, cudaStream_t s) {
+    map_stresses_kernel<<<(M.n + 127) / 128, 128, 0, s>>>(rho, vel, L.d_obstacle, L.d_ptr, L.dimx, L.dimy, L.dimz, M.cx, M.cy, M.cz,
+                                                          M.nx, M.ny, M.nz, F.p, F.sx, F.sy, F.sz, M.n, dx, offx, offy, offz, pscale,
+                                                          sscale, L.tau, radius);
+}
+
+// K4.  Per-triangle contributions are formed in FP32 exactly as the reference does (forces/surface.jl:298-352)
+// and then summed in FP64 by a fixed-shape tree (warp shuffles + one CTA): deterministic, unlike the
+// reference's 9 same-address FP32 atomics per triangle.
+__global__ void __launch_bounds__(1024) integrate_forces_kernel(const float* __restrict__ p_map, const float* __restrict__ sx_map,
+                                                                const float* __restrict__ sy_map, const float* __restrict__ sz_map,
+                                                                const float* __restrict__ tcx, const float* __restrict__ tcy,
+                                                                const float* __restrict__ tcz, const float* __restrict__ tnx,
+                                                                const float* __restrict__ tny, const float* __restrict__ tnz,
+                                                                const float* __restrict__ areas, int n_tri, float offx, float offy,
+                                                                float offz, float refx, float refy, float refz, double* __restrict__ out) {
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n_tri; i += blockDim.x) {
+        float p = p_map[i], tau_x = sx_map[i], tau_y = sy_map[i], tau_z = sz_map[i];
+        float nx = tnx[i], ny = tny[i], nz = tnz[i], A = areas[i];
+        float cx = __fadd_rn(tcx[i], offx), cy = __fadd_rn(tcy[i], offy), cz = __fadd_rn(tcz[i], offz);
+        float dFp_x = __fmul_rn(__fmul_rn(-p, nx), A), dFp_y = __fmul_rn(__fmul_rn(-p, ny), A), dFp_z = __fmul_rn(__fmul_rn(-p, nz), A);
+        float dFv_x = __fmul_rn(tau_x, A), dFv_y = __fmul_rn(tau_y, A), dFv_z = __fmul_rn(tau_z, A);
+        float dFx = __fadd_rn(dFp_x, dFv_x), dFy = __fadd_rn(dFp_y, dFv_y), dFz = __fadd_rn(dFp_z, dFv_z);
+        float rx = __fsub_rn(cx, refx), ry = __fsub_rn(cy, refy), rz = __fsub_rn(cz, refz);
+        float dMx = __fsub_rn(__fmul_rn(ry, dFz), __fmul_rn(rz, dFy));
+        float dMy = __fsub_rn(__fmul_rn(rz, dFx), __fmul_rn(rx, dFz));
+        float dMz = __fsub_rn(__fmul_rn(rx, dFy), __fmul_rn(ry, dFx));
+        acc[0] += dFp_x; acc[1] += dFp_y; acc[2] += dFp_z;
+        acc[3] += dFv_x; acc[4] += dFv_y; acc[5] += dFv_z;
+        acc[6] += dMx; acc[7] += dMy; acc[8] += dMz;
+    }
+    __shared__ double s_part[32][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][j] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            double v = lane < (int)(blockDim.x >> 5) ? s_part[lane][j] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) out[j] = v;
+        }
+    }
+}
+void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, cudaStream_t s) {
+    integrate_forces_kernel<<<1, 1024, 0, s>>>(F.p, F.sx, F.sy, F.sz, M.cx, M.cy, M.cz, M.nx, M.ny, M.nz, M.area, M.n, offx, offy, offz,
+                                               (float)F.mc[0], (float)F.mc[1], (float)F.mc[2], F.d_acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// R1  flow statistics over the non-obstacle cells of one level: n, sum(rho), min, max, max|u|, sum(rho*u^2).
+// partial layout per CTA: [n, rho_sum, rho_min, rho_max, v_max, ke]
+__global__ void __launch_bounds__(256) flow_stats_kernel(const float* __restrict__ rho, const float* __restrict__ vel,
+                                                         const uint8_t* __restrict__ obstacle, size_t ncell, double* __restrict__ partials) {
+    double n = 0, rs = 0, ke = 0;
+    float rmin = INFINITY, rmax = -INFINITY, vmax = 0.f;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (size_t)gridDim.x * blockDim.x) {
+        if (obstacle[c]) continue;
+        size_t b = c >> 9, loc = c & 511;
+        size_t vi = b * 3 * BS3 + loc;
+        float r = rho[c], ux = vel[vi], uy = vel[vi + BS3], uz = vel[vi + 2 * BS3];
+        float v2 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz));
+        n += 1; rs += r; ke += (double)__fmul_rn(r, v2);
+        rmin = fminf(rmin, r); rmax = fmaxf(rmax, r); vmax = fmaxf(vmax, __fsqrt_rn(v2));
+    }
+    __shared__ double s_d[8][3];
+    __shared__ float s_f[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_down_sync(0xffffffffu, n, o); rs += __shfl_down_sync(0xffffffffu, rs, o); ke += __shfl_down_sync(0xffffffffu, ke, o);
+        rmin = fminf(rmin, __shfl_down_sync(0xffffffffu, rmin, o)); rmax = fmaxf(rmax, __shfl_down_sync(0xffffffffu, rmax, o));
+        vmax = fmaxf(vmax, __shfl_down_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) { s_d[warp][0] = n; s_d[warp][1] = rs; s_d[warp][2] = ke; s_f[warp][0] = rmin; s_f[warp][1] = rmax; s_f[warp][2] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            n += s_d[w][0]; rs += s_d[w][1]; ke += s_d[w][2];
+            rmin = fminf(rmin, s_f[w][0]); rmax = fmaxf(rmax, s_f[w][1]); vmax = fmaxf(vmax, s_f[w][2]);
+        }
+        double* o = partials + (size_t)blockIdx.x * 6;
+        o[0] = n; o[1] = rs; o[2] = rmin; o[3] = rmax; o[4] = vmax; o[5] = ke;
+    }
+}
+void launch_flow_stats(const Level& L, const float* rho, const float* vel, double* d_partials, int nparts, cudaStream_t s) {
+    flow_stats_kernel<<<nparts, 256, 0, s>>>(rho, vel, L.d_obstacle, (size_t)L.nb * BS3, d_partials);
+}
+
+}  // namespace ludwig

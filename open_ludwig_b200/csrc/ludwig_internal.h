@@ -1,0 +1,159 @@
+// ludwig_internal.h — internal data model of libludwig_b200.so (not part of the ABI).
+//
+// HBM layout (B200-first; differs from the reference's direction-major SoA, blocks.jl:118-150):
+//   * blocks are renumbered along a Morton curve of (bx,by,bz) so that the 26 neighbours of a block
+//     are close in launch order and their halo sectors are still resident in the 126 MB L2;
+//   * populations are BLOCK-major:  f[b][k][z][y][x]  (one block = 27 x 2 KiB = 54 KiB contiguous),
+//     velocities vel[b][c][512], density rho[b][512], flags obstacle/sponge/wall_dist [b][512];
+//   * neighbour table nbr[b][27] holds 0-based internal indices, -1 = none.
+// ref2int / int2ref keep the permutation so every table can be diffed against the reference order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ludwig_b200.h"
+
+namespace ludwig {
+
+constexpr int BS = 8;
+constexpr int BS3 = 512;
+constexpr int Q = 27;
+
+// physics_v2.jl:99-117: k = (dx+1) + 3(dy+1) + 9(dz+1), dx fastest.
+__host__ __device__ constexpr int lat_cx(int k) { return k % 3 - 1; }
+__host__ __device__ constexpr int lat_cy(int k) { return (k / 3) % 3 - 1; }
+__host__ __device__ constexpr int lat_cz(int k) { return k / 9 - 1; }
+__host__ __device__ constexpr int lat_opp(int k) { return 26 - k; }
+__host__ __device__ constexpr int lat_mirror_y(int k) { return k + 3 * (-2 * lat_cy(k)); }
+__host__ __device__ constexpr int lat_mirror_z(int k) { return k + 9 * (-2 * lat_cz(k)); }
+__host__ __device__ constexpr float lat_w(int k) {
+    return (lat_cx(k) * lat_cx(k) + lat_cy(k) * lat_cy(k) + lat_cz(k) * lat_cz(k)) == 0   ? 8.0f / 27.0f
+           : (lat_cx(k) * lat_cx(k) + lat_cy(k) * lat_cy(k) + lat_cz(k) * lat_cz(k)) == 1 ? 2.0f / 27.0f
+           : (lat_cx(k) * lat_cx(k) + lat_cy(k) * lat_cy(k) + lat_cz(k) * lat_cz(k)) == 2 ? 1.0f / 54.0f
+                                                                                         : 1.0f / 216.0f;
+}
+
+// per-block flag word (bflags[b])
+enum : uint32_t {
+    BF_INTERIOR = 1u,    // all 26 neighbour blocks exist -> no boundary / interface handling needed
+    BF_OBSTACLE = 2u,    // at least one obstacle cell
+    BF_SPONGE = 4u,      // at least one cell with sponge > 0
+    BF_WALLDIST = 8u,    // at least one cell with 0 < wall_dist < 10
+};
+
+struct Level {
+    int level_id = 0;   // 1-based
+    int nb = 0;
+    int dimx = 0, dimy = 0, dimz = 0;   // extents of the reference's block_pointer
+    float tau = 0.f;
+    double dx = 0.0;
+    bool temporal = false;
+    bool has_children = false;
+
+    // permutation (host + device)
+    std::vector<int32_t> ref2int, int2ref;
+    int32_t* d_ref2int = nullptr;
+    int32_t* d_int2ref = nullptr;
+
+    // topology (device)
+    int32_t* d_nbr = nullptr;      // [nb][27] internal, -1 none
+    int32_t* d_bcoord = nullptr;   // [nb][4]  bx,by,bz (0-based), flags
+    int32_t* d_ptr = nullptr;      // [dimx*dimy*dimz] col-major like the reference, internal 0-based, -1 none
+    int32_t* d_list_interior = nullptr;  // internal indices of BF_INTERIOR blocks
+    int32_t* d_list_boundary = nullptr;  // the rest
+    int n_interior = 0, n_boundary = 0;
+
+    // static fields (device)
+    uint8_t* d_obstacle = nullptr;  // [nb][512]
+    float* d_sponge = nullptr;
+    float* d_wall_dist = nullptr;
+
+    // state (device).  f[0] = reference `f`, f[1] = `f_temp`; same for vel.
+    float* d_f[2] = {nullptr, nullptr};
+    float* d_vel[2] = {nullptr, nullptr};
+    float* d_rho[2] = {nullptr, nullptr};   // rho[rho_cur] is the reference's level.rho; the other one is
+    int rho_cur = 0;                        // the pre-step density (implicit rho_old), only if has_children
+    // explicit old-state copies, only materialised by ludwig_level_snapshot_old (fine-grained API)
+    float* d_f_old = nullptr;
+    float* d_vel_old = nullptr;
+    float* d_rho_old = nullptr;
+    bool explicit_old = false;
+    int64_t last_t_sub = -1;   // parity of the most recent step (for implicit-old bookkeeping)
+
+    // Bouzidi (compact)
+    bool bouzidi = false;
+    int n_bc = 0;
+    int32_t* d_bc_cell = nullptr;    // [n_bc] internal cell index  b*512 + z*64 + y*8 + x
+    uint16_t* d_bc_q = nullptr;      // [n_bc][27] fp16 q values (compact copy of the dense q_map rows)
+    float* d_bc_tmp = nullptr;       // [n_bc][27] gathered corrections (two-phase K2)
+};
+
+}  // namespace ludwig
+
+struct ludwig_mesh {
+    int n = 0;
+    float *cx = nullptr, *cy = nullptr, *cz = nullptr, *nx = nullptr, *ny = nullptr, *nz = nullptr, *area = nullptr;
+};
+
+struct ludwig_forces {
+    const ludwig_mesh* mesh = nullptr;
+    double rho_ref = 0, u_ref = 0, area_ref = 0, chord_ref = 0, mc[3] = {0, 0, 0};
+    int symmetric = 0;
+    float *p = nullptr, *sx = nullptr, *sy = nullptr, *sz = nullptr;   // [n_tri]
+    double* d_acc = nullptr;    // [9] reduction result
+    double* h_acc = nullptr;    // pinned
+};
+
+struct ludwig_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<ludwig::Level*> levels;
+    std::string err;
+    int64_t bytes = 0;
+    double* d_stats = nullptr;   // flow-stats partials
+    double* h_stats = nullptr;   // pinned
+    int num_sms = 148;
+};
+
+namespace ludwig {
+
+// Arguments of one K1 launch (physics_kernels.jl:9-38 minus the lattice arrays, which are constexpr here).
+struct K1Args {
+    const float* f_in; float* f_out;
+    const float* vel_in; float* vel_out;
+    float* rho_out;
+    const uint8_t* obstacle; const float* sponge; const float* wall_dist;
+    const int32_t* nbr; const int32_t* bcoord;
+    const int32_t* list;   // internal block indices to process (nullptr = identity)
+    int n_list;
+    // parent (physics_v2.jl:43-53)
+    const float *pf_new, *pf_old, *prho_new, *prho_old, *pvel_new, *pvel_old;
+    const int32_t* pptr; int pdimx, pdimy, pdimz;
+    float tau, tau_parent, c_wale, nu_bg, u_inlet, inlet_turb, tw;
+    int is_l1, is_symmetric, nxg, nyg, nzg, wm, seed, use_temporal, sponge_blend;
+};
+
+// k1_generic_strict.cu (compiled with -fmad=false) / k1_generic_fast.cu (default contraction)
+void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
+void launch_k1_generic_fast(const K1Args& a, cudaStream_t s);
+// k1_interior.cu: optimised kernel for BF_INTERIOR blocks (fast mode only)
+void launch_k1_interior(const K1Args& a, cudaStream_t s);
+
+// k_misc.cu
+void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
+void launch_fill(float* p, float v, size_t n, cudaStream_t s);
+void launch_bouzidi(const Level& L, float* f_out, float q_min, bool strict, cudaStream_t s);
+void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
+void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
+void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
+void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
+void launch_block_flags(Level& L, cudaStream_t s);
+void launch_map_stresses(const Level& L, const float* rho, const float* vel, const ludwig_mesh& M, ludwig_forces& F, float dx,
+                         float offx, float offy, float offz, float pscale, float sscale, int radius, cudaStream_t s);
+void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, cudaStream_t s);
+void launch_flow_stats(const Level& L, const float* rho, const float* vel, double* d_partials, int nparts, cudaStream_t s);
+
+}  // namespace ludwig
