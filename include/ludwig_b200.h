@@ -180,6 +180,19 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]);
  * (diagnostics_vram.jl:17 prints the reference's). */
 int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
 
+/* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */
+
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a host framework can
+ * record its own events on it or order other work against it.  NULL for a CPU backend. */
+void* ludwig_ctx_stream(ludwig_ctx* ctx);
+/* Number of kernels this library has launched on the context since creation. */
+int64_t ludwig_launch_count(const ludwig_ctx* ctx);
+/* Per-kernel device timing of K1's dominant kernel: when enabled, every launch of the plain-interior K1 kernel
+ * is bracketed by CUDA events on the context's stream.  ludwig_profile_read synchronises, returns the summed
+ * duration [ms], the number of bracketed launches and the lattice cells they updated, and resets the counters. */
+int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on);
+int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, int64_t* cells);
+
 #ifdef __cplusplus
 }
 #endif

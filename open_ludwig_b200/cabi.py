@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_mesh_create", "ludwig_mesh_destroy", "ludwig_forces_create", "ludwig_forces_destroy",
     "ludwig_init_equilibrium", "ludwig_step_batch", "ludwig_level_step", "ludwig_level_snapshot_old",
     "ludwig_compute_aerodynamics", "ludwig_forces_download_maps", "ludwig_flow_stats", "ludwig_device_bytes",
+    "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read",
 )
 
 
@@ -94,6 +95,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_forces_download_maps": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "ludwig_flow_stats": (C.c_int, [vp, i32, C.POINTER(f64)]),
         "ludwig_device_bytes": (C.c_int64, [vp]),
+        "ludwig_ctx_stream": (vp, [vp]),
+        "ludwig_launch_count": (C.c_int64, [vp]),
+        "ludwig_profile_enable": (C.c_int, [vp, i32]),
+        "ludwig_profile_read": (C.c_int, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -199,6 +204,22 @@ class Context:
 
     def device_bytes(self) -> int:
         return int(self.lib.ludwig_device_bytes(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the context (0 for a CPU backend) — wrap with torch.cuda.ExternalStream to time on it."""
+        return int(self.lib.ludwig_ctx_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.ludwig_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.ludwig_profile_enable(self._h, int(on)), "ludwig_profile_enable")
+
+    def profile_read(self):
+        ms, n, cells = C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.lib.ludwig_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(cells)), "ludwig_profile_read")
+        return ms.value, n.value, cells.value
 
     # -- upload (main.jl:98,101,145) ---------------------------------------------------
     def add_level(self, lv: BlockLevel) -> int:

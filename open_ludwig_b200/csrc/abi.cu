@@ -8,6 +8,7 @@
 //   * no dense f_post_collision (K2 is two-phase, see k_misc.cu).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -153,13 +154,37 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
     if (p.strict_fp) {
         a.list = nullptr; a.n_list = L.nb;
         launch_k1_generic_strict(a, ctx->stream);
+        ctx->launches += 1;
     } else {
-        a.list = L.d_list_interior; a.n_list = L.n_interior;
-        launch_k1_interior(a, ctx->stream);
-        a.list = L.d_list_boundary; a.n_list = L.n_boundary;
-        launch_k1_generic_fast(a, ctx->stream);
+        static const bool no_plain = getenv("LUDWIG_NO_PLAIN") != nullptr;   // development knob: A/B the optimised kernel
+        if (no_plain) {
+            a.list = nullptr; a.n_list = L.nb;
+            launch_k1_generic_fast(a, ctx->stream);
+            ctx->launches += 1;
+        } else {
+            a.list = L.d_list_interior; a.n_list = L.n_interior;
+            const bool prof = ctx->profiling && L.n_interior > 0;
+            if (prof) {
+                if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+                    cudaEvent_t e0, e1;
+                    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+                    ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
+                }
+                CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+            }
+            launch_k1_interior(a, ctx->stream);
+            if (prof) {
+                CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+                ctx->ev_used += 2;
+                ctx->prof_cells += (int64_t)L.n_interior * BS3;
+            }
+            if (L.n_interior > 0) ctx->launches += 1;
+            a.list = L.d_list_boundary; a.n_list = L.n_boundary;
+            launch_k1_generic_fast(a, ctx->stream);
+            if (L.n_boundary > 0) ctx->launches += 1;
+        }
     }
-    if (L.bouzidi && L.n_bc > 0) launch_bouzidi(L, L.d_f[out], p.q_min_threshold, p.strict_fp != 0, ctx->stream);
+    if (L.bouzidi && L.n_bc > 0) { launch_bouzidi(L, L.d_f[out], p.q_min_threshold, p.strict_fp != 0, ctx->stream); ctx->launches += 2; }
     L.rho_cur = rho_out;
     L.last_t_sub = t_sub;
     CU(cudaGetLastError());
@@ -215,6 +240,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     for (Level* L : ctx->levels) free_level(L);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LUDWIG_OK;
@@ -223,6 +249,29 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
 const char* ludwig_last_error(const ludwig_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int ludwig_num_levels(const ludwig_ctx* ctx) { return ctx ? (int)ctx->levels.size() : LUDWIG_EINVAL; }
 int64_t ludwig_device_bytes(const ludwig_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+void* ludwig_ctx_stream(ludwig_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t ludwig_launch_count(const ludwig_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on) {
+    if (!ctx) return LUDWIG_EINVAL;
+    ctx->profiling = on != 0;
+    return LUDWIG_OK;
+}
+int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, int64_t* cells) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaStreamSynchronize(ctx->stream));
+    double tot = 0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        tot += ms;
+    }
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+    if (cells) *cells = ctx->prof_cells;
+    ctx->ev_used = 0; ctx->prof_cells = 0;
+    return LUDWIG_OK;
+}
 
 int ludwig_sync(ludwig_ctx* ctx) {
     if (!ctx) return LUDWIG_EINVAL;
@@ -338,7 +387,7 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     CU(cudaStreamSynchronize(ctx->stream));
     CU(memcpy_sync(ctx->stream, bcoord.data(), L.d_bcoord, bcoord.size() * 4, cudaMemcpyDeviceToHost));
     std::vector<int32_t> li, lb;
-    for (int bi = 0; bi < nb; ++bi) ((bcoord[(size_t)bi * 4 + 3] & BF_INTERIOR) ? li : lb).push_back(bi);
+    for (int bi = 0; bi < nb; ++bi) ((uint32_t)bcoord[(size_t)bi * 4 + 3] == BF_INTERIOR ? li : lb).push_back(bi);   // plain = interior, no obstacle/sponge/wall cell
     L.n_interior = (int)li.size(); L.n_boundary = (int)lb.size();
     CU(dalloc(ctx, &L.d_list_interior, li.size())); CU(dalloc(ctx, &L.d_list_boundary, lb.size()));
     if (!li.empty()) CU(memcpy_sync(ctx->stream, L.d_list_interior, li.data(), li.size() * 4, cudaMemcpyHostToDevice));

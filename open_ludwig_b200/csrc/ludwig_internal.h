@@ -62,7 +62,7 @@ struct Level {
     int32_t* d_nbr = nullptr;      // [nb][27] internal, -1 none
     int32_t* d_bcoord = nullptr;   // [nb][4]  bx,by,bz (0-based), flags
     int32_t* d_ptr = nullptr;      // [dimx*dimy*dimz] col-major like the reference, internal 0-based, -1 none
-    int32_t* d_list_interior = nullptr;  // internal indices of BF_INTERIOR blocks
+    int32_t* d_list_interior = nullptr;  // internal indices of plain blocks (flags == BF_INTERIOR exactly)
     int32_t* d_list_boundary = nullptr;  // the rest
     int n_interior = 0, n_boundary = 0;
 
@@ -116,6 +116,12 @@ struct ludwig_ctx {
     double* d_stats = nullptr;   // flow-stats partials
     double* h_stats = nullptr;   // pinned
     int num_sms = 148;
+    int64_t launches = 0;
+    // K1 profiling (ludwig_profile_enable)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)
+    size_t ev_used = 0;
+    int64_t prof_cells = 0;
 };
 
 namespace ludwig {

@@ -830,5 +830,9 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
 }
 
 int64_t ludwig_device_bytes(const ludwig_ctx*) { return 0; }
+void* ludwig_ctx_stream(ludwig_ctx*) { return nullptr; }
+int64_t ludwig_launch_count(const ludwig_ctx*) { return 0; }
+int ludwig_profile_enable(ludwig_ctx*, int32_t) { return LUDWIG_OK; }
+int ludwig_profile_read(ludwig_ctx*, double* ms, int64_t* n, int64_t* c) { if (ms) *ms = 0; if (n) *n = 0; if (c) *c = 0; return LUDWIG_OK; }
 
 }  // extern "C"
