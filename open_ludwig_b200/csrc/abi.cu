@@ -156,12 +156,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         launch_k1_generic_strict(a, ctx->stream);
         ctx->launches += 1;
     } else {
-        static const bool no_plain = getenv("LUDWIG_NO_PLAIN") != nullptr;   // development knob: A/B the optimised kernel
-        if (no_plain) {
-            a.list = nullptr; a.n_list = L.nb;
-            launch_k1_generic_fast(a, ctx->stream);
-            ctx->launches += 1;
-        } else {
+        {
             a.list = L.d_list_interior; a.n_list = L.n_interior;
             const bool prof = ctx->profiling && L.n_interior > 0;
             if (prof) {
@@ -172,7 +167,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
                 }
                 CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
             }
-            launch_k1_interior(a, ctx->stream);
+            launch_k1_plain(a, ctx->stream);
             if (prof) {
                 CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
                 ctx->ev_used += 2;
@@ -180,7 +175,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             }
             if (L.n_interior > 0) ctx->launches += 1;
             a.list = L.d_list_boundary; a.n_list = L.n_boundary;
-            launch_k1_generic_fast(a, ctx->stream);
+            launch_k1_full(a, ctx->stream);
             if (L.n_boundary > 0) ctx->launches += 1;
         }
     }

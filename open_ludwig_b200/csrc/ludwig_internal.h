@@ -142,11 +142,11 @@ struct K1Args {
     int is_l1, is_symmetric, nxg, nyg, nzg, wm, seed, use_temporal, sponge_blend;
 };
 
-// k1_generic_strict.cu (compiled with -fmad=false) / k1_generic_fast.cu (default contraction)
+// k1_generic_strict.cu (compiled with -fmad=false): the parity build, one thread per cell, reference operation order
 void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
-void launch_k1_generic_fast(const K1Args& a, cudaStream_t s);
-// k1_interior.cu: optimised kernel for BF_INTERIOR blocks (fast mode only)
-void launch_k1_interior(const K1Args& a, cudaStream_t s);
+// k1_fast.cu: fast mode.  plain = interior blocks without obstacle/sponge/near-wall cells; full = all other blocks
+void launch_k1_plain(const K1Args& a, cudaStream_t s);
+void launch_k1_full(const K1Args& a, cudaStream_t s);
 
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);

@@ -103,3 +103,84 @@ def noise_state(level: BlockLevel, amp_rho: float = 0.01, u0: float = 0.03, amp_
     f = equilibrium(rho, ux, uy, uz)
     vel = np.stack([ux, uy, uz], axis=0)
     return f, rho, vel
+
+
+# ----------------------------------------------------------------------------------------------------
+# Synthetic multi-level case for differential tests (no STL): exercises every branch of K1/K2/K3/K4.
+
+def sub_level(parent: BlockLevel, lo, hi, tau: float, level_id: int, temporal_storage: bool = True) -> BlockLevel:
+    """Child level made of the 8 children of every parent block with lo <= (bx,by,bz) <= hi (1-based, inclusive),
+    built with the reference's conventions: children of block b are 2b-1, 2b (domain.jl:103-110), blocks sorted
+    lexicographically (domain.jl:171), neighbour table 0 where no block (domain_topology.jl:135-160),
+    block_pointer extents = max active coordinate (blocks.jl:104-115)."""
+    coords = []
+    for bx in range(lo[0], hi[0] + 1):
+        for by in range(lo[1], hi[1] + 1):
+            for bz in range(lo[2], hi[2] + 1):
+                for dbx in (0, 1):
+                    for dby in (0, 1):
+                        for dbz in (0, 1):
+                            coords.append((2 * bx - 1 + dbx, 2 * by - 1 + dby, 2 * bz - 1 + dbz))
+    coords = np.array(sorted(coords), dtype=np.int32)
+    nb = coords.shape[0]
+    dimx, dimy, dimz = (int(coords[:, i].max()) for i in range(3))
+    bp = np.zeros((dimz, dimy, dimx), np.int32)
+    bp[coords[:, 2] - 1, coords[:, 1] - 1, coords[:, 0] - 1] = np.arange(1, nb + 1, dtype=np.int32)
+    nt = np.zeros((27, nb), np.int32)
+    for d in range(27):
+        x, y, z = coords[:, 0] + CX[d], coords[:, 1] + CY[d], coords[:, 2] + CZ[d]
+        ok = (x >= 1) & (x <= dimx) & (y >= 1) & (y <= dimy) & (z >= 1) & (z <= dimz)
+        nt[d] = np.where(ok, bp[np.clip(z, 1, dimz) - 1, np.clip(y, 1, dimy) - 1, np.clip(x, 1, dimx) - 1], 0)
+    return BlockLevel(level_id=level_id, dx=parent.dx / 2, tau=tau, block_pointer=bp, neighbor_table=nt,
+                      active_block_coords=coords, obstacle=np.zeros((nb, 8, 8, 8), np.uint8),
+                      sponge=np.zeros((nb, 8, 8, 8), np.float32), wall_dist=np.full((nb, 8, 8, 8), 100.0, np.float32),
+                      temporal_storage=temporal_storage)
+
+
+def add_sphere_obstacle(level: BlockLevel, centre, radius: float, seed: int = 7, with_bouzidi: bool = True):
+    """Marks the cells inside a sphere (global cell coordinates of this level) as obstacle, sets wall_dist on the
+    fluid cells touching it and builds a Bouzidi q_map / boundary-cell list (q from the analytic sphere
+    intersection, rounded to Float16 like bouzidi_setup.jl:128)."""
+    gx, gy, gz = global_coords(level)
+    px, py, pz = gx - 0.5, gy - 0.5, gz - 0.5   # cell centres in lattice units
+    r2 = (px - centre[0]) ** 2 + (py - centre[1]) ** 2 + (pz - centre[2]) ** 2
+    level.obstacle[...] = (r2 < radius * radius).astype(np.uint8)
+    dist = np.sqrt(r2) - radius
+    near = (level.obstacle == 0) & (dist < 1.8)
+    level.wall_dist[...] = np.where(near, np.maximum(dist, 0.05) * level.dx, 100.0).astype(np.float32)
+    if not with_bouzidi:
+        return level
+    nb = level.n_blocks
+    q = np.zeros((27, nb, 8, 8, 8), np.float64)
+    for k in range(27):
+        if k == 13:
+            continue
+        c = np.array([CX[k], CY[k], CZ[k]], np.float64)
+        cn = np.linalg.norm(c)
+        d = c / cn
+        ox, oy, oz = px - centre[0], py - centre[1], pz - centre[2]
+        bq = ox * d[0] + oy * d[1] + oz * d[2]
+        disc = bq * bq - (r2 - radius * radius)
+        t = -bq - np.sqrt(np.maximum(disc, 0.0))
+        hit = (disc > 0) & (t > 1e-9)
+        qq = np.where(hit, t / cn, 0.0)
+        q[k] = np.where((qq > 0) & (qq <= 1.0), qq, 0.0)
+    has = (q > 0).any(axis=0)
+    b, z, y, x = np.nonzero(has)   # ordered by (b,z,y,x): the reference's single-thread order
+    level.q_map = q.astype(np.float16)
+    level.tri_map = np.zeros((27, nb, 8, 8, 8), np.int32)
+    level.cell_block = (b + 1).astype(np.int32)
+    level.cell_x, level.cell_y, level.cell_z = ((v + 1).astype(np.int8) for v in (x, y, z))
+    level.n_boundary_cells = int(len(b))
+    level.bouzidi_enabled = level.n_boundary_cells > 0
+    return level
+
+
+def add_outlet_sponge(level: BlockLevel, nx_cells: int, frac: float = 0.25):
+    """Cosine outlet sponge like apply_sponge! (domain_generation.jl:215-289), in lattice units."""
+    gx, _, _ = global_coords(level)
+    px = gx - 0.5
+    start = nx_cells * (1.0 - frac)
+    s = np.where(px > start, 0.5 * (1.0 + np.cos(np.pi * (nx_cells - px) / (nx_cells * frac))), 0.0)
+    level.sponge[...] = s.astype(np.float32)
+    return level
