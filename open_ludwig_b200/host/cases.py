@@ -1,0 +1,41 @@
+"""Where the reference's case folders live and the named configurations of SURVEY.md §8(d).
+
+The case files (config.yaml + STL) are the reference's own input format, kept verbatim.  In the build container
+they are read from /root/reference/CASES; ``tools/fetch_cases.py`` copies them to baseline/_ref/CASES (git-ignored,
+shipped to the GPU box with the working tree) because /root/reference does not exist there.
+"""
+from __future__ import annotations
+
+import os
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SEARCH = (os.path.join(_ROOT, "baseline", "_ref", "CASES"), "/root/reference/CASES", os.path.join(_ROOT, "cases"))
+
+# name -> (case folder, overrides merged over its config.yaml)
+CASE_OVERRIDES = {
+    # config 3: the configuration RESULTS_SPHERE_RE1M.txt was produced with (N = 25 cells/L, U = 14.8 m/s; :38,:153)
+    "sphere_re1m": ("ball1m", {"basic": {"surface_resolution": 25, "flow": {"velocity": 14.8}}}),
+    # the shipped ball1m case = RESULTS_SPHERE_RE10M.txt / CASES/ball1m/RESULTS/*.csv
+    "sphere_re10m": ("ball1m", None),
+    # config 1: coarsest single-level grid, 500 steps
+    "ball1m_coarse": ("ball1m", {"basic": {"surface_resolution": 7, "num_levels": 1, "simulation": {"steps": 500}},
+                                 "advanced": {"diagnostics": {"freq": 100}}}),
+    "wing5": ("Wing_5_deg", None),
+    "bunny": ("Stanford_bunny", None),
+}
+
+
+def case_dir(case: str) -> str:
+    for base in SEARCH:
+        p = os.path.join(base, case)
+        if os.path.isfile(os.path.join(p, "config.yaml")):
+            return p
+    raise FileNotFoundError(f"case folder {case!r} not found in {SEARCH}")
+
+
+def have_case(case: str) -> bool:
+    try:
+        case_dir(case)
+        return True
+    except FileNotFoundError:
+        return False
