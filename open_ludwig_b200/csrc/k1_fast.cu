@@ -57,11 +57,13 @@ struct Moments {
     v2 rho, jx, jy, jz, Pxx, Pyy, Pzz, Pxy, Pyz, Pzx;
 };
 
-// add the pair (f_k, f_(26-k)), k in 0..12, to the raw moments
+// add the pair (f_k, f_(26-k)), k in 0..12, to the raw moments.  Populations are shifted by their rest weight
+// first (f - w_k, exact by Sterbenz), so every sum below adds numbers of size |f - w| ~ 1e-3 w instead of
+// O(0.1): the moments rho - 1 and sum f c c - delta/3 carry ~1e-10 of round-off instead of ~3e-8.
 template <int K>
 __device__ __forceinline__ void acc_pair(Moments& m, v2 fk, v2 fo) {
     constexpr int cx = lat_cx(K), cy = lat_cy(K), cz = lat_cz(K);
-    const v2 s = vadd(fk, fo), d = vsub(fk, fo);
+    const v2 s = vadd(vadd(fk, V(-wk(K))), vadd(fo, V(-wk(K)))), d = vsub(fk, fo);
     m.rho = vadd(m.rho, s);
     if (cx == 1) m.jx = vadd(m.jx, d); else if (cx == -1) m.jx = vsub(m.jx, d);
     if (cy == 1) m.jy = vadd(m.jy, d); else if (cy == -1) m.jy = vsub(m.jy, d);
@@ -177,7 +179,11 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         // combos c = jy + 3 jz; combo c and 8-c hold opposite directions: (km,k0,kp)(c) <-> (kp,k0,km)(8-c)
         v2 am, a0, ap, bm, b0, bp;
         pull3(1, 1, am, a0, ap);          // centre combo: k = 12,13,14
-        m.rho = a0;
+        // moments are accumulated for f - w_k.  The FP32 weights all carry the same relative error, sum_k w_k =
+        // 1 + 7.45e-9 (the reference's equilibrium therefore creates that much mass per step); adding it back here
+        // keeps rho = sum_k f_k exactly as the reference computes it, and makes the shifted second moments
+        // consistent with its feq (sum_k w_k c_a c_b = (1 + eps) delta/3).
+        m.rho = vadd(vadd(a0, V(-W0)), V(7.4505806e-9f));
         acc_pair<12>(m, am, ap);
         if (FULL) { f[12] = am; f[13] = a0; f[14] = ap; }
 #define LUDWIG_COMBO(JY, JZ)                                                   \
@@ -229,7 +235,9 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         obsA = o.x != 0; obsB = o.y != 0;
     }
 
-    v2 rho = vmax(m.rho, 0.01f);                    // :172
+    v2 rho = vmax(vadd(m.rho, V(1.0f)), 0.01f);     // :172
+    // rho - 1 at full precision (m.rho), except in the (never observed) clamped case
+    v2 drho = make_float2(rho.x > 0.01f ? m.rho.x : rho.x - 1.0f, rho.y > 0.01f ? m.rho.y : rho.y - 1.0f);
     const v2 inv_rho = vrcp(rho);
     v2 ux = vmul(m.jx, inv_rho), uy = vmul(m.jy, inv_rho), uz = vmul(m.jz, inv_rho);
 
@@ -238,15 +246,17 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         const v2 sp = ld2(a.sponge + (size_t)b * BS3 + c0);   // sp == 0 leaves everything unchanged
         const v2 om = vsub(V(1.0f), sp);
         rho = vfma(rho, om, sp);
+        drho = vmul(drho, om);                       // rho' - 1 = (rho - 1)(1 - sp)
         ux = vfma(ux, om, vmul(V(a.u_inlet), sp));
         uy = vmul(uy, om);
         uz = vmul(uz, om);
         if (a.sponge_blend == 1) {
             const float ui2 = a.u_inlet * a.u_inlet;
             // raw second moments of feq(1, u_inlet, 0, 0): delta/3 + u u  (cross terms vanish)
-            m.Pxx = vfma(m.Pxx, om, vmul(V(1.0f / 3.0f + ui2), sp));
-            m.Pyy = vfma(m.Pyy, om, vmul(V(1.0f / 3.0f), sp));
-            m.Pzz = vfma(m.Pzz, om, vmul(V(1.0f / 3.0f), sp));
+            // (shifted moments: the delta/3 parts cancel, only u_inlet^2 remains on xx)
+            m.Pxx = vfma(m.Pxx, om, vmul(V(ui2), sp));
+            m.Pyy = vmul(m.Pyy, om);
+            m.Pzz = vmul(m.Pzz, om);
             m.Pxy = vmul(m.Pxy, om); m.Pyz = vmul(m.Pyz, om); m.Pzx = vmul(m.Pzx, om);
         }
     }
@@ -312,7 +322,7 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
 
     // ---- regularized collision (:305-354)
     const v2 usq = vfma(uze, uze, vfma(uye, uye, vmul(uxe, uxe)));
-    const v2 third_rho = vmul(rho, V(1.0f / 3.0f));
+    const v2 third_rho = vmul(drho, V(1.0f / 3.0f));   // (rho - 1)/3: the shifted moments already lack delta/3
     const v2 rux = vmul(rho, uxe), ruy = vmul(rho, uye), ruz = vmul(rho, uze);
     const v2 Pi_xx = vsub(vsub(m.Pxx, third_rho), vmul(rux, uxe));
     const v2 Pi_yy = vsub(vsub(m.Pyy, third_rho), vmul(ruy, uye));
