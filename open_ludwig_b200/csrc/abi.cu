@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <unordered_map>
 
 #include "ludwig_internal.h"
 
@@ -59,7 +60,7 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_ref2int, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_list_interior, L->d_list_boundary,
+    void* ptrs[] = {L->d_ref2int, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_full,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old, L->d_bc_cell, L->d_bc_q, L->d_bc_tmp};
     for (void* p : ptrs)
@@ -125,6 +126,99 @@ ParentView make_parent_view(const Level& P, int64_t parent_t_sub, bool explicit_
     return v;
 }
 
+// Fast-mode tables of one level: ghost blocks for the missing IN-DOMAIN neighbours (refinement interface), the
+// neighbour table that addresses them, the interface pre-pass work list and the three K1 work lists.  Built at the
+// first fast step because "in-domain" depends on ludwig_params.domain_n{x,y,z} (physics_v2.jl:55-56).
+int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
+    if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_list_plain,
+                    (void*)L.d_list_plain_g, (void*)L.d_list_full})
+        if (q) cudaFree(q);
+    L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr;
+    L.d_list_plain = L.d_list_plain_g = L.d_list_full = nullptr;
+    const int nb = L.nb;
+    const int scale = 1 << (L.level_id - 1);
+    const int ext[3] = {p.domain_nx * scale / BS, p.domain_ny * scale / BS, p.domain_nz * scale / BS};   // blocks per axis
+    std::vector<int32_t> nbrf(L.h_nbr);
+    std::vector<int32_t> gcoord;
+    std::unordered_map<uint64_t, int> gid;
+    auto key = [](int x, int y, int z) { return ((uint64_t)(uint32_t)x << 42) | ((uint64_t)(uint32_t)y << 21) | (uint64_t)(uint32_t)z; };
+    if (L.level_id > 1) {
+        for (int b = 0; b < nb; ++b)
+            for (int d = 0; d < 27; ++d) {
+                if (L.h_nbr[(size_t)b * 27 + d] >= 0) continue;
+                int x = L.h_bcoord[(size_t)b * 4] + d % 3 - 1, y = L.h_bcoord[(size_t)b * 4 + 1] + (d / 3) % 3 - 1, z = L.h_bcoord[(size_t)b * 4 + 2] + d / 9 - 1;
+                if (x < 0 || x >= ext[0] || y < 0 || y >= ext[1] || z < 0 || z >= ext[2]) continue;   // outside the domain: a face BC, not a ghost
+                auto it = gid.find(key(x, y, z));
+                int g;
+                if (it == gid.end()) { g = (int)gid.size(); gid.emplace(key(x, y, z), g); gcoord.insert(gcoord.end(), {x, y, z, 0}); }
+                else g = it->second;
+                nbrf[(size_t)b * 27 + d] = nb + g;
+            }
+    }
+    const int ng = (int)gid.size();
+    // work list: ghost cell (g,c) must provide population k iff the cell that pulls it, c + c_k, lies in a real block
+    std::vector<int32_t> gcell;
+    std::vector<uint32_t> gmask;
+    auto real_at = [&](int x, int y, int z) {
+        if (x < 0 || x >= L.dimx || y < 0 || y >= L.dimy || z < 0 || z >= L.dimz) return false;
+        return L.h_ptr[x + (size_t)L.dimx * (y + (size_t)L.dimy * z)] >= 0;
+    };
+    for (int g = 0; g < ng; ++g) {
+        const int gx = gcoord[(size_t)g * 4], gy = gcoord[(size_t)g * 4 + 1], gz = gcoord[(size_t)g * 4 + 2];
+        bool realn[27];
+        for (int d = 0; d < 27; ++d) realn[d] = real_at(gx + d % 3 - 1, gy + (d / 3) % 3 - 1, gz + d / 9 - 1);
+        for (int c = 0; c < BS3; ++c) {
+            const int x = c & 7, y = (c >> 3) & 7, z = c >> 6;
+            if (x > 0 && x < 7 && y > 0 && y < 7 && z > 0 && z < 7) continue;
+            uint32_t m = 0;
+            for (int k = 0; k < 27; ++k) {
+                if (k == 13) continue;
+                int dx = x + (k % 3 - 1), dy = y + ((k / 3) % 3 - 1), dz = z + (k / 9 - 1);
+                int ox = dx < 0 ? -1 : (dx > 7 ? 1 : 0), oy = dy < 0 ? -1 : (dy > 7 ? 1 : 0), oz = dz < 0 ? -1 : (dz > 7 ? 1 : 0);
+                if (ox == 0 && oy == 0 && oz == 0) continue;
+                if (realn[(ox + 1) + (oy + 1) * 3 + (oz + 1) * 9]) m |= 1u << k;
+            }
+            if (m) { gcell.push_back(g * BS3 + c); gmask.push_back(m); }
+        }
+    }
+    // K1 work lists
+    std::vector<int32_t> lp, lg, lf;
+    for (int b = 0; b < nb; ++b) {
+        bool all = true, ghost = false;
+        for (int d = 0; d < 27; ++d) {
+            int v = nbrf[(size_t)b * 27 + d];
+            if (v < 0) all = false; else if (v >= nb) ghost = true;
+        }
+        const uint32_t feat = (uint32_t)L.h_bcoord[(size_t)b * 4 + 3] & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
+        if (all && !feat) (ghost ? lg : lp).push_back(b); else lf.push_back(b);
+    }
+    L.n_ghost = ng; L.n_gcell = (int)gcell.size();
+    L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_full = (int)lf.size();
+    CU(dalloc(ctx, &L.d_nbr_fast, nbrf.size()));
+    CU(memcpy_sync(ctx->stream, L.d_nbr_fast, nbrf.data(), nbrf.size() * 4, cudaMemcpyHostToDevice));
+    if (ng > 0) {
+        CU(dalloc(ctx, &L.d_gcoord, gcoord.size())); CU(dalloc(ctx, &L.d_fghost, (size_t)ng * Q * BS3));
+        CU(dalloc(ctx, &L.d_gcell, gcell.size())); CU(dalloc(ctx, &L.d_gmask, gmask.size()));
+        CU(memcpy_sync(ctx->stream, L.d_gcoord, gcoord.data(), gcoord.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemsetAsync(L.d_fghost, 0, (size_t)ng * Q * BS3 * 4, ctx->stream));
+        if (!gcell.empty()) {
+            CU(memcpy_sync(ctx->stream, L.d_gcell, gcell.data(), gcell.size() * 4, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_gmask, gmask.data(), gmask.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    struct { std::vector<int32_t>* v; int32_t** d; } lists[3] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&lf, &L.d_list_full}};
+    for (auto& l : lists) {
+        CU(dalloc(ctx, l.d, l.v->size()));
+        if (!l.v->empty()) CU(memcpy_sync(ctx->stream, *l.d, l.v->data(), l.v->size() * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    L.fast_dom[0] = p.domain_nx; L.fast_dom[1] = p.domain_ny; L.fast_dom[2] = p.domain_nz;
+    L.fast_ready = true;
+    return LUDWIG_OK;
+}
+
 // perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2.
 int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p) {
     const int in = (t_sub % 2 == 0) ? 0 : 1, out = 1 - in;   // solver_control.jl:35-41
@@ -135,7 +229,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
     a.vel_in = L.d_vel[in]; a.vel_out = L.d_vel[out];
     a.rho_out = L.d_rho[rho_out];
     a.obstacle = L.d_obstacle; a.sponge = L.d_sponge; a.wall_dist = L.d_wall_dist;
-    a.nbr = L.d_nbr; a.bcoord = L.d_bcoord;
+    a.nbr = L.d_nbr; a.bcoord = L.d_bcoord; a.nb = L.nb; a.ghost_delta = 0;
     if (pv) {
         a.pf_new = pv->f_new; a.pf_old = pv->f_old; a.prho_new = pv->rho_new; a.prho_old = pv->rho_old;
         a.pvel_new = pv->vel_new; a.pvel_old = pv->vel_old;
@@ -156,28 +250,43 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         launch_k1_generic_strict(a, ctx->stream);
         ctx->launches += 1;
     } else {
-        {
-            a.list = L.d_list_interior; a.n_list = L.n_interior;
-            const bool prof = ctx->profiling && L.n_interior > 0;
-            if (prof) {
-                if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
-                    cudaEvent_t e0, e1;
-                    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-                    ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
-                }
-                CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
-            }
-            launch_k1_plain(a, ctx->stream);
-            if (prof) {
-                CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
-                ctx->ev_used += 2;
-                ctx->prof_cells += (int64_t)L.n_interior * BS3;
-            }
-            if (L.n_interior > 0) ctx->launches += 1;
-            a.list = L.d_list_boundary; a.n_list = L.n_boundary;
-            launch_k1_full(a, ctx->stream);
-            if (L.n_boundary > 0) ctx->launches += 1;
+        int rc = ensure_fast_tables(ctx, L, p);
+        if (rc) return rc;
+        a.nbr = L.d_nbr_fast;
+        a.ghost_delta = L.d_fghost ? (long long)(L.d_fghost - L.d_f[in]) : 0;
+        if (L.n_gcell > 0 && pv) {   // interface halo pre-pass: fills the ghost blocks K1 is about to pull from
+            GhostArgs g{};
+            g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
+            g.pf_new = pv->f_new; g.pf_old = pv->f_old; g.prho_new = pv->rho_new; g.prho_old = pv->rho_old;
+            g.pvel_new = pv->vel_new; g.pvel_old = pv->vel_old;
+            g.pptr = pv->P->d_ptr; g.pdimx = pv->P->dimx; g.pdimy = pv->P->dimy; g.pdimz = pv->P->dimz;
+            g.tau = L.tau; g.tau_parent = pv->P->tau; g.tw = tw; g.use_temporal = p.use_temporal;
+            launch_ghost_interp(g, ctx->stream);
+            ctx->launches += 1;
         }
+        a.list = L.d_list_plain; a.n_list = L.n_plain;
+        const bool prof = ctx->profiling && L.n_plain > 0;
+        if (prof) {
+            if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+                cudaEvent_t e0, e1;
+                CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+                ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
+            }
+            CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+        }
+        launch_k1_plain(a, ctx->stream);
+        if (prof) {
+            CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+            ctx->ev_used += 2;
+            ctx->prof_cells += (int64_t)L.n_plain * BS3;
+        }
+        if (L.n_plain > 0) ctx->launches += 1;
+        a.list = L.d_list_plain_g; a.n_list = L.n_plain_g;
+        launch_k1_plain_ghost(a, ctx->stream);
+        if (L.n_plain_g > 0) ctx->launches += 1;
+        a.list = L.d_list_full; a.n_list = L.n_full;
+        launch_k1_full(a, ctx->stream);
+        if (L.n_full > 0) ctx->launches += 1;
     }
     if (L.bouzidi && L.n_bc > 0) { launch_bouzidi(L, L.d_f[out], p.q_min_threshold, p.strict_fp != 0, ctx->stream); ctx->launches += 2; }
     L.rho_cur = rho_out;
@@ -377,16 +486,11 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
         CU(memcpy_sync(ctx->stream, L.d_bc_q, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
     }
 
-    // --- per-block flags and the interior / boundary work lists
+    // --- per-block feature flags (obstacle / sponge / near-wall); the fast-mode work lists are built lazily
     launch_block_flags(L, ctx->stream);
     CU(cudaStreamSynchronize(ctx->stream));
     CU(memcpy_sync(ctx->stream, bcoord.data(), L.d_bcoord, bcoord.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<int32_t> li, lb;
-    for (int bi = 0; bi < nb; ++bi) ((uint32_t)bcoord[(size_t)bi * 4 + 3] == BF_INTERIOR ? li : lb).push_back(bi);   // plain = interior, no obstacle/sponge/wall cell
-    L.n_interior = (int)li.size(); L.n_boundary = (int)lb.size();
-    CU(dalloc(ctx, &L.d_list_interior, li.size())); CU(dalloc(ctx, &L.d_list_boundary, lb.size()));
-    if (!li.empty()) CU(memcpy_sync(ctx->stream, L.d_list_interior, li.data(), li.size() * 4, cudaMemcpyHostToDevice));
-    if (!lb.empty()) CU(memcpy_sync(ctx->stream, L.d_list_boundary, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice));
+    L.h_nbr = std::move(nbr); L.h_bcoord = std::move(bcoord); L.h_ptr = std::move(ptr);
 
     // --- the previous level now has children: double-buffer its density (implicit rho_old)
     if (!ctx->levels.empty()) {

@@ -22,6 +22,8 @@
 // (FADD2 / FMUL2 / FFMA2, sm_100+), halving the issue slots of the collision; cx = 0 populations and all
 // stores are 64-bit accesses; a warp is one z-plane (64 cells), a CTA (256 threads) one 8^3 block; CTAs walk
 // the blocks in Morton order so that halo sectors are L2 hits.
+#include <climits>
+
 #include "ludwig_internal.h"
 
 namespace ludwig {
@@ -106,16 +108,114 @@ __device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, 
     return F;
 }
 
-template <bool FULL>
+
+// ---------------------------------------------------------------------------------------------------------
+// Interface halo pre-pass.  In the reference every missing-neighbour population of a fine block is interpolated
+// inside the stream-collide thread that needs it (interpolate_with_rescaling, physics_interpolation.jl:16-138):
+// 8 parent corners x (f_k, rho, u) x (new, old) scattered loads per population, serialised in a handful of
+// divergent lanes.  Here the missing in-domain neighbour blocks of a level exist as GHOST blocks; one thread per
+// ghost CELL computes the 8-corner rho/u blend once and then every population some real cell will pull from it
+// (a static bit mask built with the topology), writing f_ghost[g][k][cell].  K1 then treats ghost blocks as
+// ordinary neighbours, so interface blocks run the plain kernel.  Same arithmetic per population as the
+// reference (the rho/u interpolation it repeats per direction is direction-independent).
+__global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int gc = a.gcell[i];
+    const uint32_t mask = a.gmask[i];
+    const int g = gc >> 9, c = gc & 511;
+    const int4 gb = *reinterpret_cast<const int4*>(a.gcoord + (size_t)g * 4);
+    const int fine_gx = gb.x * BS + (c & 7) + 1, fine_gy = gb.y * BS + ((c >> 3) & 7) + 1, fine_gz = gb.z * BS + (c >> 6) + 1;
+
+    float px_cont = ((float)fine_gx - 0.5f) * 0.5f;
+    float py_cont = ((float)fine_gy - 0.5f) * 0.5f;
+    float pz_cont = ((float)fine_gz - 0.5f) * 0.5f;
+    int px0 = (int)floorf(px_cont), py0 = (int)floorf(py_cont), pz0 = (int)floorf(pz_cont);
+    const int px1 = px0 + 1, py1 = py0 + 1, pz1 = pz0 + 1;
+    const float wx = px_cont - (float)px0, wy = py_cont - (float)py0, wz = pz_cont - (float)pz0;
+    px0 = max(1, px0); py0 = max(1, py0); pz0 = max(1, pz0);
+
+    // corner order: 000,100,010,110,001,101,011,111 (x fastest)
+    int pb[8], loc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int pgx = (q & 1) ? px1 : px0, pgy = (q & 2) ? py1 : py0, pgz = (q & 4) ? pz1 : pz0;
+        const int bx = (pgx - 1) >> 3, by = (pgy - 1) >> 3, bz = (pgz - 1) >> 3;
+        pb[q] = -1;
+        if (bx >= 0 && bx < a.pdimx && by >= 0 && by < a.pdimy && bz >= 0 && bz < a.pdimz) pb[q] = a.pptr[bx + a.pdimx * (by + a.pdimy * bz)];
+        loc[q] = ((pgx - 1) & 7) + 8 * ((pgy - 1) & 7) + 64 * ((pgz - 1) & 7);
+    }
+    const bool blend = a.use_temporal == 1 && a.tw < 0.99f;
+    const float tw = a.tw;
+    // rho, u at the corners (invalid corner: (1,0,0,0); corners 1..7 then fall back to corner 0, valid or not)
+    float cr[8], cux[8], cuy[8], cuz[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (pb[q] >= 0) {
+            const size_t ri = (size_t)pb[q] * BS3 + loc[q], vi = (size_t)pb[q] * 3 * BS3 + loc[q];
+            float r = a.prho_new[ri], x = a.pvel_new[vi], y = a.pvel_new[vi + BS3], z = a.pvel_new[vi + 2 * BS3];
+            if (blend) {
+                const float ro = a.prho_old[ri], xo = a.pvel_old[vi], yo = a.pvel_old[vi + BS3], zo = a.pvel_old[vi + 2 * BS3];
+                r = ro * (1.0f - tw) + r * tw; x = xo * (1.0f - tw) + x * tw; y = yo * (1.0f - tw) + y * tw; z = zo * (1.0f - tw) + z * tw;
+            }
+            cr[q] = r; cux[q] = x; cuy[q] = y; cuz[q] = z;
+        } else if (q == 0) {
+            cr[q] = 1.0f; cux[q] = 0.0f; cuy[q] = 0.0f; cuz[q] = 0.0f;
+        } else {
+            cr[q] = cr[0]; cux[q] = cux[0]; cuy[q] = cuy[0]; cuz[q] = cuz[0];
+        }
+    }
+    auto trilin = [&](const float* v) {
+        float c00 = v[0] * (1.0f - wx) + v[1] * wx;
+        float c01 = v[4] * (1.0f - wx) + v[5] * wx;
+        float c10 = v[2] * (1.0f - wx) + v[3] * wx;
+        float c11 = v[6] * (1.0f - wx) + v[7] * wx;
+        float c0 = c00 * (1.0f - wy) + c10 * wy;
+        float c1 = c01 * (1.0f - wy) + c11 * wy;
+        return c0 * (1.0f - wz) + c1 * wz;
+    };
+    const float rho_int = trilin(cr), ux_int = trilin(cux), uy_int = trilin(cuy), uz_int = trilin(cuz);
+    const float tau_c = a.tau_parent - 0.5f, tau_f = a.tau - 0.5f;
+    const float scale = tau_c > 1.0e-6f ? fminf(fmaxf(tau_f / tau_c, 0.01f), 100.0f) : 1.0f;
+
+    float* __restrict__ dst = a.f_ghost + (size_t)g * (Q * BS3) + c;
+    for (uint32_t m = mask; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
+        const int kx = k % 3 - 1, ky = (k / 3) % 3 - 1, kz = k / 9 - 1;
+        const int d2 = kx * kx + ky * ky + kz * kz;
+        const float w_k = d2 == 0 ? 8.0f / 27.0f : d2 == 1 ? 2.0f / 27.0f : d2 == 2 ? 1.0f / 54.0f : 1.0f / 216.0f;
+        float cf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (pb[q] >= 0) {
+                const size_t fi = ((size_t)pb[q] * Q + k) * BS3 + loc[q];
+                float v = a.pf_new[fi];
+                if (blend) v = a.pf_old[fi] * (1.0f - tw) + v * tw;
+                cf[q] = v;
+            } else cf[q] = q == 0 ? w_k : cf[0];
+        }
+        const float f_int = trilin(cf);
+        const float feq_int = calc_eq(rho_int, ux_int, uy_int, uz_int, w_k, (float)kx, (float)ky, (float)kz);
+        const float f_neq = f_int - feq_int;
+        dst[k * BS3] = feq_int + f_neq * scale;
+    }
+}
+
+constexpr long long MISSING = LLONG_MIN;
+
+// FULL : see file header.   VELFB : some axis neighbour may lack a velocity field (ghost block or domain face) ->
+// fall back to the cell's own value (physics_utils.jl:69).
+template <bool FULL, bool VELFB>
 __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args a) {
-    __shared__ long long s_fo[27];   // element offset of each neighbour block in f_in  (-1: block missing)
-    __shared__ long long s_vo[27];   // ... in vel_in
+    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
+    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
     const int b = a.list[blockIdx.x];
     const int t = threadIdx.x;
     if (t < 27) {
-        int nbi = a.nbr[(size_t)b * 27 + t];
-        s_fo[t] = nbi >= 0 ? (long long)nbi * (Q * BS3) : -1;
-        s_vo[t] = nbi >= 0 ? (long long)nbi * (3 * BS3) : -1;
+        const int nbi = a.nbr[(size_t)b * 27 + t];
+        // indices >= nb address the level's ghost blocks (interface halo, filled by ghost_interp_kernel)
+        s_fo[t] = nbi < 0 ? MISSING : (nbi < a.nb ? (long long)nbi * (Q * BS3) : a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3));
+        s_vo[t] = (nbi < 0 || nbi >= a.nb) ? MISSING : (long long)nbi * (3 * BS3);
     }
     __syncthreads();
 
@@ -150,7 +250,7 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         const int dir = zdir[jz] + ydir[jy];
         const int k0 = 1 + 3 * jy + 9 * jz, kp = k0 + 1, km = k0 - 1;
         const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
-        if (!FULL || (o0 >= 0 && oM >= 0 && oP >= 0)) {
+        if (!FULL || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
             const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
             const float* __restrict__ PM = a.f_in + oM + (loc + xM);
             const float* __restrict__ PP = a.f_in + oP + (loc + xP);
@@ -159,7 +259,7 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
             fm = make_float2(P0[km * BS3 + 1], PP[km * BS3]);   // cx=-1: sources x0+1, x0+2
         } else {
             // some source block is missing: domain face or refinement interface (rare path)
-            if (o0 >= 0) {
+            if (o0 != MISSING) {
                 const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
                 f0 = ld2(P0 + k0 * BS3); fp.y = P0[kp * BS3]; fm.x = P0[km * BS3 + 1];
             } else {
@@ -167,8 +267,8 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
                 fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
                 fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
             }
-            fp.x = oM >= 0 ? a.f_in[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
-            fm.y = oP >= 0 ? a.f_in[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+            fp.x = oM != MISSING ? a.f_in[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
+            fm.y = oP != MISSING ? a.f_in[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
         }
     };
 
@@ -216,12 +316,12 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         for (int cpt = 0; cpt < 3; ++cpt) {
             const v2 own = ld2(vo + cpt * BS3);
             // a missing neighbour block falls back to the cell's own value (physics_utils.jl:69)
-            uW[cpt] = make_float2((!FULL || oM >= 0) ? a.vel_in[oM + (row + xM) + cpt * BS3] : own.x, own.x);
-            uE[cpt] = make_float2(own.y, (!FULL || oP >= 0) ? a.vel_in[oP + (row + xP) + cpt * BS3] : own.y);
-            uN[cpt] = (!FULL || oN >= 0) ? ld2(a.vel_in + oN + lN + cpt * BS3) : own;
-            uS[cpt] = (!FULL || oS >= 0) ? ld2(a.vel_in + oS + lS + cpt * BS3) : own;
-            uT[cpt] = (!FULL || oT >= 0) ? ld2(a.vel_in + oT + lT + cpt * BS3) : own;
-            uB[cpt] = (!FULL || oB >= 0) ? ld2(a.vel_in + oB + lB + cpt * BS3) : own;
+            uW[cpt] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + cpt * BS3] : own.x, own.x);
+            uE[cpt] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + cpt * BS3] : own.y);
+            uN[cpt] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + cpt * BS3) : own;
+            uS[cpt] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + cpt * BS3) : own;
+            uT[cpt] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + cpt * BS3) : own;
+            uB[cpt] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + cpt * BS3) : own;
         }
     }
 
@@ -393,11 +493,19 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
 
 void launch_k1_plain(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<false><<<a.n_list, 256, 0, s>>>(a);
+    k1f::k1_fast_kernel<false, false><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) {
+    if (a.n_list <= 0) return;
+    k1f::k1_fast_kernel<false, true><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1_full(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<true><<<a.n_list, 256, 0, s>>>(a);
+    k1f::k1_fast_kernel<true, true><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_ghost_interp(const GhostArgs& g, cudaStream_t s) {
+    if (g.n <= 0) return;
+    k1f::ghost_interp_kernel<<<(g.n + 127) / 128, 128, 0, s>>>(g);
 }
 
 }  // namespace ludwig

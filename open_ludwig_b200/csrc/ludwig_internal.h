@@ -62,9 +62,23 @@ struct Level {
     int32_t* d_nbr = nullptr;      // [nb][27] internal, -1 none
     int32_t* d_bcoord = nullptr;   // [nb][4]  bx,by,bz (0-based), flags
     int32_t* d_ptr = nullptr;      // [dimx*dimy*dimz] col-major like the reference, internal 0-based, -1 none
-    int32_t* d_list_interior = nullptr;  // internal indices of plain blocks (flags == BF_INTERIOR exactly)
-    int32_t* d_list_boundary = nullptr;  // the rest
-    int n_interior = 0, n_boundary = 0;
+    // host copies used to build the fast-mode tables lazily (they depend on the domain extents in ludwig_params)
+    std::vector<int32_t> h_nbr, h_bcoord, h_ptr;
+
+    // fast-mode tables (built by ensure_fast_tables at the first fast step)
+    bool fast_ready = false;
+    int fast_dom[3] = {0, 0, 0};
+    int32_t* d_nbr_fast = nullptr;       // [nb][27]: real index, nb + ghost id, or -1 (outside the domain)
+    int n_ghost = 0;
+    int32_t* d_gcoord = nullptr;         // [n_ghost][4]
+    float* d_fghost = nullptr;           // [n_ghost][27][512]
+    int32_t* d_gcell = nullptr;          // interface pre-pass work list
+    uint32_t* d_gmask = nullptr;
+    int n_gcell = 0;
+    int32_t* d_list_plain = nullptr;     // all 26 neighbours real, no feature flag
+    int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
+    int32_t* d_list_full = nullptr;      // the rest
+    int n_plain = 0, n_plain_g = 0, n_full = 0;
 
     // static fields (device)
     uint8_t* d_obstacle = nullptr;  // [nb][512]
@@ -135,6 +149,8 @@ struct K1Args {
     const int32_t* nbr; const int32_t* bcoord;
     const int32_t* list;   // internal block indices to process (nullptr = identity)
     int n_list;
+    int nb;                 // number of real blocks: neighbour indices >= nb address ghost blocks (fast mode only)
+    long long ghost_delta;  // (f_ghost - f_in) in elements
     // parent (physics_v2.jl:43-53)
     const float *pf_new, *pf_old, *prho_new, *prho_old, *pvel_new, *pvel_old;
     const int32_t* pptr; int pdimx, pdimy, pdimz;
@@ -144,9 +160,25 @@ struct K1Args {
 
 // k1_generic_strict.cu (compiled with -fmad=false): the parity build, one thread per cell, reference operation order
 void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
-// k1_fast.cu: fast mode.  plain = interior blocks without obstacle/sponge/near-wall cells; full = all other blocks
+// Arguments of the interface-halo pre-pass (k1_fast.cu ghost_interp_kernel)
+struct GhostArgs {
+    const int32_t* gcell;    // [n] ghost cell id  g*512 + z*64 + y*8 + x
+    const uint32_t* gmask;   // [n] bit k set: some real cell pulls population k from this ghost cell
+    int n;
+    const int32_t* gcoord;   // [n_ghost][4] ghost block coords (0-based)
+    float* f_ghost;          // [n_ghost][27][512]
+    const float *pf_new, *pf_old, *prho_new, *prho_old, *pvel_new, *pvel_old;
+    const int32_t* pptr; int pdimx, pdimy, pdimz;
+    float tau, tau_parent, tw;
+    int use_temporal;
+};
+
+// k1_fast.cu: fast mode.  plain = all 26 neighbours real, no obstacle/sponge/near-wall cell; plain_ghost = same but
+// some neighbours are ghost blocks; full = every other block
 void launch_k1_plain(const K1Args& a, cudaStream_t s);
+void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s);
 void launch_k1_full(const K1Args& a, cudaStream_t s);
+void launch_ghost_interp(const GhostArgs& g, cudaStream_t s);
 
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
