@@ -180,6 +180,31 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]);
  * (diagnostics_vram.jl:17 prints the reference's). */
 int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
 
+/* -- multi-GPU: one process per GPU (no reference counterpart: the reference is single-device, main.jl:75) -------
+ *
+ * Every rank creates a context on its own GPU, calls ludwig_ctx_set_partition(rank, world) and then creates the SAME
+ * levels from the SAME global tables.  The library orders the blocks of each level along a Morton curve and gives
+ * rank r the r-th of `world` contiguous ranges (ludwig_partition_starts); it allocates state only for its own blocks.
+ * After the last level: every rank exports CUDA-IPC handles of its state (ludwig_ipc_export), the host all-gathers
+ * the buffers (torch.distributed / MPI) and hands the concatenation to ludwig_ipc_attach.  From then on K1 pulls the
+ * populations and velocities of neighbour blocks owned by another GPU directly through the peer mapping (NVLink
+ * loads inside the stream-collide kernel: no halo packing, no exchange phase), the interface pre-pass and K3 read
+ * remote parents / cells the same way.  The only collective the data path needs is a cross-rank barrier after every
+ * level step (registered with ludwig_set_barrier_callback; may be stream-ordered).  ludwig_flow_stats and
+ * ludwig_compute_aerodynamics return the calling rank's PARTIAL result (triangles dealt round-robin); all 18
+ * aerodynamic outputs are linear in the partial sums, so the caller adds them over the ranks.  Fast mode only. */
+int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* [world+1] or NULL */);
+int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
+int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user);
+/* Reference (1-based) indices of the blocks this rank owns on `level`, in the library's internal order. */
+int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices /* or NULL */);
+/* Upload / download of ONLY this rank's blocks of a state field: Float32[8,8,8,n_local,ncomp] in the order
+ * ludwig_level_local_blocks returns (a 512^3-per-GPU box on 8 GPUs has 116 GB of populations: no host holds it all). */
+int ludwig_level_upload_local(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src);
+int ludwig_level_download_local(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst);
+int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_t* needed_bytes);
+int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_per_rank);
+
 /* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */
 
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a host framework can

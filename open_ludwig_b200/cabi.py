@@ -31,7 +31,11 @@ EXPORTED_SYMBOLS = (
     "ludwig_init_equilibrium", "ludwig_step_batch", "ludwig_level_step", "ludwig_level_snapshot_old",
     "ludwig_compute_aerodynamics", "ludwig_forces_download_maps", "ludwig_flow_stats", "ludwig_device_bytes",
     "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read",
+    "ludwig_partition_starts", "ludwig_ctx_set_partition", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
+    "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
 )
+
+BARRIER_CB = C.CFUNCTYPE(None, C.c_void_p)
 
 
 class LudwigError(RuntimeError):
@@ -99,6 +103,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_launch_count": (C.c_int64, [vp]),
         "ludwig_profile_enable": (C.c_int, [vp, i32]),
         "ludwig_profile_read": (C.c_int, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
+        "ludwig_partition_starts": (C.c_int, [i32, i32, vp]),
+        "ludwig_ctx_set_partition": (C.c_int, [vp, i32, i32]),
+        "ludwig_set_barrier_callback": (C.c_int, [vp, BARRIER_CB, vp]),
+        "ludwig_level_local_blocks": (C.c_int, [vp, i32, C.POINTER(i32), vp]),
+        "ludwig_level_upload_local": (C.c_int, [vp, i32, i32, vp]),
+        "ludwig_level_download_local": (C.c_int, [vp, i32, i32, vp]),
+        "ludwig_ipc_export": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
+        "ludwig_ipc_attach": (C.c_int, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -165,6 +177,7 @@ class Context:
         if rc != 0:
             raise LudwigError(f"ludwig_ctx_create failed ({rc}): is a CUDA device visible?")
         self.n_blocks: list[int] = []
+        self.rank, self.world = 0, 1
         self._meshes: list[C.c_void_p] = []
         self._forces: list[C.c_void_p] = []
 
@@ -220,6 +233,46 @@ class Context:
         ms, n, cells = C.c_double(), C.c_int64(), C.c_int64()
         self._check(self.lib.ludwig_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(cells)), "ludwig_profile_read")
         return ms.value, n.value, cells.value
+
+    # -- multi-GPU (one process per GPU) ----------------------------------------------------
+    def set_partition(self, rank: int, world: int):
+        self._check(self.lib.ludwig_ctx_set_partition(self._h, rank, world), "ludwig_ctx_set_partition")
+        self.rank, self.world = rank, world
+
+    def set_barrier(self, fn):
+        """fn(): cross-rank barrier called by the library after every level step (keep a reference to the thunk)."""
+        self._barrier_thunk = BARRIER_CB(lambda _user: fn())
+        self._check(self.lib.ludwig_set_barrier_callback(self._h, self._barrier_thunk, None), "ludwig_set_barrier_callback")
+
+    def local_blocks(self, level: int) -> np.ndarray:
+        """0-based reference indices of the blocks this rank owns, in the library's internal order."""
+        n = C.c_int32()
+        self._check(self.lib.ludwig_level_local_blocks(self._h, level, C.byref(n), None), "ludwig_level_local_blocks")
+        out = np.empty(n.value, np.int32)
+        self._check(self.lib.ludwig_level_local_blocks(self._h, level, C.byref(n), _ptr(out)), "ludwig_level_local_blocks")
+        return out - 1
+
+    def upload_local(self, level: int, which: int, arr: np.ndarray):
+        """arr: [ncomp, n_local, 8,8,8] for this rank's blocks in local_blocks(level) order."""
+        a = _as(arr, np.float32)
+        self._check(self.lib.ludwig_level_upload_local(self._h, level, which, _ptr(a)), "ludwig_level_upload_local")
+
+    def download_local(self, level: int, which: int, n_local: int) -> np.ndarray:
+        nc = _NCOMP[which]
+        out = np.empty((n_local, 8, 8, 8) if nc == 1 else (nc, n_local, 8, 8, 8), np.float32)
+        self._check(self.lib.ludwig_level_download_local(self._h, level, which, _ptr(out)), "ludwig_level_download_local")
+        return out
+
+    def ipc_export(self) -> bytes:
+        need = C.c_int64()
+        self._check(self.lib.ludwig_ipc_export(self._h, None, 0, C.byref(need)), "ludwig_ipc_export")
+        buf = (C.c_ubyte * max(need.value, 1))()
+        self._check(self.lib.ludwig_ipc_export(self._h, buf, need.value, C.byref(need)), "ludwig_ipc_export")
+        return bytes(buf)[:need.value]
+
+    def ipc_attach(self, all_handles: bytes, bytes_per_rank: int):
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._check(self.lib.ludwig_ipc_attach(self._h, buf, bytes_per_rank), "ludwig_ipc_attach")
 
     # -- upload (main.jl:98,101,145) ---------------------------------------------------
     def add_level(self, lv: BlockLevel) -> int:

@@ -60,7 +60,7 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_ref2int, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_full,
+    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_full,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old, L->d_bc_cell, L->d_bc_q, L->d_bc_tmp};
     for (void* p : ptrs)
@@ -68,26 +68,41 @@ void free_level(Level* L) {
     delete L;
 }
 
+// The calling rank's own base pointers in the per-rank tables (the other ranks' entries come from ludwig_ipc_attach).
+void set_own_peers(ludwig_ctx* ctx, Level& L) {
+    for (int i = 0; i < 2; ++i) { L.peer_f[i][ctx->rank] = L.d_f[i]; L.peer_vel[i][ctx->rank] = L.d_vel[i]; L.peer_rho[i][ctx->rank] = L.d_rho[i]; }
+    L.peer_obstacle[ctx->rank] = L.d_obstacle;
+}
+
+PeerPtrs peers_of(const float* const (&tab)[MAX_RANKS]) {
+    PeerPtrs p;
+    for (int r = 0; r < MAX_RANKS; ++r) p.p[r] = tab[r];
+    return p;
+}
+
 // Upload one reference-layout field [ncomp][nb_ref][512] into the internal layout [nb_int][ncomp][512],
 // one component at a time through a 2 KiB-per-block staging buffer.
-int upload_field(ludwig_ctx* ctx, Level& L, const float* h_src, float* d_dst, int ncomp) {
+int upload_field(ludwig_ctx* ctx, Level& L, const float* h_src, float* d_dst, int ncomp, bool local_order = false) {
     float* stage = nullptr;
-    size_t n = (size_t)L.nb * BS3;
+    // global: the host array covers the whole level in reference order, d_int2ref picks the local blocks;
+    // local_order: the host array holds only this rank's blocks, already in the library's internal order
+    size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;
     CU(cudaMalloc((void**)&stage, n * 4));
     for (int k = 0; k < ncomp; ++k) {
         cudaError_t e = cudaMemcpyAsync(stage, h_src + n * k, n * 4, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) { launch_ref_to_int(stage, d_dst, L.d_int2ref, L.nb, ncomp, k, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
+        if (e == cudaSuccess) { launch_ref_to_int(stage, d_dst, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
         if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("upload_field: ") + cudaGetErrorString(e)); }
     }
     cudaFree(stage);
     return LUDWIG_OK;
 }
-int download_field(ludwig_ctx* ctx, Level& L, const float* d_src, float* h_dst, int ncomp) {
+int download_field(ludwig_ctx* ctx, Level& L, const float* d_src, float* h_dst, int ncomp, bool local_order = false) {
     float* stage = nullptr;
-    size_t n = (size_t)L.nb * BS3;
+    size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;   // global: blocks owned by other ranks are returned as zeros
     CU(cudaMalloc((void**)&stage, n * 4));
     for (int k = 0; k < ncomp; ++k) {
-        launch_int_to_ref(d_src, stage, L.d_int2ref, L.nb, ncomp, k, ctx->stream);
+        if (!local_order && L.nb != L.nb_global) CU(cudaMemsetAsync(stage, 0, n * 4, ctx->stream));
+        launch_int_to_ref(d_src, stage, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream);
         cudaError_t e = cudaMemcpyAsync(h_dst + n * k, stage, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("download_field: ") + cudaGetErrorString(e)); }
@@ -112,6 +127,8 @@ int ensure_explicit_old(ludwig_ctx* ctx, Level& L) {
 struct ParentView {
     const Level* P = nullptr;
     const float *f_new = nullptr, *f_old = nullptr, *rho_new = nullptr, *rho_old = nullptr, *vel_new = nullptr, *vel_old = nullptr;
+    int in = 0, out = 1, rho_new_i = 0, rho_old_i = 0;   // buffer indices (identical on every rank: lock-step schedule)
+    bool explicit_old = false;
 };
 
 // The parent's buffers as recursive_step_temporal! receives them (solver_control.jl:65-72):
@@ -120,9 +137,10 @@ ParentView make_parent_view(const Level& P, int64_t parent_t_sub, bool explicit_
     ParentView v;
     v.P = &P;
     int in = (parent_t_sub % 2 == 0) ? 0 : 1, out = 1 - in;
+    v.in = in; v.out = out; v.rho_new_i = P.rho_cur; v.rho_old_i = P.d_rho[1] ? 1 - P.rho_cur : P.rho_cur;
     v.f_new = P.d_f[out]; v.vel_new = P.d_vel[out]; v.rho_new = P.d_rho[P.rho_cur];
-    if (explicit_old && P.explicit_old) { v.f_old = P.d_f_old; v.vel_old = P.d_vel_old; v.rho_old = P.d_rho_old; }
-    else { v.f_old = P.d_f[in]; v.vel_old = P.d_vel[in]; v.rho_old = P.d_rho[1] ? P.d_rho[1 - P.rho_cur] : P.d_rho[P.rho_cur]; }
+    if (explicit_old && P.explicit_old) { v.f_old = P.d_f_old; v.vel_old = P.d_vel_old; v.rho_old = P.d_rho_old; v.explicit_old = true; }
+    else { v.f_old = P.d_f[in]; v.vel_old = P.d_vel[in]; v.rho_old = P.d_rho[v.rho_old_i]; }
     return v;
 }
 
@@ -189,7 +207,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         bool all = true, ghost = false;
         for (int d = 0; d < 27; ++d) {
             int v = nbrf[(size_t)b * 27 + d];
-            if (v < 0) all = false; else if (v >= nb) ghost = true;
+            if (v < 0) all = false; else if (v >= nb && v < REMOTE_BASE) ghost = true;
         }
         const uint32_t feat = (uint32_t)L.h_bcoord[(size_t)b * 4 + 3] & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
         if (all && !feat) (ghost ? lg : lp).push_back(b); else lf.push_back(b);
@@ -245,6 +263,10 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
     a.seed = (int)(t_sub % 1000000);           // physics_v2.jl:76
     a.use_temporal = p.use_temporal; a.sponge_blend = p.sponge_blend;
 
+    a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
+    if (ctx->world > 1 && (!ctx->peers_attached || p.strict_fp))
+        return fail(ctx, LUDWIG_ESTATE, !ctx->peers_attached ? "multi-GPU context: call ludwig_ipc_attach before stepping"
+                                                            : "multi-GPU stepping supports fast mode only (strict_fp = 0)");
     if (p.strict_fp) {
         a.list = nullptr; a.n_list = L.nb;
         launch_k1_generic_strict(a, ctx->stream);
@@ -257,8 +279,12 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if (L.n_gcell > 0 && pv) {   // interface halo pre-pass: fills the ghost blocks K1 is about to pull from
             GhostArgs g{};
             g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
-            g.pf_new = pv->f_new; g.pf_old = pv->f_old; g.prho_new = pv->rho_new; g.prho_old = pv->rho_old;
-            g.pvel_new = pv->vel_new; g.pvel_old = pv->vel_old;
+            const Level& P = *pv->P;
+            g.pf_new = peers_of(P.peer_f[pv->out]); g.pvel_new = peers_of(P.peer_vel[pv->out]); g.prho_new = peers_of(P.peer_rho[pv->rho_new_i]);
+            g.pf_old = peers_of(P.peer_f[pv->in]); g.pvel_old = peers_of(P.peer_vel[pv->in]); g.prho_old = peers_of(P.peer_rho[pv->rho_old_i]);
+            if (pv->explicit_old) {   // fine-grained API with real copy_to_old! buffers (single rank only)
+                g.pf_old.p[ctx->rank] = pv->f_old; g.pvel_old.p[ctx->rank] = pv->vel_old; g.prho_old.p[ctx->rank] = pv->rho_old;
+            }
             g.pptr = pv->P->d_ptr; g.pdimx = pv->P->dimx; g.pdimy = pv->P->dimy; g.pdimz = pv->P->dimz;
             g.tau = L.tau; g.tau_parent = pv->P->tau; g.tw = tw; g.use_temporal = p.use_temporal;
             launch_ghost_interp(g, ctx->stream);
@@ -288,7 +314,17 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         launch_k1_full(a, ctx->stream);
         if (L.n_full > 0) ctx->launches += 1;
     }
-    if (L.bouzidi && L.n_bc > 0) { launch_bouzidi(L, L.d_f[out], p.q_min_threshold, p.strict_fp != 0, ctx->stream); ctx->launches += 2; }
+    const bool mg = ctx->world > 1 && ctx->barrier_cb;
+    if (L.bouzidi) {
+        // K2 reads f_out of x_ff cells that may belong to another GPU: K1 must be complete everywhere before the
+        // gather, and every gather before any scatter (the same two-phase argument as on one GPU, across ranks).
+        if (mg) ctx->barrier_cb(ctx->barrier_user);
+        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.q_min_threshold, p.strict_fp != 0, 1, ctx->stream);
+        if (mg) ctx->barrier_cb(ctx->barrier_user);
+        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.q_min_threshold, p.strict_fp != 0, 2, ctx->stream);
+        if (L.n_bc > 0) ctx->launches += 2;
+    }
+    if (mg) ctx->barrier_cb(ctx->barrier_user);   // every rank finished this level step
     L.rho_cur = rho_out;
     L.last_t_sub = t_sub;
     CU(cudaGetLastError());
@@ -341,6 +377,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     if (!ctx) return LUDWIG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (Level* L : ctx->levels) free_level(L);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
@@ -391,64 +428,99 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     if (d->dim_x <= 0 || d->dim_y <= 0 || d->dim_z <= 0) return fail(ctx, LUDWIG_EINVAL, "block_pointer extents must be > 0");
     if (!d->block_pointer || !d->neighbor_table || !d->map_x || !d->map_y || !d->map_z || !d->obstacle || !d->sponge || !d->wall_dist)
         return fail(ctx, LUDWIG_EINVAL, "null table pointer");
-    const int nb = d->n_blocks;
-    const size_t nc = (size_t)nb * BS3;
+    if (ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "levels cannot be added after ludwig_ipc_attach");
+    const int nbg = d->n_blocks;                 // blocks of the whole level (all ranks)
+    const size_t ncg = (size_t)nbg * BS3;
 
     Level* Lp = new Level();
     Level& L = *Lp;
     struct Guard { Level* p; ~Guard() { if (p) free_level(p); } } guard{Lp};
-    L.level_id = d->level_id; L.nb = nb; L.dimx = d->dim_x; L.dimy = d->dim_y; L.dimz = d->dim_z;
+    L.level_id = d->level_id; L.nb_global = nbg; L.dimx = d->dim_x; L.dimy = d->dim_y; L.dimz = d->dim_z;
     L.tau = d->tau; L.dx = d->dx; L.temporal = d->temporal_storage != 0;
 
-    // --- permutation: Morton order of the block coordinates
-    std::vector<uint64_t> key(nb);
-    for (int i = 0; i < nb; ++i) {
+    // --- permutation: Morton order of the block coordinates (identical on every rank)
+    std::vector<uint64_t> key(nbg);
+    for (int i = 0; i < nbg; ++i) {
         int bx = d->map_x[i], by = d->map_y[i], bz = d->map_z[i];
         if (bx < 1 || by < 1 || bz < 1 || bx > d->dim_x || by > d->dim_y || bz > d->dim_z)
             return fail(ctx, LUDWIG_EINVAL, "block coordinate outside block_pointer extents");
         key[i] = morton3((uint32_t)(bx - 1), (uint32_t)(by - 1), (uint32_t)(bz - 1));
     }
-    L.int2ref.resize(nb);
+    L.int2ref.resize(nbg);
     std::iota(L.int2ref.begin(), L.int2ref.end(), 0);
     std::sort(L.int2ref.begin(), L.int2ref.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
-    L.ref2int.resize(nb);
-    for (int i = 0; i < nb; ++i) L.ref2int[L.int2ref[i]] = i;
+    L.ref2int.resize(nbg);
+    for (int i = 0; i < nbg; ++i) L.ref2int[L.int2ref[i]] = i;
 
-    // --- topology tables in internal numbering
+    // --- partition: `world` contiguous ranges of the Morton curve (equal block counts)
+    ludwig_partition_starts(nbg, ctx->world, nullptr);   // (validates arguments)
+    L.part_starts.resize(ctx->world + 1);
+    ludwig_partition_starts(nbg, ctx->world, L.part_starts.data());
+    L.part_start = L.part_starts[ctx->rank];
+    const int nb = L.part_starts[ctx->rank + 1] - L.part_start;
+    if (nb <= 0) return fail(ctx, LUDWIG_EINVAL, "level has fewer blocks than ranks");
+    if (nb > PTR_LOCAL_MASK) return fail(ctx, LUDWIG_EINVAL, "more than 2^24 blocks per rank on one level");
+    L.nb = nb;
+    const size_t nc = (size_t)nb * BS3;
+    auto owner_of = [&](int gi) { return (int)(std::upper_bound(L.part_starts.begin(), L.part_starts.end(), gi) - L.part_starts.begin()) - 1; };
+
+    // --- topology tables of the local blocks
     std::vector<int32_t> nbr((size_t)nb * 27), bcoord((size_t)nb * 4);
+    std::unordered_map<int, int> remote_id;
     for (int bi = 0; bi < nb; ++bi) {
-        int br = L.int2ref[bi];
+        int br = L.int2ref[L.part_start + bi];
         for (int dir = 0; dir < 27; ++dir) {
-            int32_t v = d->neighbor_table[br + (size_t)nb * dir];
-            if (v < 0 || v > nb) return fail(ctx, LUDWIG_EINVAL, "neighbor_table entry out of range");
-            nbr[(size_t)bi * 27 + dir] = v > 0 ? L.ref2int[v - 1] : -1;
+            int32_t v = d->neighbor_table[br + (size_t)nbg * dir];
+            if (v < 0 || v > nbg) return fail(ctx, LUDWIG_EINVAL, "neighbor_table entry out of range");
+            int32_t e = -1;
+            if (v > 0) {
+                const int gj = L.ref2int[v - 1];
+                const int ow = owner_of(gj);
+                if (ow == ctx->rank) e = gj - L.part_start;
+                else {
+                    auto it = remote_id.find(gj);
+                    int id;
+                    if (it == remote_id.end()) {
+                        id = (int)remote_id.size(); remote_id.emplace(gj, id);
+                        L.remote_owner.push_back(ow); L.remote_local.push_back(gj - L.part_starts[ow]);
+                    } else id = it->second;
+                    e = REMOTE_BASE + id;
+                }
+            }
+            nbr[(size_t)bi * 27 + dir] = e;
         }
         bcoord[(size_t)bi * 4 + 0] = d->map_x[br] - 1;
         bcoord[(size_t)bi * 4 + 1] = d->map_y[br] - 1;
         bcoord[(size_t)bi * 4 + 2] = d->map_z[br] - 1;
         bcoord[(size_t)bi * 4 + 3] = 0;
     }
+    L.n_remote = (int)remote_id.size();
+    // block pointer of the WHOLE level, rank-encoded: (owner << 24) | owner-local index
     size_t nptr = (size_t)d->dim_x * d->dim_y * d->dim_z;
     std::vector<int32_t> ptr(nptr);
     for (size_t i = 0; i < nptr; ++i) {
         int32_t v = d->block_pointer[i];
-        if (v < 0 || v > nb) return fail(ctx, LUDWIG_EINVAL, "block_pointer entry out of range");
-        ptr[i] = v > 0 ? L.ref2int[v - 1] : -1;
+        if (v < 0 || v > nbg) return fail(ctx, LUDWIG_EINVAL, "block_pointer entry out of range");
+        if (v > 0) {
+            const int gj = L.ref2int[v - 1], ow = owner_of(gj);
+            ptr[i] = (ow << PTR_RANK_SHIFT) | (gj - L.part_starts[ow]);
+        } else ptr[i] = -1;
     }
-    CU(dalloc(ctx, &L.d_ref2int, (size_t)nb)); CU(dalloc(ctx, &L.d_int2ref, (size_t)nb));
+    // device permutation tables: reference index of every LOCAL block
+    std::vector<int32_t> loc2ref(L.int2ref.begin() + L.part_start, L.int2ref.begin() + L.part_start + nb);
+    CU(dalloc(ctx, &L.d_int2ref, (size_t)nb));
     CU(dalloc(ctx, &L.d_nbr, (size_t)nb * 27)); CU(dalloc(ctx, &L.d_bcoord, (size_t)nb * 4)); CU(dalloc(ctx, &L.d_ptr, nptr));
-    CU(memcpy_sync(ctx->stream, L.d_ref2int, L.ref2int.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
-    CU(memcpy_sync(ctx->stream, L.d_int2ref, L.int2ref.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+    CU(memcpy_sync(ctx->stream, L.d_int2ref, loc2ref.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
     CU(memcpy_sync(ctx->stream, L.d_nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
     CU(memcpy_sync(ctx->stream, L.d_bcoord, bcoord.data(), bcoord.size() * 4, cudaMemcpyHostToDevice));
     CU(memcpy_sync(ctx->stream, L.d_ptr, ptr.data(), nptr * 4, cudaMemcpyHostToDevice));
 
-    // --- static fields
+    // --- static fields (the host arrays cover the whole level; each rank keeps its own blocks)
     CU(dalloc(ctx, &L.d_obstacle, nc)); CU(dalloc(ctx, &L.d_sponge, nc)); CU(dalloc(ctx, &L.d_wall_dist, nc));
     {
         uint8_t* stage = nullptr;
-        CU(cudaMalloc((void**)&stage, nc));
-        cudaError_t e = memcpy_sync(ctx->stream, stage, d->obstacle, nc, cudaMemcpyHostToDevice);
+        CU(cudaMalloc((void**)&stage, ncg));
+        cudaError_t e = memcpy_sync(ctx->stream, stage, d->obstacle, ncg, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) { launch_ref_to_int_u8(stage, L.d_obstacle, L.d_int2ref, nb, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
         cudaFree(stage);
         if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, std::string("obstacle upload: ") + cudaGetErrorString(e));
@@ -466,24 +538,28 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     CU(dalloc(ctx, &L.d_rho[0], nc));
     launch_fill(L.d_rho[0], 1.0f, nc, ctx->stream);
 
-    // --- Bouzidi: compact the dense FP16 q_map rows of the boundary cells
+    // --- Bouzidi: compact the dense FP16 q_map rows of the (local) boundary cells
     L.bouzidi = d->bouzidi_enabled != 0 && d->n_boundary_cells > 0 && d->q_map_f16 != nullptr;
-    L.n_bc = L.bouzidi ? d->n_boundary_cells : 0;
-    if (L.n_bc > 0) {
+    if (L.bouzidi) {
         if (!d->cell_block || !d->cell_x || !d->cell_y || !d->cell_z) return fail(ctx, LUDWIG_EINVAL, "null boundary-cell list");
-        std::vector<int32_t> cells(L.n_bc);
-        std::vector<uint16_t> q((size_t)L.n_bc * 27);
-        for (int i = 0; i < L.n_bc; ++i) {
+        std::vector<int32_t> cells;
+        std::vector<uint16_t> q;
+        for (int i = 0; i < d->n_boundary_cells; ++i) {
             int br = d->cell_block[i] - 1, x = d->cell_x[i] - 1, y = d->cell_y[i] - 1, z = d->cell_z[i] - 1;
-            if (br < 0 || br >= nb || x < 0 || x > 7 || y < 0 || y > 7 || z < 0 || z > 7)
+            if (br < 0 || br >= nbg || x < 0 || x > 7 || y < 0 || y > 7 || z < 0 || z > 7)
                 return fail(ctx, LUDWIG_EINVAL, "boundary cell out of range");
+            const int gi = L.ref2int[br];
+            if (gi < L.part_start || gi >= L.part_start + nb) continue;   // another rank's cell
             int loc = x + 8 * y + 64 * z;
-            cells[i] = L.ref2int[br] * BS3 + loc;
-            for (int k = 0; k < 27; ++k) q[(size_t)i * 27 + k] = d->q_map_f16[(size_t)br * BS3 + loc + nc * k];
+            cells.push_back((gi - L.part_start) * BS3 + loc);
+            for (int k = 0; k < 27; ++k) q.push_back(d->q_map_f16[(size_t)br * BS3 + loc + ncg * k]);
         }
-        CU(dalloc(ctx, &L.d_bc_cell, (size_t)L.n_bc)); CU(dalloc(ctx, &L.d_bc_q, (size_t)L.n_bc * 27)); CU(dalloc(ctx, &L.d_bc_tmp, (size_t)L.n_bc * 27));
-        CU(memcpy_sync(ctx->stream, L.d_bc_cell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
-        CU(memcpy_sync(ctx->stream, L.d_bc_q, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
+        L.n_bc = (int)cells.size();
+        if (L.n_bc > 0) {
+            CU(dalloc(ctx, &L.d_bc_cell, cells.size())); CU(dalloc(ctx, &L.d_bc_q, q.size())); CU(dalloc(ctx, &L.d_bc_tmp, q.size()));
+            CU(memcpy_sync(ctx->stream, L.d_bc_cell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_bc_q, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
+        }
     }
 
     // --- per-block feature flags (obstacle / sponge / near-wall); the fast-mode work lists are built lazily
@@ -503,8 +579,10 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
         }
     }
     CU(cudaStreamSynchronize(ctx->stream));
+    set_own_peers(ctx, L);
     guard.p = nullptr;
     ctx->levels.push_back(Lp);
+    if (!ctx->levels.empty() && ctx->levels.size() >= 2) set_own_peers(ctx, *ctx->levels[ctx->levels.size() - 2]);
     if (out_index) *out_index = (int32_t)ctx->levels.size() - 1;
     return LUDWIG_OK;
 }
@@ -541,7 +619,7 @@ int ludwig_level_upload(ludwig_ctx* ctx, int32_t level, int32_t which, const voi
     Level& L = *ctx->levels[level];
     if (which == LUDWIG_OBSTACLE) {
         uint8_t* stage = nullptr;
-        size_t nc = (size_t)L.nb * BS3;
+        size_t nc = (size_t)L.nb_global * BS3;
         CU(cudaMalloc((void**)&stage, nc));
         cudaError_t e = memcpy_sync(ctx->stream, stage, src, nc, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) { launch_ref_to_int_u8(stage, L.d_obstacle, L.d_int2ref, L.nb, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
@@ -561,8 +639,9 @@ int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* d
     Level& L = *ctx->levels[level];
     if (which == LUDWIG_OBSTACLE) {
         uint8_t* stage = nullptr;
-        size_t nc = (size_t)L.nb * BS3;
+        size_t nc = (size_t)L.nb_global * BS3;
         CU(cudaMalloc((void**)&stage, nc));
+        CU(cudaMemsetAsync(stage, 0, nc, ctx->stream));
         launch_int_to_ref_u8(L.d_obstacle, stage, L.d_int2ref, L.nb, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) e = memcpy_sync(ctx->stream, dst, stage, nc, cudaMemcpyDeviceToHost);
@@ -650,6 +729,9 @@ int ludwig_init_equilibrium(ludwig_ctx* ctx) {
 int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params) {
     if (!ctx || !params || ctx->levels.empty() || batch_size < 0) return fail(ctx, LUDWIG_EINVAL, "bad step args");
     CU(cudaSetDevice(ctx->device));
+    if (ctx->world > 1 && !ctx->barrier_cb) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: register ludwig_set_barrier_callback first");
+    // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
+    if (ctx->world > 1) ctx->barrier_cb(ctx->barrier_user);
     for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
         int rc = recursive_step(ctx, 0, t_start + t_offset, nullptr, 0.0f, u_curr, *params);
         if (rc) return rc;
@@ -662,6 +744,7 @@ int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t par
     if (!level_ok(ctx, level) || !params) return fail(ctx, LUDWIG_EINVAL, "bad level");
     CU(cudaSetDevice(ctx->device));
     Level& L = *ctx->levels[level];
+    if (ctx->world > 1 && ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);
     if (level == 0) return step_level(ctx, L, nullptr, t_sub, temporal_weight, u_curr, *params);
     Level& P = *ctx->levels[level - 1];
     if (params->use_temporal && !P.temporal) return fail(ctx, LUDWIG_ESTATE, "parent has no temporal storage");
@@ -695,8 +778,14 @@ int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* F, int32_t level
     const float pscale = (float)(rho_phys * velocity_scale * velocity_scale);   // forces/surface.jl:402-403
     const float offx = (float)mesh_offset[0], offy = (float)mesh_offset[1], offz = (float)mesh_offset[2];
     // K3 reads level.rho and level.vel (NOT vel_temp) whatever the parity — forces/surface.jl:412
-    launch_map_stresses(L, L.d_rho[L.rho_cur], L.d_vel[0], M, *F, (float)L.dx, offx, offy, offz, pscale, pscale, search_radius, ctx->stream);
-    launch_integrate_forces(M, *F, offx, offy, offz, ctx->stream);
+    if (ctx->world > 1 && ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);   // K3 reads cells owned by other GPUs
+    // multi-GPU: triangles are dealt round-robin to the ranks; each rank returns PARTIAL sums (every output of this
+    // call is linear in them), the caller adds the 18 numbers over the ranks.
+    PeerBytes obs;
+    for (int r = 0; r < MAX_RANKS; ++r) obs.p[r] = L.peer_obstacle[r];
+    launch_map_stresses(L, peers_of(L.peer_rho[L.rho_cur]), peers_of(L.peer_vel[0]), obs, M, *F, (float)L.dx, offx, offy, offz, pscale, pscale,
+                        search_radius, ctx->rank, ctx->world, ctx->stream);
+    launch_integrate_forces(M, *F, offx, offy, offz, ctx->rank, ctx->world, ctx->stream);
     CU(cudaMemcpyAsync(F->h_acc, F->d_acc, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     // FP64 sums of the FP32 per-triangle contributions (the reference's FP32 atomics lose ~1e-4 here)
@@ -747,6 +836,119 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
     }
     if (n > 0) { out[0] = n; out[1] = rs / n; out[2] = rmin; out[3] = rmax; out[4] = vmax; out[5] = 0.5 * ke; }
     else { out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 1; out[4] = 0; out[5] = 0; }
+    return LUDWIG_OK;
+}
+
+// ---- multi-GPU (one process per GPU) -------------------------------------------------------------------------
+
+int ludwig_level_upload_local(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src) {
+    if (!level_ok(ctx, level) || !src || which == LUDWIG_OBSTACLE) return fail(ctx, LUDWIG_EINVAL, "bad level/src/field");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    float* p; int ncomp;
+    int rc = resolve_field(ctx, L, which, true, &p, &ncomp);
+    if (rc) return rc;
+    return upload_field(ctx, L, (const float*)src, p, ncomp, true);
+}
+int ludwig_level_download_local(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst) {
+    if (!level_ok(ctx, level) || !dst || which == LUDWIG_OBSTACLE) return fail(ctx, LUDWIG_EINVAL, "bad level/dst/field");
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    float* p; int ncomp;
+    int rc = resolve_field(ctx, L, which, false, &p, &ncomp);
+    if (rc) return rc;
+    return download_field(ctx, L, p, (float*)dst, ncomp, true);
+}
+
+int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts) {
+    if (n_blocks < 0 || world < 1 || world > MAX_RANKS) return LUDWIG_EINVAL;
+    if (starts) for (int r = 0; r <= world; ++r) starts[r] = (int32_t)(((int64_t)n_blocks * r) / world);
+    return LUDWIG_OK;
+}
+
+int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
+    if (!ctx || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return fail(ctx, LUDWIG_EINVAL, "bad rank/world (max 8 ranks)");
+    if (!ctx->levels.empty()) return fail(ctx, LUDWIG_ESTATE, "set the partition before creating levels");
+    ctx->rank = rank; ctx->world = world;
+    return LUDWIG_OK;
+}
+
+int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user) {
+    if (!ctx) return LUDWIG_EINVAL;
+    ctx->barrier_cb = fn; ctx->barrier_user = user;
+    return LUDWIG_OK;
+}
+
+int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices) {
+    if (!level_ok(ctx, level)) return fail(ctx, LUDWIG_EINVAL, "bad level");
+    Level& L = *ctx->levels[level];
+    if (n_local) *n_local = L.nb;
+    if (ref_indices) for (int i = 0; i < L.nb; ++i) ref_indices[i] = L.int2ref[L.part_start + i] + 1;   // 1-based like every table
+    return LUDWIG_OK;
+}
+
+// 7 handles per level: f, f_temp, vel, vel_temp, rho[0], rho[1] (zeros if absent), obstacle.
+int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_t* needed_bytes) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t need = (int64_t)ctx->levels.size() * 7 * (int64_t)sizeof(cudaIpcMemHandle_t);
+    if (needed_bytes) *needed_bytes = need;
+    if (!out) return LUDWIG_OK;
+    if (capacity_bytes < need) return fail(ctx, LUDWIG_EINVAL, "ipc export buffer too small");
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto* h = (cudaIpcMemHandle_t*)out;
+    std::memset(out, 0, (size_t)need);
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        Level& L = *ctx->levels[l];
+        void* ptrs[7] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle};
+        for (int i = 0; i < 7; ++i)
+            if (ptrs[i]) CU(cudaIpcGetMemHandle(&h[l * 7 + i], ptrs[i]));
+    }
+    return LUDWIG_OK;
+}
+
+// all_handles: the export buffers of ranks 0..world-1 concatenated (what an all_gather returns).
+int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_per_rank) {
+    if (!ctx || !all_handles) return fail(ctx, LUDWIG_EINVAL, "bad attach args");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t need = (int64_t)ctx->levels.size() * 7 * (int64_t)sizeof(cudaIpcMemHandle_t);
+    if (bytes_per_rank != need) return fail(ctx, LUDWIG_EINVAL, "ipc attach: handle buffer size mismatch (same levels on every rank?)");
+    for (int r = 0; r < ctx->world; ++r) {
+        if (r == ctx->rank) continue;
+        const auto* h = (const cudaIpcMemHandle_t*)((const char*)all_handles + (size_t)r * need);
+        for (size_t l = 0; l < ctx->levels.size(); ++l) {
+            Level& L = *ctx->levels[l];
+            void* own[7] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle};
+            void* mapped[7] = {};
+            for (int i = 0; i < 7; ++i) {
+                if (!own[i]) continue;   // same structure on every rank: absent here = absent there
+                CU(cudaIpcOpenMemHandle(&mapped[i], h[l * 7 + i], cudaIpcMemLazyEnablePeerAccess));
+                ctx->ipc_opened.push_back(mapped[i]);
+            }
+            L.peer_f[0][r] = (const float*)mapped[0]; L.peer_f[1][r] = (const float*)mapped[1];
+            L.peer_vel[0][r] = (const float*)mapped[2]; L.peer_vel[1][r] = (const float*)mapped[3];
+            L.peer_rho[0][r] = (const float*)mapped[4]; L.peer_rho[1][r] = (const float*)mapped[5];
+            L.peer_obstacle[r] = (const uint8_t*)mapped[6];
+        }
+    }
+    // remote-block offset tables, relative to the local buffers (K1 adds them to f_in / vel_in)
+    for (Level* Lp : ctx->levels) {
+        Level& L = *Lp;
+        set_own_peers(ctx, L);
+        if (L.n_remote == 0) continue;
+        for (int par = 0; par < 2; ++par) {
+            std::vector<long long> of(L.n_remote), ov(L.n_remote);
+            for (int i = 0; i < L.n_remote; ++i) {
+                const int ow = L.remote_owner[i];
+                of[i] = (long long)((L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3) - L.d_f[par]);
+                ov[i] = (long long)((L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3) - L.d_vel[par]);
+            }
+            CU(dalloc(ctx, &L.d_roff_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_roff_v[par], (size_t)L.n_remote));
+            CU(memcpy_sync(ctx->stream, L.d_roff_f[par], of.data(), of.size() * 8, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_roff_v[par], ov.data(), ov.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    ctx->peers_attached = true;
     return LUDWIG_OK;
 }
 

@@ -33,6 +33,7 @@ __device__ __forceinline__ Corner get_blended(const K1Args& a, int pgx, int pgy,
     if (pbx >= 0 && pbx < a.pdimx && pby >= 0 && pby < a.pdimy && pbz >= 0 && pbz < a.pdimz) {
         int pb = a.pptr[pbx + a.pdimx * (pby + a.pdimy * pbz)];
         if (pb >= 0) {
+            pb &= PTR_LOCAL_MASK;   // single-rank paths only: the owner bits are 0
             int loc = ((pgx - 1) & 7) + 8 * ((pgy - 1) & 7) + 64 * ((pgz - 1) & 7);
             size_t fi = ((size_t)pb * Q + k) * BS3 + loc;
             size_t ri = (size_t)pb * BS3 + loc;

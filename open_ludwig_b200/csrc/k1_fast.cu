@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
     for (int q = 0; q < 8; ++q) {
         const int pgx = (q & 1) ? px1 : px0, pgy = (q & 2) ? py1 : py0, pgz = (q & 4) ? pz1 : pz0;
         const int bx = (pgx - 1) >> 3, by = (pgy - 1) >> 3, bz = (pgz - 1) >> 3;
-        pb[q] = -1;
+        pb[q] = -1;   // (owner rank << 24) | owner-local block index
         if (bx >= 0 && bx < a.pdimx && by >= 0 && by < a.pdimy && bz >= 0 && bz < a.pdimz) pb[q] = a.pptr[bx + a.pdimx * (by + a.pdimy * bz)];
         loc[q] = ((pgx - 1) & 7) + 8 * ((pgy - 1) & 7) + 64 * ((pgz - 1) & 7);
     }
@@ -152,10 +152,13 @@ __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         if (pb[q] >= 0) {
-            const size_t ri = (size_t)pb[q] * BS3 + loc[q], vi = (size_t)pb[q] * 3 * BS3 + loc[q];
-            float r = a.prho_new[ri], x = a.pvel_new[vi], y = a.pvel_new[vi + BS3], z = a.pvel_new[vi + 2 * BS3];
+            const int pr = pb[q] >> PTR_RANK_SHIFT, pl = pb[q] & PTR_LOCAL_MASK;
+            const size_t ri = (size_t)pl * BS3 + loc[q], vi = (size_t)pl * 3 * BS3 + loc[q];
+            const float* __restrict__ vn = a.pvel_new.p[pr];
+            float r = a.prho_new.p[pr][ri], x = vn[vi], y = vn[vi + BS3], z = vn[vi + 2 * BS3];
             if (blend) {
-                const float ro = a.prho_old[ri], xo = a.pvel_old[vi], yo = a.pvel_old[vi + BS3], zo = a.pvel_old[vi + 2 * BS3];
+                const float* __restrict__ vo = a.pvel_old.p[pr];
+                const float ro = a.prho_old.p[pr][ri], xo = vo[vi], yo = vo[vi + BS3], zo = vo[vi + 2 * BS3];
                 r = ro * (1.0f - tw) + r * tw; x = xo * (1.0f - tw) + x * tw; y = yo * (1.0f - tw) + y * tw; z = zo * (1.0f - tw) + z * tw;
             }
             cr[q] = r; cux[q] = x; cuy[q] = y; cuz[q] = z;
@@ -188,9 +191,10 @@ __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (pb[q] >= 0) {
-                const size_t fi = ((size_t)pb[q] * Q + k) * BS3 + loc[q];
-                float v = a.pf_new[fi];
-                if (blend) v = a.pf_old[fi] * (1.0f - tw) + v * tw;
+                const int pr = pb[q] >> PTR_RANK_SHIFT, pl = pb[q] & PTR_LOCAL_MASK;
+                const size_t fi = ((size_t)pl * Q + k) * BS3 + loc[q];
+                float v = a.pf_new.p[pr][fi];
+                if (blend) v = a.pf_old.p[pr][fi] * (1.0f - tw) + v * tw;
                 cf[q] = v;
             } else cf[q] = q == 0 ? w_k : cf[0];
         }
@@ -214,8 +218,12 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
     if (t < 27) {
         const int nbi = a.nbr[(size_t)b * 27 + t];
         // indices >= nb address the level's ghost blocks (interface halo, filled by ghost_interp_kernel)
-        s_fo[t] = nbi < 0 ? MISSING : (nbi < a.nb ? (long long)nbi * (Q * BS3) : a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3));
-        s_vo[t] = (nbi < 0 || nbi >= a.nb) ? MISSING : (long long)nbi * (3 * BS3);
+        // (another GPU's block: offset of the peer-mapped block relative to the local buffer — K1 pulls it over NVLink)
+        s_fo[t] = nbi < 0 ? MISSING
+                  : nbi < a.nb ? (long long)nbi * (Q * BS3)
+                  : nbi < REMOTE_BASE ? a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3)
+                                      : a.roff_f[nbi - REMOTE_BASE];
+        s_vo[t] = nbi < 0 ? MISSING : nbi < a.nb ? (long long)nbi * (3 * BS3) : nbi < REMOTE_BASE ? MISSING : a.roff_v[nbi - REMOTE_BASE];
     }
     __syncthreads();
 

@@ -49,14 +49,14 @@ __global__ void ref_to_int_kernel(const float4* __restrict__ src_k, float4* __re
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nb * 128) return;
     int b = (int)(i >> 7), q = (int)(i & 127);
-    dst[((size_t)b * ncomp + k) * 128 + q] = src_k[(size_t)int2ref[b] * 128 + q];
+    dst[((size_t)b * ncomp + k) * 128 + q] = src_k[(size_t)(int2ref ? int2ref[b] : b) * 128 + q];
 }
 __global__ void int_to_ref_kernel(const float4* __restrict__ src, float4* __restrict__ dst_k, const int32_t* __restrict__ int2ref,
                                   int nb, int ncomp, int k) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nb * 128) return;
     int b = (int)(i >> 7), q = (int)(i & 127);
-    dst_k[(size_t)int2ref[b] * 128 + q] = src[((size_t)b * ncomp + k) * 128 + q];
+    dst_k[(size_t)(int2ref ? int2ref[b] : b) * 128 + q] = src[((size_t)b * ncomp + k) * 128 + q];
 }
 void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s) {
     size_t n = (size_t)nb * 128;
@@ -119,7 +119,7 @@ void launch_block_flags(Level& L, cudaStream_t s) {
 template <bool STRICT>
 __global__ void bouzidi_gather_kernel(const float* __restrict__ f_out, const int32_t* __restrict__ bc_cell,
                                       const uint16_t* __restrict__ bc_q, const int32_t* __restrict__ nbr,
-                                      float* __restrict__ tmp, int n_bc, float q_min) {
+                                      const long long* __restrict__ roff, float* __restrict__ tmp, int n_bc, float q_min) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_bc * 27) return;
     int ci = i / 27, k = i - ci * 27;
@@ -141,7 +141,9 @@ __global__ void bouzidi_gather_kernel(const float* __restrict__ f_out, const int
             } else {
                 int ox = nx < 0 ? -1 : (nx > 7 ? 1 : 0), oy = ny < 0 ? -1 : (ny > 7 ? 1 : 0), oz = nz < 0 ? -1 : (nz > 7 ? 1 : 0);
                 int nbi = nbr[(size_t)b * 27 + (ox + 1) + (oy + 1) * 3 + (oz + 1) * 9];
-                if (nbi >= 0) f_ff = f_out[((size_t)nbi * Q + k) * BS3 + (nz & 7) * 64 + (ny & 7) * 8 + (nx & 7)];
+                const int lc = (nz & 7) * 64 + (ny & 7) * 8 + (nx & 7);
+                if (nbi >= REMOTE_BASE) f_ff = f_out[roff[nbi - REMOTE_BASE] + k * BS3 + lc];   // block owned by another GPU
+                else if (nbi >= 0) f_ff = f_out[((size_t)nbi * Q + k) * BS3 + lc];
             }
             float coeff1 = 2.0f * q;
             if (STRICT) res = __fadd_rn(__fmul_rn(coeff1, f_k), __fmul_rn(__fsub_rn(1.0f, coeff1), f_ff));
@@ -165,26 +167,29 @@ __global__ void bouzidi_scatter_kernel(float* __restrict__ f_out, const int32_t*
     int cell = bc_cell[ci];
     f_out[((size_t)(cell >> 9) * Q + (26 - k)) * BS3 + (cell & 511)] = v;
 }
-void launch_bouzidi(const Level& L, float* f_out, float q_min, bool strict, cudaStream_t s) {
+// phase 1 = gather, 2 = scatter, 0 = both (multi-GPU runs them separately with a cross-rank barrier in between)
+void launch_bouzidi(const Level& L, float* f_out, const long long* roff, float q_min, bool strict, int phase, cudaStream_t s) {
     if (!L.bouzidi || L.n_bc == 0) return;
     int n = L.n_bc * 27;
     unsigned grid = (n + 255) / 256;
-    if (strict) bouzidi_gather_kernel<true><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, L.d_bc_tmp, L.n_bc, q_min);
-    else bouzidi_gather_kernel<false><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, L.d_bc_tmp, L.n_bc, q_min);
-    bouzidi_scatter_kernel<<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_tmp, L.n_bc);
+    if (phase != 2) {
+        if (strict) bouzidi_gather_kernel<true><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, roff, L.d_bc_tmp, L.n_bc, q_min);
+        else bouzidi_gather_kernel<false><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, roff, L.d_bc_tmp, L.n_bc, q_min);
+    }
+    if (phase != 1) bouzidi_scatter_kernel<<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_tmp, L.n_bc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3  nearest-fluid-cell search per triangle + pressure / shear (forces/surface.jl:32-124,138-266).
 // The arithmetic is written with explicit _rn intrinsics so that it matches the oracle without FMA.
-__global__ void map_stresses_kernel(const float* __restrict__ rho, const float* __restrict__ vel, const uint8_t* __restrict__ obstacle,
+__global__ void map_stresses_kernel(const PeerPtrs rho, const PeerPtrs vel, const PeerBytes obstacle,
                                     const int32_t* __restrict__ ptr, int dimx, int dimy, int dimz,
                                     const float* __restrict__ tcx, const float* __restrict__ tcy, const float* __restrict__ tcz,
                                     const float* __restrict__ tnx, const float* __restrict__ tny, const float* __restrict__ tnz,
                                     float* __restrict__ p_map, float* __restrict__ sx_map, float* __restrict__ sy_map, float* __restrict__ sz_map,
                                     int n_tri, float dx, float offx, float offy, float offz, float pscale, float sscale,
-                                    float tau_molecular, int search_radius) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                    float tau_molecular, int search_radius, int tri_first, int tri_stride) {
+    int i = tri_first + (blockIdx.x * blockDim.x + threadIdx.x) * tri_stride;   // multi-GPU: triangles are dealt round-robin
     if (i >= n_tri) return;
     float tx = __fadd_rn(tcx[i], offx), ty = __fadd_rn(tcy[i], offy), tz = __fadd_rn(tcz[i], offz);
     float n_x = tnx[i], n_y = tny[i], n_z = tnz[i];
@@ -201,20 +206,22 @@ __global__ void map_stresses_kernel(const float* __restrict__ rho, const float* 
                     if (cgx < 1 || cgy < 1 || cgz < 1) continue;
                     int bx = (cgx - 1) >> 3, by = (cgy - 1) >> 3, bz = (cgz - 1) >> 3;
                     if (bx >= dimx || by >= dimy || bz >= dimz) continue;
-                    int bi = ptr[bx + dimx * (by + dimy * bz)];
-                    if (bi < 0) continue;
+                    int enc = ptr[bx + dimx * (by + dimy * bz)];
+                    if (enc < 0) continue;
+                    const int pr = enc >> PTR_RANK_SHIFT, bi = enc & PTR_LOCAL_MASK;   // owning rank, its local block
                     int loc = ((cgx - 1) & 7) + 8 * ((cgy - 1) & 7) + 64 * ((cgz - 1) & 7);
                     size_t c = (size_t)bi * BS3 + loc;
-                    if (obstacle[c]) continue;
+                    if (obstacle.p[pr][c]) continue;
                     float ccx = __fmul_rn(__fsub_rn((float)cgx, 0.5f), dx), ccy = __fmul_rn(__fsub_rn((float)cgy, 0.5f), dx),
                           ccz = __fmul_rn(__fsub_rn((float)cgz, 0.5f), dx);
                     float ex = __fsub_rn(tx, ccx), ey = __fsub_rn(ty, ccy), ez = __fsub_rn(tz, ccz);
                     float dist_sq = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
                     if (dist_sq < best_dist_sq) {
                         best_dist_sq = dist_sq;
-                        best_rho = rho[c];
+                        best_rho = rho.p[pr][c];
                         size_t vi = (size_t)bi * 3 * BS3 + loc;
-                        best_ux = vel[vi]; best_uy = vel[vi + BS3]; best_uz = vel[vi + 2 * BS3];
+                        const float* __restrict__ vp = vel.p[pr];
+                        best_ux = vp[vi]; best_uy = vp[vi + BS3]; best_uz = vp[vi + 2 * BS3];
                         best_wall_dist = __fdiv_rn(__fsqrt_rn(dist_sq), dx);
                         found = true;
                     }
@@ -240,11 +247,14 @@ __global__ void map_stresses_kernel(const float* __restrict__ rho, const float* 
     }
     p_map[i] = p_val; sx_map[i] = tau_x; sy_map[i] = tau_y; sz_map[i] = tau_z;
 }
-void launch_map_stresses(const Level& L, const float* rho, const float* vel, const ludwig_mesh& M, ludwig_forces& F, float dx,
-                         float offx, float offy, float offz, float pscale, float sscale, int radius, cudaStream_t s) {
-    map_stresses_kernel<<<(M.n + 127) / 128, 128, 0, s>>>(rho, vel, L.d_obstacle, L.d_ptr, L.dimx, L.dimy, L.dimz, M.cx, M.cy, M.cz,
-                                                          M.nx, M.ny, M.nz, F.p, F.sx, F.sy, F.sz, M.n, dx, offx, offy, offz, pscale,
-                                                          sscale, L.tau, radius);
+void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
+                         ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,
+                         int tri_first, int tri_stride, cudaStream_t s) {
+    const int n_mine = (M.n - tri_first + tri_stride - 1) / tri_stride;
+    if (n_mine <= 0) return;
+    map_stresses_kernel<<<(n_mine + 127) / 128, 128, 0, s>>>(rho, vel, obstacle, L.d_ptr, L.dimx, L.dimy, L.dimz, M.cx, M.cy, M.cz,
+                                                             M.nx, M.ny, M.nz, F.p, F.sx, F.sy, F.sz, M.n, dx, offx, offy, offz, pscale,
+                                                             sscale, L.tau, radius, tri_first, tri_stride);
 }
 
 // K4.  Per-triangle contributions are formed in FP32 exactly as the reference does (forces/surface.jl:298-352)
@@ -256,9 +266,10 @@ __global__ void __launch_bounds__(1024) integrate_forces_kernel(const float* __r
                                                                 const float* __restrict__ tcz, const float* __restrict__ tnx,
                                                                 const float* __restrict__ tny, const float* __restrict__ tnz,
                                                                 const float* __restrict__ areas, int n_tri, float offx, float offy,
-                                                                float offz, float refx, float refy, float refz, double* __restrict__ out) {
+                                                                float offz, float refx, float refy, float refz, int tri_first,
+                                                                int tri_stride, double* __restrict__ out) {
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = threadIdx.x; i < n_tri; i += blockDim.x) {
+    for (int i = tri_first + threadIdx.x * tri_stride; i < n_tri; i += blockDim.x * tri_stride) {
         float p = p_map[i], tau_x = sx_map[i], tau_y = sy_map[i], tau_z = sz_map[i];
         float nx = tnx[i], ny = tny[i], nz = tnz[i], A = areas[i];
         float cx = __fadd_rn(tcx[i], offx), cy = __fadd_rn(tcy[i], offy), cz = __fadd_rn(tcz[i], offz);
@@ -293,9 +304,10 @@ __global__ void __launch_bounds__(1024) integrate_forces_kernel(const float* __r
         }
     }
 }
-void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, cudaStream_t s) {
+void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, int tri_first, int tri_stride,
+                             cudaStream_t s) {
     integrate_forces_kernel<<<1, 1024, 0, s>>>(F.p, F.sx, F.sy, F.sz, M.cx, M.cy, M.cz, M.nx, M.ny, M.nz, M.area, M.n, offx, offy, offz,
-                                               (float)F.mc[0], (float)F.mc[1], (float)F.mc[2], F.d_acc);
+                                               (float)F.mc[0], (float)F.mc[1], (float)F.mc[2], tri_first, tri_stride, F.d_acc);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -21,6 +21,22 @@ namespace ludwig {
 constexpr int BS = 8;
 constexpr int BS3 = 512;
 constexpr int Q = 27;
+constexpr int MAX_RANKS = 8;
+// Neighbour-table encoding: -1 none | [0, nb) local block | [nb, REMOTE_BASE) ghost block nb+g | >= REMOTE_BASE remote
+// block (owned by another rank; REMOTE_BASE + index into the level's remote-offset tables).
+constexpr int32_t REMOTE_BASE = 1 << 30;
+// Block-pointer table encoding (coords -> block): -1 none | (owner_rank << 24) | owner_local_index.
+constexpr int PTR_RANK_SHIFT = 24;
+constexpr int32_t PTR_LOCAL_MASK = (1 << PTR_RANK_SHIFT) - 1;
+
+// Base pointers of one level's state on every rank (own memory for the calling rank, CUDA-IPC peer mappings for the
+// others), passed by value to the kernels that may touch blocks owned by another GPU.
+struct PeerPtrs {
+    const float* p[MAX_RANKS];
+};
+struct PeerBytes {
+    const uint8_t* p[MAX_RANKS];
+};
 
 // physics_v2.jl:99-117: k = (dx+1) + 3(dy+1) + 9(dz+1), dx fastest.
 __host__ __device__ constexpr int lat_cx(int k) { return k % 3 - 1; }
@@ -53,7 +69,21 @@ struct Level {
     bool temporal = false;
     bool has_children = false;
 
-    // permutation (host + device)
+    // partition (one process per GPU): blocks are cut into `world` contiguous ranges of the Morton curve
+    int nb_global = 0;
+    int part_start = 0;                    // global-internal index of local block 0
+    std::vector<int32_t> part_starts;      // [world+1]
+    std::vector<int32_t> remote_owner, remote_local;   // remote blocks referenced by local neighbour tables
+    int n_remote = 0;
+    long long* d_roff_f[2] = {nullptr, nullptr};   // per parity (index = parity of the INPUT buffer)
+    long long* d_roff_v[2] = {nullptr, nullptr};
+    // peer base pointers (index = rank); own pointers for this rank
+    const float* peer_f[2][MAX_RANKS] = {};
+    const float* peer_vel[2][MAX_RANKS] = {};
+    const float* peer_rho[2][MAX_RANKS] = {};
+    const uint8_t* peer_obstacle[MAX_RANKS] = {};
+
+    // permutation (host + device): GLOBAL internal (Morton) index <-> reference index
     std::vector<int32_t> ref2int, int2ref;
     int32_t* d_ref2int = nullptr;
     int32_t* d_int2ref = nullptr;
@@ -98,7 +128,7 @@ struct Level {
     int64_t last_t_sub = -1;   // parity of the most recent step (for implicit-old bookkeeping)
 
     // Bouzidi (compact)
-    bool bouzidi = false;
+    bool bouzidi = false;      // the LEVEL has Bouzidi cells (on some rank); n_bc counts the local ones
     int n_bc = 0;
     int32_t* d_bc_cell = nullptr;    // [n_bc] internal cell index  b*512 + z*64 + y*8 + x
     uint16_t* d_bc_q = nullptr;      // [n_bc][27] fp16 q values (compact copy of the dense q_map rows)
@@ -130,6 +160,11 @@ struct ludwig_ctx {
     double* d_stats = nullptr;   // flow-stats partials
     double* h_stats = nullptr;   // pinned
     int num_sms = 148;
+    int rank = 0, world = 1;
+    bool peers_attached = false;
+    void (*barrier_cb)(void*) = nullptr;   // cross-rank barrier, stream-ordered or blocking (multi-GPU only)
+    void* barrier_user = nullptr;
+    std::vector<void*> ipc_opened;
     int64_t launches = 0;
     // K1 profiling (ludwig_profile_enable)
     bool profiling = false;
@@ -149,8 +184,10 @@ struct K1Args {
     const int32_t* nbr; const int32_t* bcoord;
     const int32_t* list;   // internal block indices to process (nullptr = identity)
     int n_list;
-    int nb;                 // number of real blocks: neighbour indices >= nb address ghost blocks (fast mode only)
+    int nb;                 // number of local real blocks: see the neighbour-table encoding above
     long long ghost_delta;  // (f_ghost - f_in) in elements
+    const long long* roff_f;   // [n_remote] (peer f_in block base - local f_in) in elements, for this step's parity
+    const long long* roff_v;   // [n_remote] same for vel_in
     // parent (physics_v2.jl:43-53)
     const float *pf_new, *pf_old, *prho_new, *prho_old, *pvel_new, *pvel_old;
     const int32_t* pptr; int pdimx, pdimy, pdimz;
@@ -167,8 +204,8 @@ struct GhostArgs {
     int n;
     const int32_t* gcoord;   // [n_ghost][4] ghost block coords (0-based)
     float* f_ghost;          // [n_ghost][27][512]
-    const float *pf_new, *pf_old, *prho_new, *prho_old, *pvel_new, *pvel_old;
-    const int32_t* pptr; int pdimx, pdimy, pdimz;
+    PeerPtrs pf_new, pf_old, prho_new, prho_old, pvel_new, pvel_old;   // parent state per owning rank
+    const int32_t* pptr; int pdimx, pdimy, pdimz;                      // parent block pointer (rank-encoded)
     float tau, tau_parent, tw;
     int use_temporal;
 };
@@ -183,15 +220,16 @@ void launch_ghost_interp(const GhostArgs& g, cudaStream_t s);
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
 void launch_fill(float* p, float v, size_t n, cudaStream_t s);
-void launch_bouzidi(const Level& L, float* f_out, float q_min, bool strict, cudaStream_t s);
+void launch_bouzidi(const Level& L, float* f_out, const long long* roff_f_out, float q_min, bool strict, int phase, cudaStream_t s);
 void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
 void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_block_flags(Level& L, cudaStream_t s);
-void launch_map_stresses(const Level& L, const float* rho, const float* vel, const ludwig_mesh& M, ludwig_forces& F, float dx,
-                         float offx, float offy, float offz, float pscale, float sscale, int radius, cudaStream_t s);
-void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, cudaStream_t s);
+void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
+                         ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,
+                         int tri_first, int tri_stride, cudaStream_t s);
+void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx, float offy, float offz, int tri_first, int tri_stride, cudaStream_t s);
 void launch_flow_stats(const Level& L, const float* rho, const float* vel, double* d_partials, int nparts, cudaStream_t s);
 
 }  // namespace ludwig

@@ -830,6 +830,27 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
 }
 
 int64_t ludwig_device_bytes(const ludwig_ctx*) { return 0; }
+// multi-GPU entry points: the oracle is single-process; it only shares the (host-side) partition rule
+int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts) {
+    if (n_blocks < 0 || world < 1 || world > 8) return LUDWIG_EINVAL;
+    if (starts) for (int r = 0; r <= world; ++r) starts[r] = (int32_t)(((int64_t)n_blocks * r) / world);
+    return LUDWIG_OK;
+}
+int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
+    return (rank == 0 && world == 1) ? LUDWIG_OK : fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank");
+}
+int ludwig_set_barrier_callback(ludwig_ctx*, void (*)(void*), void*) { return LUDWIG_OK; }
+int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices) {
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return LUDWIG_EINVAL;
+    int nb = ctx->levels[level]->nb;
+    if (n_local) *n_local = nb;
+    if (ref_indices) for (int i = 0; i < nb; ++i) ref_indices[i] = i + 1;
+    return LUDWIG_OK;
+}
+int ludwig_level_upload_local(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src) { return ludwig_level_upload(ctx, level, which, src); }
+int ludwig_level_download_local(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst) { return ludwig_level_download(ctx, level, which, dst); }
+int ludwig_ipc_export(ludwig_ctx*, void*, int64_t, int64_t* needed) { if (needed) *needed = 0; return LUDWIG_OK; }
+int ludwig_ipc_attach(ludwig_ctx* ctx, const void*, int64_t) { return fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank"); }
 void* ludwig_ctx_stream(ludwig_ctx*) { return nullptr; }
 int64_t ludwig_launch_count(const ludwig_ctx*) { return 0; }
 int ludwig_profile_enable(ludwig_ctx*, int32_t) { return LUDWIG_OK; }
