@@ -6,8 +6,9 @@
 
 A "step" is one coarse time step of the whole hot path (K1 on every block of the level; the synthetic box has
 no Bouzidi cells or refinement) over a 512^3 single-level box with open x faces and periodic y/z — the
-configuration BASELINE.json's metric is quoted on.  Multi-GPU (N>1): one process per GPU, the box is replicated
-per rank (weak scaling, per-rank 512^3).  See DESIGN.md "Multi-GPU".
+configuration BASELINE.json's metric is quoted on.  Multi-GPU (N>1): one process per GPU, weak scaling: the box grows
+to (512 N) x 512 x 512 cells, the library partitions its blocks along a Morton curve and K1 pulls the halo blocks of
+other GPUs through NVLink peer mappings.  See DESIGN.md "Multi-GPU".
 
 Prints ONE JSON line (rank 0).
 """
@@ -38,37 +39,61 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the run (NVML; falls back to nvidia-smi)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        util = n.nvmlDeviceGetUtilizationRates(self.handle).gpu
+        return [str(sm), str(mx)] + ["Active" if f else "Not Active" for f in flags] + [util]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([s.strip() for s in out.split(",")] + [100])
             except Exception:
                 pass
-            self._stop_evt.wait(0.15)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        busy = [s for s in self.samples if s[6] and s[6] > 0] or self.samples      # samples taken under load
+        sm = sorted(int(s[0]) for s in busy if str(s[0]).isdigit())
+        mx = [int(s[1]) for s in self.samples if str(s[1]).isdigit()]
         reasons = set()
-        for s in self.samples:
+        for s in busy:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "samples_under_load": len(busy)}
 
 
 def make_params(cabi, n_cells_axis, strict):
@@ -119,31 +144,44 @@ def run_reference(args, rank, world):
 
 
 def run_ours(args, rank, local_rank, world):
+    import copy
     import torch
     import torch.distributed as dist
     from open_ludwig_b200 import cabi
+    from open_ludwig_b200 import multigpu as mg
     from open_ludwig_b200.host import synthetic as syn
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
+    # weak scaling: 512^3 cells (64^3 blocks) per GPU; the global box is (64 N) x 64 x 64 blocks and the library's
+    # Morton-range partition gives every rank one 64^3 cube (x is the most significant Morton digit here).
     nb = args.nb
     ncell_axis = nb * 8
-    lv = syn.make_box_level(nb, nb, nb)
-    p = make_params(cabi, ncell_axis, args.strict)
+    lv = syn.make_box_level(nb * world, nb, nb)
+    p = cabi.Params(c_wale=0.5, nu_sgs_bg=0.0005, inlet_turbulence=0.01, q_min_threshold=0.001, wall_model_active=0, use_temporal=0,
+                    sponge_blend=1, symmetric=0, domain_nx=ncell_axis * world, domain_ny=ncell_axis, domain_nz=ncell_axis, strict_fp=args.strict)
     ctx = cabi.Context(device=local_rank)
+    if world > 1:
+        ctx.set_partition(rank, world)
     ctx.add_level(lv)
-    # initial state: equilibrium of a hashed (rho,u) field, generated one x-slab of blocks
-    # at a time would need a partial-upload ABI; the full host arrays are 14.5 GB for 512^3, so build them once.
+    if world > 1:
+        mg.attach_peers(ctx, dev)
+    # initial state: equilibrium of a hashed (rho,u) field, generated for this rank's blocks only
     t0 = time.time()
-    f, rho, vel = syn.noise_state(lv)
-    ctx.upload(0, cabi.F, f); ctx.upload(0, cabi.F_TEMP, f)
-    ctx.upload(0, cabi.VEL, vel); ctx.upload(0, cabi.VEL_TEMP, vel); ctx.upload(0, cabi.RHO, rho)
+    loc = ctx.local_blocks(0)
+    mine = copy.copy(lv)
+    mine.active_block_coords = lv.active_block_coords[loc]
+    f, rho, vel = syn.noise_state(mine)
+    ctx.upload_local(0, cabi.F, f); ctx.upload_local(0, cabi.F_TEMP, f)
+    ctx.upload_local(0, cabi.VEL, vel); ctx.upload_local(0, cabi.VEL_TEMP, vel); ctx.upload_local(0, cabi.RHO, rho)
     del f, rho, vel
     setup_s = time.time() - t0
+    cells_per_rank = len(loc) * 512
 
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
@@ -151,20 +189,20 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()
     t = 1
+    barrier()
     ctx.step_batch(t, args.warmup, 0.03, p); t += args.warmup
     ctx.sync()
 
     # ---- timed region 1: device-resident throughput (value) + per-kernel timing of the dominant kernel
     ctx.profile_enable(True)
     n0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     ev0.record(stream)
     ctx.step_batch(t, args.steps, 0.03, p); t += args.steps
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - n0
     k_ms, k_launches, k_cells = ctx.profile_read()
@@ -177,34 +215,39 @@ def run_ours(args, rank, local_rank, world):
     stats = None
     for _ in range(args.steps):
         ctx.step_batch(t, 1, 0.03, p); t += 1
-        stats = ctx.flow_stats(0)          # D2H of the per-CTA partials + host reduction (syncs)
+        stats = ctx.flow_stats(0)          # device reduction + D2H of the per-CTA partials + host reduction (syncs)
+        if world > 1:
+            stats = mg.reduce_stats(stats, dev)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
 
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    ncell = torch.tensor([cells_per_rank], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ncell)
     ms_max, e2e_ms_max = float(times[0]), float(times[1])
-
-    cells_per_rank = lv.n_cells
-    mlups = cells_per_rank * world * args.steps / (ms_max * 1e-3) / 1e6
-    e2e_mlups = cells_per_rank * world * args.steps / (e2e_ms_max * 1e-3) / 1e6
+    total_cells = float(ncell[0])
+    mlups = total_cells * args.steps / (ms_max * 1e-3) / 1e6
+    e2e_mlups = total_cells * args.steps / (e2e_ms_max * 1e-3) / 1e6
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_avg_ms = k_ms / max(k_launches, 1)
         achieved = (k_cells / max(k_launches, 1)) * BYTES_PER_LU / (k_avg_ms * 1e-3) / 1e9 if k_launches else None
-        stats_parts = min(4096, max(1, min(148 * 8, (lv.n_cells + 255) // 256)))
+        stats_parts = min(4096, max(1, min(148 * 8, (cells_per_rank + 255) // 256)))
         line = {
             "metric": "MLUPS (D3Q27 FP32)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic uniform {ncell_axis}^3 D3Q27 box per GPU, single refinement level, inlet/outlet x + periodic y/z, "
-                                   "regularized-BGK + WALE (c_wale 0.5, nu_bg 5e-4, inlet turbulence 0.01)",
-                       "blocks": lv.n_blocks, "cells_per_gpu": cells_per_rank, "fp_mode": "strict" if args.strict else "fast",
-                       "l2": f"working set {ctx.device_bytes() / 1e9:.1f} GB >> 126 MB L2, no flush needed",
-                       "multi_gpu": "replicated box per rank (no halo exchange on this path yet)" if world > 1 else "single GPU"},
+            "config": {"workload": f"synthetic uniform {ncell_axis}^3 D3Q27 box per GPU ({ncell_axis * world}x{ncell_axis}x{ncell_axis} in total), single refinement "
+                                   "level, inlet/outlet x + periodic y/z, regularized-BGK + WALE (c_wale 0.5, nu_bg 5e-4, inlet turbulence 0.01)",
+                       "blocks_per_gpu": len(loc), "cells_per_gpu": cells_per_rank, "fp_mode": "strict" if args.strict else "fast",
+                       "l2": f"working set {ctx.device_bytes() / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
+                       "multi_gpu": ("Morton-range block partition, K1 pulls remote halo blocks over NVLink peer mappings (CUDA IPC), "
+                                     "one stream-ordered NCCL barrier per step") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_plain_kernel", "kernel_ms": k_avg_ms,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_fast_kernel<PLAIN> (rank 0)", "kernel_ms": k_avg_ms,
                          "bytes_per_lu": BYTES_PER_LU, "lu_per_launch": k_cells / max(k_launches, 1),
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": int(64), "d2h_bytes_per_step": int(stats_parts * 48),
@@ -218,6 +261,8 @@ def run_ours(args, rank, local_rank, world):
             c_mlups, cores, sample, _ = cpu_leg(args.cpu_nb, args.cpu_steps, 1)
             line["cpu_baseline"] = {"value": c_mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,94 @@
+"""N > 1 host logic on CPU: two gloo ranks (world_size 2) run the partition rule the library uses, agree on a disjoint
+cover, on symmetric halo ownership, and reduce per-rank flow statistics / partial forces exactly like bench.py and
+tools/mg_check.py do on the GPUs (open_ludwig_b200/multigpu.py).  The GPU side of the same path (bit-identical to the
+single-GPU run) is tools/mg_check.py, run with `gpurun --gpus 2`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from open_ludwig_b200 import cabi, partition
+from open_ludwig_b200.host import synthetic as syn
+
+PORT = 29631
+
+
+def test_partition_rule_matches_library(cuda_lib, oracle_lib):
+    """ludwig_partition_starts is host code: callable without a GPU, identical in both libraries and in the mirror."""
+    for path in (cuda_lib, oracle_lib):
+        lib = C.CDLL(path)
+        for n, w in ((96, 2), (1728, 8), (7, 3), (262144, 8)):
+            out = (C.c_int32 * (w + 1))()
+            assert lib.ludwig_partition_starts(n, w, out) == 0
+            assert list(out) == list(partition.partition_starts(n, w))
+        assert lib.ludwig_partition_starts(10, 9, None) != 0          # more than 8 ranks: rejected
+
+
+def test_bench_box_partition_gives_cubes():
+    """bench.py's weak-scaling box (64 N x 64 x 64 blocks): every rank's Morton range is one 64^3 cube
+    (checked at 1/8 scale: 8 N x 8 x 8)."""
+    for world in (2, 4, 8):
+        lv = syn.make_box_level(8 * world, 8, 8)
+        for r in range(world):
+            c = lv.active_block_coords[partition.local_blocks(lv.active_block_coords, r, world)]
+            assert len(c) == 512 and c[:, 0].min() == 8 * r + 1 and c[:, 0].max() == 8 * r + 8
+
+
+def _worker(rank, world, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(PORT))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from open_ludwig_b200 import multigpu as mg
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+        import test_k1_features_gpu as T
+        levels = T.build_case()
+        dev = torch.device("cpu")
+        for lv in levels:
+            mine = partition.local_blocks(lv.active_block_coords, rank, world)
+            # 1. disjoint cover, same order on every rank
+            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([len(mine)]))
+            pad = int(max(s.item() for s in sizes))
+            buf = torch.full((pad,), -1, dtype=torch.int64); buf[:len(mine)] = torch.from_numpy(mine.astype(np.int64))
+            allb = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(allb, buf)
+            cat = np.concatenate([b.numpy()[:int(s.item())] for b, s in zip(allb, sizes)])
+            assert sorted(cat.tolist()) == list(range(lv.n_blocks))
+            assert np.array_equal(cat, partition.morton_order(lv.active_block_coords))
+            # 2. halo symmetry: every remote block I pull from is owned by the peer, and the peer pulls from me too
+            rem = partition.remote_neighbours(lv.neighbor_table, lv.active_block_coords, rank, world)
+            own = partition.owner_of_ref(lv.active_block_coords, world)
+            assert np.all(own[rem] != rank) and len(rem) > 0
+            cnt = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(cnt, torch.tensor([len(rem)]))
+            assert all(int(c.item()) > 0 for c in cnt)
+        # 3. reductions: per-rank oracle statistics of the rank's own blocks combine to the statistics of the level
+        lib = tmp["oracle"]
+        lv = syn.make_box_level(4, 2, 2)
+        f, rho, vel = syn.noise_state(lv)
+        with cabi.Context(lib) as c:
+            c.add_level(lv); c.upload(0, cabi.RHO, rho); c.upload(0, cabi.VEL, vel)
+            whole = c.flow_stats(0)
+        mine = partition.local_blocks(lv.active_block_coords, rank, world)
+        sub = syn.make_box_level(len(mine), 1, 1)              # any level with the same number of blocks
+        with cabi.Context(lib) as c:
+            c.add_level(sub); c.upload(0, cabi.RHO, rho[mine]); c.upload(0, cabi.VEL, vel[:, mine])
+            part = c.flow_stats(0)
+        red = mg.reduce_stats(part, dev)
+        assert red["n_fluid"] == whole["n_fluid"] and red["rho_min"] == whole["rho_min"] and red["rho_max"] == whole["rho_max"]
+        assert red["v_max"] == whole["v_max"]
+        assert abs(red["rho_mean"] - whole["rho_mean"]) < 1e-12 and abs(red["kinetic_energy"] - whole["kinetic_energy"]) < 1e-9
+        aero = mg.reduce_aero({"Fx": 1.0 + rank, "Cd": 0.25 * (rank + 1)}, dev)
+        assert aero["Fx"] == sum(1.0 + r for r in range(world)) and aero["Cd"] == 0.25 * sum(r + 1 for r in range(world))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_plumbing(oracle_lib):
+    mp.spawn(_worker, args=(2, {"oracle": oracle_lib}), nprocs=2, join=True)
