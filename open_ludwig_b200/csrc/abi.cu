@@ -290,6 +290,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             launch_ghost_interp(g, ctx->stream);
             ctx->launches += 1;
         }
+        if (ctx->stream2 && L.n_full > 0) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));   // everything before this step
         a.list = L.d_list_plain; a.n_list = L.n_plain;
         const bool prof = ctx->profiling && L.n_plain > 0;
         if (prof) {
@@ -310,9 +311,19 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         a.list = L.d_list_plain_g; a.n_list = L.n_plain_g;
         launch_k1_plain_ghost(a, ctx->stream);
         if (L.n_plain_g > 0) ctx->launches += 1;
+        // The full-feature kernel is latency-bound on few blocks: run it on a second stream, concurrently with the
+        // two plain launches (all three only read f_in / vel_in and write disjoint blocks of f_out).
         a.list = L.d_list_full; a.n_list = L.n_full;
-        launch_k1_full(a, ctx->stream);
-        if (L.n_full > 0) ctx->launches += 1;
+        if (L.n_full > 0) {
+            const bool fork = ctx->stream2 != nullptr && (L.n_plain + L.n_plain_g) > 0;
+            if (fork) {
+                CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                launch_k1_full(a, ctx->stream2);
+                CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            } else launch_k1_full(a, ctx->stream);
+            ctx->launches += 1;
+        }
     }
     const bool mg = ctx->world > 1 && ctx->barrier_cb;
     if (L.bouzidi) {
@@ -364,6 +375,11 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
+    if (getenv("LUDWIG_TWO_STREAMS")) {   // opt-in: overlapping the full-feature kernel gained < 1.5 % (the step is HBM-bound) and blurs per-kernel timing
+        if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
+    }
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -383,6 +399,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) { cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     delete ctx;
     return LUDWIG_OK;
 }

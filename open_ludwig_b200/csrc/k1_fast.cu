@@ -44,7 +44,8 @@ __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ v2 vrcp(v2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
 __device__ __forceinline__ v2 vsqrt(v2 a) { return make_float2(sqrt_approx(a.x), sqrt_approx(a.y)); }
-__device__ __forceinline__ void st2(float* p, v2 v) { *reinterpret_cast<float2*>(p) = v; }
+// streaming store (st.global.cs): outputs are not re-read by this kernel, keep L2 for the halo sectors of f_in
+__device__ __forceinline__ void st2(float* p, v2 v) { __stcs(reinterpret_cast<float2*>(p), v); }
 __device__ __forceinline__ v2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
 constexpr float W0 = 8.0f / 27.0f, W1 = 2.0f / 27.0f, W2 = 1.0f / 54.0f, W3 = 1.0f / 216.0f;

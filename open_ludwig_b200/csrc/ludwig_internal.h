@@ -154,6 +154,8 @@ struct ludwig_forces {
 struct ludwig_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // concurrent launch of the full-feature K1 kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<ludwig::Level*> levels;
     std::string err;
     int64_t bytes = 0;
