@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BYTES_PER_LU = 216  # 27 x 4 B read + 27 x 4 B write
+# dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<PLAIN> per lattice update, from the ncu capture
+# profiles/r1c_dram_traffic_k1_256cube.csv: (2 090 983 680 + 1 903 583 488) B / (30 720 blocks x 512 cells)
+TRAFFIC_BYTES_PER_LU = (2090983680 + 1903583488) / (30720 * 512)
 
 
 def measured_peaks():
@@ -247,7 +250,9 @@ def run_ours(args, rank, local_rank, world):
                        "multi_gpu": ("Morton-range block partition, K1 pulls remote halo blocks over NVLink peer mappings (CUDA IPC), "
                                      "one stream-ordered NCCL barrier per step") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_fast_kernel<PLAIN> (rank 0)", "kernel_ms": k_avg_ms,
+                         "traffic": TRAFFIC_BYTES_PER_LU * k_cells / max(k_launches, 1) if k_launches else None,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per LU (profiles/r1c_dram_traffic_k1_256cube.csv) x LU per launch",
+                         "peak_source": peak_src, "kernel": "k1_fast_kernel<PLAIN> (rank 0)", "kernel_ms": k_avg_ms,
                          "bytes_per_lu": BYTES_PER_LU, "lu_per_launch": k_cells / max(k_launches, 1),
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": int(64), "d2h_bytes_per_step": int(stats_parts * 48),
