@@ -13,6 +13,8 @@
 #include <numeric>
 #include <unordered_map>
 
+#include <cuda_fp16.h>
+
 #include "ludwig_internal.h"
 
 using namespace ludwig;
@@ -60,9 +62,9 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_full,
+    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
-                    L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old, L->d_bc_cell, L->d_bc_q, L->d_bc_tmp};
+                    L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete L;
@@ -151,10 +153,10 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
     CU(cudaStreamSynchronize(ctx->stream));
     for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_list_plain,
-                    (void*)L.d_list_plain_g, (void*)L.d_list_full})
+                    (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full})
         if (q) cudaFree(q);
     L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr;
-    L.d_list_plain = L.d_list_plain_g = L.d_list_full = nullptr;
+    L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = nullptr;
     const int nb = L.nb;
     const int scale = 1 << (L.level_id - 1);
     const int ext[3] = {p.domain_nx * scale / BS, p.domain_ny * scale / BS, p.domain_nz * scale / BS};   // blocks per axis
@@ -202,7 +204,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         }
     }
     // K1 work lists
-    std::vector<int32_t> lp, lg, lf;
+    std::vector<int32_t> lp, lg, le, lf;
     for (int b = 0; b < nb; ++b) {
         bool all = true, ghost = false;
         for (int d = 0; d < 27; ++d) {
@@ -210,10 +212,12 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
             if (v < 0) all = false; else if (v >= nb && v < REMOTE_BASE) ghost = true;
         }
         const uint32_t feat = (uint32_t)L.h_bcoord[(size_t)b * 4 + 3] & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
-        if (all && !feat) (ghost ? lg : lp).push_back(b); else lf.push_back(b);
+        if (all && !feat) (ghost ? lg : lp).push_back(b);
+        else if (all) le.push_back(b);
+        else lf.push_back(b);
     }
     L.n_ghost = ng; L.n_gcell = (int)gcell.size();
-    L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_full = (int)lf.size();
+    L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_feat = (int)le.size(); L.n_full = (int)lf.size();
     CU(dalloc(ctx, &L.d_nbr_fast, nbrf.size()));
     CU(memcpy_sync(ctx->stream, L.d_nbr_fast, nbrf.data(), nbrf.size() * 4, cudaMemcpyHostToDevice));
     if (ng > 0) {
@@ -226,7 +230,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
             CU(memcpy_sync(ctx->stream, L.d_gmask, gmask.data(), gmask.size() * 4, cudaMemcpyHostToDevice));
         }
     }
-    struct { std::vector<int32_t>* v; int32_t** d; } lists[3] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&lf, &L.d_list_full}};
+    struct { std::vector<int32_t>* v; int32_t** d; } lists[4] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}};
     for (auto& l : lists) {
         CU(dalloc(ctx, l.d, l.v->size()));
         if (!l.v->empty()) CU(memcpy_sync(ctx->stream, *l.d, l.v->data(), l.v->size() * 4, cudaMemcpyHostToDevice));
@@ -234,6 +238,32 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     CU(cudaStreamSynchronize(ctx->stream));
     L.fast_dom[0] = p.domain_nx; L.fast_dom[1] = p.domain_ny; L.fast_dom[2] = p.domain_nz;
     L.fast_ready = true;
+    return LUDWIG_OK;
+}
+
+// Active Bouzidi links of the local boundary cells for a given q_min (bouzidi_kernel.jl:36-38: q > q_min && q <= 1).
+int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
+    if (L.links_qmin == q_min) return LUDWIG_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void* q : {(void*)L.d_link_cell, (void*)L.d_link_k, (void*)L.d_link_q, (void*)L.d_link_tmp})
+        if (q) cudaFree(q);
+    L.d_link_cell = nullptr; L.d_link_k = nullptr; L.d_link_q = nullptr; L.d_link_tmp = nullptr;
+    std::vector<int32_t> lc; std::vector<uint8_t> lk; std::vector<float> lq;
+    for (int i = 0; i < L.n_bc; ++i)
+        for (int k = 0; k < 27; ++k) {
+            __half_raw hr; hr.x = L.h_bc_q[(size_t)i * 27 + k];
+            const float q = __half2float(__half(hr));
+            if (q > q_min && q <= 1.0f) { lc.push_back(L.h_bc_cell[i]); lk.push_back((uint8_t)k); lq.push_back(q); }
+        }
+    L.n_links = (int)lc.size();
+    if (L.n_links > 0) {
+        CU(dalloc(ctx, &L.d_link_cell, lc.size())); CU(dalloc(ctx, &L.d_link_k, lk.size())); CU(dalloc(ctx, &L.d_link_q, lq.size()));
+        CU(dalloc(ctx, &L.d_link_tmp, lq.size()));
+        CU(memcpy_sync(ctx->stream, L.d_link_cell, lc.data(), lc.size() * 4, cudaMemcpyHostToDevice));
+        CU(memcpy_sync(ctx->stream, L.d_link_k, lk.data(), lk.size(), cudaMemcpyHostToDevice));
+        CU(memcpy_sync(ctx->stream, L.d_link_q, lq.data(), lq.size() * 4, cudaMemcpyHostToDevice));
+    }
+    L.links_qmin = q_min;
     return LUDWIG_OK;
 }
 
@@ -290,8 +320,25 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             launch_ghost_interp(g, ctx->stream);
             ctx->launches += 1;
         }
-        if (ctx->stream2 && L.n_full > 0) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));   // everything before this step
-        a.list = L.d_list_plain; a.n_list = L.n_plain;
+        // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
+        // levels, where each of them is a few waves of latency-bound CTAs, they run concurrently on side streams.
+        const bool fork = ctx->side[0] != nullptr && L.nb <= ctx->fork_max_blocks;
+        int used = 0;
+        if (fork) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream) -> int {
+            if (n <= 0) return LUDWIG_OK;
+            a.list = list; a.n_list = n;
+            if (!fork || main_stream) fn(a, ctx->stream);
+            else {
+                cudaStream_t st = ctx->side[used];
+                CU(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+                fn(a, st);
+                CU(cudaEventRecord(ctx->ev_join[used], st));
+                ++used;
+            }
+            ctx->launches += 1;
+            return LUDWIG_OK;
+        };
         const bool prof = ctx->profiling && L.n_plain > 0;
         if (prof) {
             if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
@@ -301,39 +348,28 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             }
             CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
         }
-        launch_k1_plain(a, ctx->stream);
+        if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true))) return rc;
         if (prof) {
             CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
             ctx->ev_used += 2;
             ctx->prof_cells += (int64_t)L.n_plain * BS3;
         }
-        if (L.n_plain > 0) ctx->launches += 1;
-        a.list = L.d_list_plain_g; a.n_list = L.n_plain_g;
-        launch_k1_plain_ghost(a, ctx->stream);
-        if (L.n_plain_g > 0) ctx->launches += 1;
-        // The full-feature kernel is latency-bound on few blocks: run it on a second stream, concurrently with the
-        // two plain launches (all three only read f_in / vel_in and write disjoint blocks of f_out).
-        a.list = L.d_list_full; a.n_list = L.n_full;
-        if (L.n_full > 0) {
-            const bool fork = ctx->stream2 != nullptr && (L.n_plain + L.n_plain_g) > 0;
-            if (fork) {
-                CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-                launch_k1_full(a, ctx->stream2);
-                CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
-                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-            } else launch_k1_full(a, ctx->stream);
-            ctx->launches += 1;
-        }
+        if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0))) return rc;
+        if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0))) return rc;
+        if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0))) return rc;
+        for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
     }
     const bool mg = ctx->world > 1 && ctx->barrier_cb;
     if (L.bouzidi) {
         // K2 reads f_out of x_ff cells that may belong to another GPU: K1 must be complete everywhere before the
         // gather, and every gather before any scatter (the same two-phase argument as on one GPU, across ranks).
         if (mg) ctx->barrier_cb(ctx->barrier_user);
-        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.q_min_threshold, p.strict_fp != 0, 1, ctx->stream);
+        int rcb = ensure_bouzidi_links(ctx, L, p.q_min_threshold);
+        if (rcb) return rcb;
+        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 1, ctx->stream);
         if (mg) ctx->barrier_cb(ctx->barrier_user);
-        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.q_min_threshold, p.strict_fp != 0, 2, ctx->stream);
-        if (L.n_bc > 0) ctx->launches += 2;
+        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 2, ctx->stream);
+        if (L.n_links > 0) ctx->launches += 2;
     }
     if (mg) ctx->barrier_cb(ctx->barrier_user);   // every rank finished this level step
     L.rho_cur = rho_out;
@@ -375,10 +411,13 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
-    if (getenv("LUDWIG_TWO_STREAMS")) {   // opt-in: overlapping the full-feature kernel gained < 1.5 % (the step is HBM-bound) and blurs per-kernel timing
-        if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
+    if (!getenv("LUDWIG_SINGLE_STREAM")) {
+        bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 3 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { delete ctx; return LUDWIG_ECUDA; }
+        if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
@@ -399,7 +438,8 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
-    if (ctx->stream2) { cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 3; ++i) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     delete ctx;
     return LUDWIG_OK;
 }
@@ -572,11 +612,7 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
             for (int k = 0; k < 27; ++k) q.push_back(d->q_map_f16[(size_t)br * BS3 + loc + ncg * k]);
         }
         L.n_bc = (int)cells.size();
-        if (L.n_bc > 0) {
-            CU(dalloc(ctx, &L.d_bc_cell, cells.size())); CU(dalloc(ctx, &L.d_bc_q, q.size())); CU(dalloc(ctx, &L.d_bc_tmp, q.size()));
-            CU(memcpy_sync(ctx->stream, L.d_bc_cell, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
-            CU(memcpy_sync(ctx->stream, L.d_bc_q, q.data(), q.size() * 2, cudaMemcpyHostToDevice));
-        }
+        L.h_bc_cell = std::move(cells); L.h_bc_q = std::move(q);
     }
 
     // --- per-block feature flags (obstacle / sponge / near-wall); the fast-mode work lists are built lazily

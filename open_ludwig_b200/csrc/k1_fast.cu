@@ -6,9 +6,9 @@
 //          every large level).  The regularized collision needs only the 10 moments rho, j, sum f c c — not the
 //          27 populations — so loads are streamed straight into the moment accumulators and no f[27] array
 //          lives in registers.
-//   FULL   every other block: missing neighbours (domain faces, refinement interfaces -> k1_boundary.cuh),
-//          obstacle cells (full-way bounce-back), sponge blending, wall-model force.  Keeps f[27] because
-//          bounce-back returns the pulled populations.  Per-block flag bits gate each feature uniformly.
+//   FULL   every other block (two instantiations, with / without missing-neighbour handling): missing neighbours (domain faces, refinement interfaces -> k1_boundary.cuh),
+//          obstacle cells (full-way bounce-back), sponge blending, wall-model force:
+//          bounce-back returns the pulled populations (re-pulled at the end, solid cells skip the collision).  Per-block flag bits gate each feature uniformly.
 //
 // Arithmetic (fast mode = FMA on, sums regrouped; parity is carried by the strict build):
 //   * opposite directions are paired: s_k = f_k + f_(26-k), d_k = f_k - f_(26-k), k = 0..12;
@@ -23,6 +23,7 @@
 // stores are 64-bit accesses; a warp is one z-plane (64 cells), a CTA (256 threads) one 8^3 block; CTAs walk
 // the blocks in Morton order so that halo sectors are L2 hits.
 #include <climits>
+#include <cstdlib>
 
 #include "ludwig_internal.h"
 
@@ -210,8 +211,10 @@ constexpr long long MISSING = LLONG_MIN;
 
 // FULL : see file header.   VELFB : some axis neighbour may lack a velocity field (ghost block or domain face) ->
 // fall back to the cell's own value (physics_utils.jl:69).
-template <bool FULL, bool VELFB>
-__global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args a) {
+//        MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh; blocks with features but all 26
+//        neighbours present (the near-body bulk) use FULL without MISS and never carry that code.
+template <bool FULL, bool VELFB, bool MISS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
     __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
     __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
     const int b = a.list[blockIdx.x];
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
     if (FULL) {
         const int4 bc = *reinterpret_cast<const int4*>(a.bcoord + (size_t)b * 4);
         bflags = (uint32_t)bc.w;
-        gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1;
+        if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
     const float* __restrict__ fin_own = a.f_in + (size_t)b * (Q * BS3) + c0;   // own cell A, direction 0
 
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         const int dir = zdir[jz] + ydir[jy];
         const int k0 = 1 + 3 * jy + 9 * jz, kp = k0 + 1, km = k0 - 1;
         const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
-        if (!FULL || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
+        if (!MISS || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
             const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
             const float* __restrict__ PM = a.f_in + oM + (loc + xM);
             const float* __restrict__ PP = a.f_in + oP + (loc + xP);
@@ -281,9 +284,44 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         }
     };
 
+    bool obsA = false, obsB = false;
+    if (FULL && (bflags & BF_OBSTACLE)) {
+        const uchar2 o = *reinterpret_cast<const uchar2*>(a.obstacle + (size_t)b * BS3 + c0);
+        obsA = o.x != 0; obsB = o.y != 0;
+    }
+    float* __restrict__ fout = a.f_out + (size_t)b * (Q * BS3) + c0;
+    float* __restrict__ vout = a.vel_out + (size_t)b * (3 * BS3) + c0;
+    float* __restrict__ rout = a.rho_out + (size_t)b * BS3 + c0;
+
+    // Full-way bounce-back (physics_kernels.jl:154-166): an obstacle cell returns every pulled population in the
+    // opposite direction, f_out[26-k] = pulled f_k.  No arithmetic: pull again and store (4-byte stores into the
+    // obstacle cell only).  Threads whose two cells are both solid do nothing else — solid blocks are a pure copy.
+    auto bounce_back = [&]() {
+#pragma unroll
+        for (int jz = 0; jz < 3; ++jz) {
+#pragma unroll
+            for (int jy = 0; jy < 3; ++jy) {
+                v2 fm, f0, fp;
+                pull3(jy, jz, fm, f0, fp);
+                const int k0 = 1 + 3 * jy + 9 * jz;
+                if (obsA && obsB) {
+                    st2(fout + (26 - (k0 - 1)) * BS3, fm); st2(fout + (26 - k0) * BS3, f0); st2(fout + (26 - (k0 + 1)) * BS3, fp);
+                } else if (obsA) {
+                    fout[(26 - (k0 - 1)) * BS3] = fm.x; fout[(26 - k0) * BS3] = f0.x; fout[(26 - (k0 + 1)) * BS3] = fp.x;
+                } else {
+                    fout[(26 - (k0 - 1)) * BS3 + 1] = fm.y; fout[(26 - k0) * BS3 + 1] = f0.y; fout[(26 - (k0 + 1)) * BS3 + 1] = fp.y;
+                }
+            }
+        }
+    };
+    if (FULL && obsA && obsB) {
+        bounce_back();
+        st2(vout, V(0.f)); st2(vout + BS3, V(0.f)); st2(vout + 2 * BS3, V(0.f)); st2(rout, V(1.0f));
+        return;
+    }
+
     Moments m;
     m.jx = m.jy = m.jz = m.Pxx = m.Pyy = m.Pzz = m.Pxy = m.Pyz = m.Pzx = V(0.f);
-    v2 f[FULL ? 27 : 1];
     {
         // combos c = jy + 3 jz; combo c and 8-c hold opposite directions: (km,k0,kp)(c) <-> (kp,k0,km)(8-c)
         v2 am, a0, ap, bm, b0, bp;
@@ -294,17 +332,12 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
         // consistent with its feq (sum_k w_k c_a c_b = (1 + eps) delta/3).
         m.rho = vadd(vadd(a0, V(-W0)), V(7.4505806e-9f));
         acc_pair<12>(m, am, ap);
-        if (FULL) { f[12] = am; f[13] = a0; f[14] = ap; }
 #define LUDWIG_COMBO(JY, JZ)                                                   \
         pull3(JY, JZ, am, a0, ap);                                             \
         pull3(2 - (JY), 2 - (JZ), bm, b0, bp);                                 \
         acc_pair<3 * (JY) + 9 * (JZ)>(m, am, bp);                              \
         acc_pair<3 * (JY) + 9 * (JZ) + 1>(m, a0, b0);                          \
-        acc_pair<3 * (JY) + 9 * (JZ) + 2>(m, ap, bm);                          \
-        if (FULL) {                                                            \
-            f[3 * (JY) + 9 * (JZ)] = am; f[3 * (JY) + 9 * (JZ) + 1] = a0; f[3 * (JY) + 9 * (JZ) + 2] = ap; \
-            f[26 - (3 * (JY) + 9 * (JZ))] = bp; f[26 - (3 * (JY) + 9 * (JZ) + 1)] = b0; f[26 - (3 * (JY) + 9 * (JZ) + 2)] = bm; \
-        }
+        acc_pair<3 * (JY) + 9 * (JZ) + 2>(m, ap, bm);
         LUDWIG_COMBO(0, 0)
         LUDWIG_COMBO(1, 0)
         LUDWIG_COMBO(2, 0)
@@ -332,16 +365,6 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
             uT[cpt] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + cpt * BS3) : own;
             uB[cpt] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + cpt * BS3) : own;
         }
-    }
-
-    float* __restrict__ fout = a.f_out + (size_t)b * (Q * BS3) + c0;
-    float* __restrict__ vout = a.vel_out + (size_t)b * (3 * BS3) + c0;
-    float* __restrict__ rout = a.rho_out + (size_t)b * BS3 + c0;
-
-    bool obsA = false, obsB = false;
-    if (FULL && (bflags & BF_OBSTACLE)) {
-        const uchar2 o = *reinterpret_cast<const uchar2*>(a.obstacle + (size_t)b * BS3 + c0);
-        obsA = o.x != 0; obsB = o.y != 0;
     }
 
     v2 rho = vmax(vadd(m.rho, V(1.0f)), 0.01f);     // :172
@@ -481,36 +504,36 @@ __global__ void __launch_bounds__(256, FULL ? 2 : 3) k1_fast_kernel(const K1Args
             odd = vfma(hw, cF, odd);
         }
         even = vmul(even, V(w)); odd = vmul(odd, V(w));
-        v2 outk = vadd(even, odd), outo = vsub(even, odd);
-        if (FULL && (obsA || obsB)) {                     // full-way bounce-back (:154-166)
-            outk = make_float2(obsA ? f[26 - k].x : outk.x, obsB ? f[26 - k].y : outk.y);
-            outo = make_float2(obsA ? f[k].x : outo.x, obsB ? f[k].y : outo.y);
-        }
-        st2(fout + k * BS3, outk);
-        st2(fout + (26 - k) * BS3, outo);
+        st2(fout + k * BS3, vadd(even, odd));
+        st2(fout + (26 - k) * BS3, vsub(even, odd));
     }
     {
         v2 even = vfma(g, vneg(T), A);
         if (FULL && has_force) even = vfma(hw, vneg(uF), even);
         even = vmul(even, V(W0));
-        if (FULL && (obsA || obsB)) even = make_float2(obsA ? f[13].x : even.x, obsB ? f[13].y : even.y);
         st2(fout + 13 * BS3, even);
     }
+    if (FULL && (obsA || obsB)) bounce_back();   // overwrite the one obstacle cell of this thread
 }
 
 }  // namespace k1f
 
 void launch_k1_plain(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<false, false><<<a.n_list, 256, 0, s>>>(a);
+    k1f::k1_fast_kernel<false, false, false, 3><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<false, true><<<a.n_list, 256, 0, s>>>(a);
+    k1f::k1_fast_kernel<false, true, false, 3><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_k1_feat(const K1Args& a, cudaStream_t s) {
+    if (a.n_list <= 0) return;
+    // 80 registers / 3 CTAs per SM measured +12 % over 127 registers / 2 CTAs on Wing_5_deg (A/B on one box)
+    k1f::k1_fast_kernel<true, true, false, 3><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1_full(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<true, true><<<a.n_list, 256, 0, s>>>(a);
+    k1f::k1_fast_kernel<true, true, true, 2><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_ghost_interp(const GhostArgs& g, cudaStream_t s) {
     if (g.n <= 0) return;

@@ -116,67 +116,64 @@ void launch_block_flags(Level& L, cudaStream_t s) {
 // K1) and overwrites f_out in place.  Before K2 runs, f_post_collision == f_out bit for bit
 // (physics_kernels.jl:350-353), so here phase A gathers every correction from f_out into a compact
 // [n_bc][27] buffer and phase B scatters them — same values, no dense array, no read/write hazard.
+// One thread per ACTIVE link (q in (q_min, 1], compacted on the host when q_min is first seen): the reference's
+// thread-per-cell loop over 27 mostly inactive directions (bouzidi_kernel.jl:35-38) becomes a dense list.
 template <bool STRICT>
-__global__ void bouzidi_gather_kernel(const float* __restrict__ f_out, const int32_t* __restrict__ bc_cell,
-                                      const uint16_t* __restrict__ bc_q, const int32_t* __restrict__ nbr,
-                                      const long long* __restrict__ roff, float* __restrict__ tmp, int n_bc, float q_min) {
+__global__ void bouzidi_gather_kernel(const float* __restrict__ f_out, const int32_t* __restrict__ link_cell,
+                                      const uint8_t* __restrict__ link_k, const float* __restrict__ link_q,
+                                      const int32_t* __restrict__ nbr, const long long* __restrict__ roff,
+                                      float* __restrict__ tmp, int n_links) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_bc * 27) return;
-    int ci = i / 27, k = i - ci * 27;
-    float q = __half2float(__ushort_as_half(bc_q[i]));
-    float res = __int_as_float(0x7fc00000);   // NaN = "link inactive"
-    if (q > q_min && q <= 1.0f) {
-        int cell = bc_cell[ci];
-        int b = cell >> 9, c = cell & 511;
-        int x = c & 7, y = (c >> 3) & 7, z = c >> 6;
-        int opp_k = 26 - k;
-        const float* fb = f_out + (size_t)b * Q * BS3;
-        float f_k = fb[k * BS3 + c];
-        if (q < 0.5f) {
-            int cx = k % 3 - 1, cy = (k / 3) % 3 - 1, cz = k / 9 - 1;
-            int nx = x - cx, ny = y - cy, nz = z - cz;   // x + c_opp(k)
-            float f_ff = f_k;
-            if (((nx | ny | nz) & ~7) == 0) {
-                f_ff = fb[k * BS3 + nz * 64 + ny * 8 + nx];
-            } else {
-                int ox = nx < 0 ? -1 : (nx > 7 ? 1 : 0), oy = ny < 0 ? -1 : (ny > 7 ? 1 : 0), oz = nz < 0 ? -1 : (nz > 7 ? 1 : 0);
-                int nbi = nbr[(size_t)b * 27 + (ox + 1) + (oy + 1) * 3 + (oz + 1) * 9];
-                const int lc = (nz & 7) * 64 + (ny & 7) * 8 + (nx & 7);
-                if (nbi >= REMOTE_BASE) f_ff = f_out[roff[nbi - REMOTE_BASE] + k * BS3 + lc];   // block owned by another GPU
-                else if (nbi >= 0) f_ff = f_out[((size_t)nbi * Q + k) * BS3 + lc];
-            }
-            float coeff1 = 2.0f * q;
-            if (STRICT) res = __fadd_rn(__fmul_rn(coeff1, f_k), __fmul_rn(__fsub_rn(1.0f, coeff1), f_ff));
-            else res = coeff1 * f_k + (1.0f - coeff1) * f_ff;
+    if (i >= n_links) return;
+    const float q = link_q[i];
+    const int k = link_k[i];
+    const int cell = link_cell[i];
+    const int b = cell >> 9, c = cell & 511;
+    const float* fb = f_out + (size_t)b * Q * BS3;
+    const float f_k = fb[k * BS3 + c];
+    float res;
+    if (q < 0.5f) {
+        const int x = c & 7, y = (c >> 3) & 7, z = c >> 6;
+        const int cx = k % 3 - 1, cy = (k / 3) % 3 - 1, cz = k / 9 - 1;
+        const int nx = x - cx, ny = y - cy, nz = z - cz;   // x_ff = x + c_opp(k)
+        float f_ff = f_k;
+        if (((nx | ny | nz) & ~7) == 0) {
+            f_ff = fb[k * BS3 + nz * 64 + ny * 8 + nx];
         } else {
-            float f_opp_post = fb[opp_k * BS3 + c];
-            float inv_2q = 1.0f / (2.0f * q);
-            float coeff2 = __fmul_rn(__fsub_rn(__fmul_rn(2.0f, q), 1.0f), inv_2q);
-            if (STRICT) res = __fadd_rn(__fmul_rn(inv_2q, f_k), __fmul_rn(coeff2, f_opp_post));
-            else res = inv_2q * f_k + coeff2 * f_opp_post;
+            int ox = nx < 0 ? -1 : (nx > 7 ? 1 : 0), oy = ny < 0 ? -1 : (ny > 7 ? 1 : 0), oz = nz < 0 ? -1 : (nz > 7 ? 1 : 0);
+            int nbi = nbr[(size_t)b * 27 + (ox + 1) + (oy + 1) * 3 + (oz + 1) * 9];
+            const int lc = (nz & 7) * 64 + (ny & 7) * 8 + (nx & 7);
+            if (nbi >= REMOTE_BASE) f_ff = f_out[roff[nbi - REMOTE_BASE] + k * BS3 + lc];   // block owned by another GPU
+            else if (nbi >= 0) f_ff = f_out[((size_t)nbi * Q + k) * BS3 + lc];
         }
+        const float coeff1 = 2.0f * q;
+        if (STRICT) res = __fadd_rn(__fmul_rn(coeff1, f_k), __fmul_rn(__fsub_rn(1.0f, coeff1), f_ff));
+        else res = coeff1 * f_k + (1.0f - coeff1) * f_ff;
+    } else {
+        const float f_opp_post = fb[(26 - k) * BS3 + c];
+        const float inv_2q = 1.0f / (2.0f * q);
+        const float coeff2 = __fmul_rn(__fsub_rn(__fmul_rn(2.0f, q), 1.0f), inv_2q);
+        if (STRICT) res = __fadd_rn(__fmul_rn(inv_2q, f_k), __fmul_rn(coeff2, f_opp_post));
+        else res = inv_2q * f_k + coeff2 * f_opp_post;
     }
     tmp[i] = res;
 }
-__global__ void bouzidi_scatter_kernel(float* __restrict__ f_out, const int32_t* __restrict__ bc_cell, const float* __restrict__ tmp, int n_bc) {
+__global__ void bouzidi_scatter_kernel(float* __restrict__ f_out, const int32_t* __restrict__ link_cell,
+                                       const uint8_t* __restrict__ link_k, const float* __restrict__ tmp, int n_links) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_bc * 27) return;
-    float v = tmp[i];
-    if (v != v) return;
-    int ci = i / 27, k = i - ci * 27;
-    int cell = bc_cell[ci];
-    f_out[((size_t)(cell >> 9) * Q + (26 - k)) * BS3 + (cell & 511)] = v;
+    if (i >= n_links) return;
+    const int cell = link_cell[i];
+    f_out[((size_t)(cell >> 9) * Q + (26 - link_k[i])) * BS3 + (cell & 511)] = tmp[i];
 }
 // phase 1 = gather, 2 = scatter, 0 = both (multi-GPU runs them separately with a cross-rank barrier in between)
-void launch_bouzidi(const Level& L, float* f_out, const long long* roff, float q_min, bool strict, int phase, cudaStream_t s) {
-    if (!L.bouzidi || L.n_bc == 0) return;
-    int n = L.n_bc * 27;
-    unsigned grid = (n + 255) / 256;
+void launch_bouzidi(const Level& L, float* f_out, const long long* roff, bool strict, int phase, cudaStream_t s) {
+    if (L.n_links == 0) return;
+    unsigned grid = (L.n_links + 255) / 256;
     if (phase != 2) {
-        if (strict) bouzidi_gather_kernel<true><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, roff, L.d_bc_tmp, L.n_bc, q_min);
-        else bouzidi_gather_kernel<false><<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_q, L.d_nbr, roff, L.d_bc_tmp, L.n_bc, q_min);
+        if (strict) bouzidi_gather_kernel<true><<<grid, 256, 0, s>>>(f_out, L.d_link_cell, L.d_link_k, L.d_link_q, L.d_nbr, roff, L.d_link_tmp, L.n_links);
+        else bouzidi_gather_kernel<false><<<grid, 256, 0, s>>>(f_out, L.d_link_cell, L.d_link_k, L.d_link_q, L.d_nbr, roff, L.d_link_tmp, L.n_links);
     }
-    if (phase != 1) bouzidi_scatter_kernel<<<grid, 256, 0, s>>>(f_out, L.d_bc_cell, L.d_bc_tmp, L.n_bc);
+    if (phase != 1) bouzidi_scatter_kernel<<<grid, 256, 0, s>>>(f_out, L.d_link_cell, L.d_link_k, L.d_link_tmp, L.n_links);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -107,8 +107,9 @@ struct Level {
     int n_gcell = 0;
     int32_t* d_list_plain = nullptr;     // all 26 neighbours real, no feature flag
     int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
-    int32_t* d_list_full = nullptr;      // the rest
-    int n_plain = 0, n_plain_g = 0, n_full = 0;
+    int32_t* d_list_feat = nullptr;      // all 26 neighbours present, some feature flag
+    int32_t* d_list_full = nullptr;      // some neighbour missing (domain face)
+    int n_plain = 0, n_plain_g = 0, n_feat = 0, n_full = 0;
 
     // static fields (device)
     uint8_t* d_obstacle = nullptr;  // [nb][512]
@@ -130,9 +131,15 @@ struct Level {
     // Bouzidi (compact)
     bool bouzidi = false;      // the LEVEL has Bouzidi cells (on some rank); n_bc counts the local ones
     int n_bc = 0;
-    int32_t* d_bc_cell = nullptr;    // [n_bc] internal cell index  b*512 + z*64 + y*8 + x
-    uint16_t* d_bc_q = nullptr;      // [n_bc][27] fp16 q values (compact copy of the dense q_map rows)
-    float* d_bc_tmp = nullptr;       // [n_bc][27] gathered corrections (two-phase K2)
+    std::vector<int32_t> h_bc_cell;  // [n_bc] internal cell index  b*512 + z*64 + y*8 + x
+    std::vector<uint16_t> h_bc_q;    // [n_bc][27] fp16 q values (the boundary cells' rows of the dense q_map)
+    // active links (q in (q_min, 1]), compacted when ludwig_params.q_min_threshold is first seen
+    float links_qmin = -1.0f;
+    int n_links = 0;
+    int32_t* d_link_cell = nullptr;  // [n_links]
+    uint8_t* d_link_k = nullptr;     // [n_links] direction k
+    float* d_link_q = nullptr;       // [n_links] q as FP32
+    float* d_link_tmp = nullptr;     // [n_links] gathered corrections (two-phase K2)
 };
 
 }  // namespace ludwig
@@ -154,8 +161,9 @@ struct ludwig_forces {
 struct ludwig_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;          // concurrent launch of the full-feature K1 kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // concurrent K1 launches of one level step on small levels
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
     std::vector<ludwig::Level*> levels;
     std::string err;
     int64_t bytes = 0;
@@ -216,13 +224,14 @@ struct GhostArgs {
 // some neighbours are ghost blocks; full = every other block
 void launch_k1_plain(const K1Args& a, cudaStream_t s);
 void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s);
-void launch_k1_full(const K1Args& a, cudaStream_t s);
+void launch_k1_feat(const K1Args& a, cudaStream_t s);   // features (obstacle/sponge/wall model), all 26 neighbours present
+void launch_k1_full(const K1Args& a, cudaStream_t s);   // features + missing neighbours (domain faces)
 void launch_ghost_interp(const GhostArgs& g, cudaStream_t s);
 
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
 void launch_fill(float* p, float v, size_t n, cudaStream_t s);
-void launch_bouzidi(const Level& L, float* f_out, const long long* roff_f_out, float q_min, bool strict, int phase, cudaStream_t s);
+void launch_bouzidi(const Level& L, float* f_out, const long long* roff_f_out, bool strict, int phase, cudaStream_t s);
 void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
 void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
