@@ -22,6 +22,8 @@ CASE_OVERRIDES = {
                                  "advanced": {"diagnostics": {"freq": 100}}}),
     "wing5": ("Wing_5_deg", None),
     "bunny": ("Stanford_bunny", None),
+    # config 5: the bunny scaled to fine resolution: 6 levels, 339 M cells, 9.4 G cell-updates per coarse step
+    "bunny_fine": ("Stanford_bunny", {"basic": {"surface_resolution": 1300, "num_levels": 6}}),
 }
 
 

@@ -135,7 +135,8 @@ def build_neighbor_table(coords: np.ndarray, dims) -> tuple:
 
 # ---- domain.jl ----------------------------------------------------------------------------------------
 
-def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, verbose: bool = False) -> Domain:
+def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, verbose: bool = False,
+                            build_tri_map: bool = True) -> Domain:
     """domain.jl:20-280."""
     lib = host_lib()
     if mesh is None:
@@ -219,13 +220,15 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
             assert got == n_bc
             cells, qv, tv = cells[:n_bc], qv[:n_bc], tv[:n_bc]
             q_map = np.zeros((27, nb, 8, 8, 8), np.float16)
-            tri_map = np.zeros((27, nb, 8, 8, 8), np.int32)
+            # tri_map (bouzidi_setup.jl:85) is never read by a kernel: 108 B/cell of host memory, optional for huge levels
+            tri_map = np.zeros((27, nb, 8, 8, 8), np.int32) if build_tri_map else None
             b, x, y, z = cells[:, 0] - 1, cells[:, 1] - 1, cells[:, 2] - 1, cells[:, 3] - 1
             q16 = qv.astype(np.float16)               # Float16(q) round-to-nearest-even (bouzidi_setup.jl:128)
             for k in range(27):
                 sel = qv[:, k] > 0.0
                 q_map[k, b[sel], z[sel], y[sel], x[sel]] = q16[sel, k]
-                tri_map[k, b[sel], z[sel], y[sel], x[sel]] = tv[sel, k]
+                if tri_map is not None:
+                    tri_map[k, b[sel], z[sel], y[sel], x[sel]] = tv[sel, k]
             cell_block = cells[:, 0].astype(np.int32)
             cell_x, cell_y, cell_z = (cells[:, i].astype(np.int8) for i in (1, 2, 3))
             qf = q16.astype(np.float32)
@@ -248,6 +251,6 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
     return Domain(cfg, params, mesh, levels, reports)
 
 
-def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False) -> Domain:
+def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False, build_tri_map: bool = True) -> Domain:
     """load_case_configuration + setup_multilevel_domain (main.jl:259-260, :90)."""
-    return setup_multilevel_domain(load_case_configuration(case_dir, overrides), verbose=verbose)
+    return setup_multilevel_domain(load_case_configuration(case_dir, overrides), verbose=verbose, build_tri_map=build_tri_map)
