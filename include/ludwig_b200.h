@@ -184,7 +184,7 @@ int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
  *
  * Every rank creates a context on its own GPU, calls ludwig_ctx_set_partition(rank, world) and then creates the SAME
  * levels from the SAME global tables.  The library orders the blocks of each level along a Morton curve and gives
- * rank r the r-th of `world` contiguous ranges (ludwig_partition_starts); it allocates state only for its own blocks.
+ * rank r the r-th of `world` contiguous ranges of equal estimated cost (ludwig_block_costs); it allocates state only for its own blocks.
  * After the last level: every rank exports CUDA-IPC handles of its state (ludwig_ipc_export), the host all-gathers
  * the buffers (torch.distributed / MPI) and hands the concatenation to ludwig_ipc_attach.  From then on K1 pulls the
  * populations and velocities of neighbour blocks owned by another GPU directly through the peer mapping (NVLink
@@ -193,7 +193,10 @@ int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
  * level step (registered with ludwig_set_barrier_callback; may be stream-ordered).  ludwig_flow_stats and
  * ludwig_compute_aerodynamics return the calling rank's PARTIAL result (triangles dealt round-robin); all 18
  * aerodynamic outputs are linear in the partial sums, so the caller adds them over the ranks.  Fast mode only. */
-int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* [world+1] or NULL */);
+int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* [world+1] or NULL */);  /* equal-count rule */
+/* Relative cost of every block (reference order) by the kernel class it will run in; ludwig_level_create cuts the
+ * Morton curve into `world` ranges of equal cost (host code, callable without a GPU). */
+int ludwig_block_costs(const ludwig_level_desc* desc, float* cost /* [n_blocks] */);
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
 int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user);
 /* Reference (1-based) indices of the blocks this rank owns on `level`, in the library's internal order. */

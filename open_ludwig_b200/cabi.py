@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_init_equilibrium", "ludwig_step_batch", "ludwig_level_step", "ludwig_level_snapshot_old",
     "ludwig_compute_aerodynamics", "ludwig_forces_download_maps", "ludwig_flow_stats", "ludwig_device_bytes",
     "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read",
-    "ludwig_partition_starts", "ludwig_ctx_set_partition", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
+    "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
 )
 
@@ -104,6 +104,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_profile_enable": (C.c_int, [vp, i32]),
         "ludwig_profile_read": (C.c_int, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
         "ludwig_partition_starts": (C.c_int, [i32, i32, vp]),
+        "ludwig_block_costs": (C.c_int, [C.POINTER(LevelDesc), vp]),
         "ludwig_ctx_set_partition": (C.c_int, [vp, i32, i32]),
         "ludwig_set_barrier_callback": (C.c_int, [vp, BARRIER_CB, vp]),
         "ludwig_level_local_blocks": (C.c_int, [vp, i32, C.POINTER(i32), vp]),

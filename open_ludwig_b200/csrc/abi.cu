@@ -509,10 +509,24 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     L.ref2int.resize(nbg);
     for (int i = 0; i < nbg; ++i) L.ref2int[L.int2ref[i]] = i;
 
-    // --- partition: `world` contiguous ranges of the Morton curve (equal block counts)
-    ludwig_partition_starts(nbg, ctx->world, nullptr);   // (validates arguments)
-    L.part_starts.resize(ctx->world + 1);
-    ludwig_partition_starts(nbg, ctx->world, L.part_starts.data());
+    // --- partition: `world` contiguous ranges of the Morton curve with (approximately) equal COST.  A block's cost
+    // follows the kernel class it will run in (measured on Wing_5_deg / bunny: feature blocks ~2x a plain block).
+    L.part_starts.assign(ctx->world + 1, 0);
+    if (ctx->world == 1) { L.part_starts[1] = nbg; }
+    else {
+        std::vector<float> cost(nbg);
+        ludwig_block_costs(d, cost.data());                    // reference order
+        std::vector<double> pre(nbg + 1, 0.0);
+        for (int gi = 0; gi < nbg; ++gi) pre[gi + 1] = pre[gi] + cost[L.int2ref[gi]];
+        for (int r = 1; r < ctx->world; ++r) {
+            const double target = pre[nbg] * r / ctx->world;
+            int cut = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+            cut = std::max(cut, L.part_starts[r - 1] + 1);
+            cut = std::min(cut, nbg - (ctx->world - r));
+            L.part_starts[r] = cut;
+        }
+        L.part_starts[ctx->world] = nbg;
+    }
     L.part_start = L.part_starts[ctx->rank];
     const int nb = L.part_starts[ctx->rank + 1] - L.part_start;
     if (nb <= 0) return fail(ctx, LUDWIG_EINVAL, "level has fewer blocks than ranks");
@@ -911,6 +925,38 @@ int ludwig_level_download_local(ludwig_ctx* ctx, int32_t level, int32_t which, v
     int rc = resolve_field(ctx, L, which, false, &p, &ncomp);
     if (rc) return rc;
     return download_field(ctx, L, p, (float*)dst, ncomp, true);
+}
+
+// Relative cost of every block of a level (reference order), from the kernel class it will run in:
+//   1.0 plain; +1.0 obstacle / sponge / near-wall cells (feature kernel); +1.0 a neighbour block missing (domain face or
+//   refinement interface: boundary code or ghost pre-pass); +0.004 per Bouzidi boundary cell; 0.6 if every cell is solid.
+int ludwig_block_costs(const ludwig_level_desc* d, float* cost) {
+    if (!d || !cost || d->n_blocks <= 0) return LUDWIG_EINVAL;
+    const int nb = d->n_blocks;
+    #pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) {
+        int n_obs = 0; bool sp = false, wd = false;
+        for (int c = 0; c < BS3; ++c) {
+            const size_t i = (size_t)b * BS3 + c;
+            n_obs += d->obstacle[i] != 0;
+            sp |= d->sponge[i] > 0.0f;
+            const float w = d->wall_dist[i];
+            wd |= (w > 0.0f && w < 10.0f);
+        }
+        bool miss = false;
+        for (int dir = 0; dir < 27; ++dir) miss |= d->neighbor_table[b + (size_t)nb * dir] == 0;
+        float c = 1.0f;
+        if (n_obs == BS3) c = 0.6f;
+        else if (n_obs > 0 || sp || wd) c += 1.0f;
+        if (miss) c += 1.0f;
+        cost[b] = c;
+    }
+    if (d->bouzidi_enabled && d->cell_block)
+        for (int i = 0; i < d->n_boundary_cells; ++i) {
+            const int b = d->cell_block[i] - 1;
+            if (b >= 0 && b < nb) cost[b] += 0.004f;
+        }
+    return LUDWIG_OK;
 }
 
 int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts) {

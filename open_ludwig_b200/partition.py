@@ -29,26 +29,69 @@ def partition_starts(n_blocks: int, world: int) -> np.ndarray:
     return np.array([(n_blocks * r) // world for r in range(world + 1)], np.int32)
 
 
-def local_blocks(coords_1based: np.ndarray, rank: int, world: int) -> np.ndarray:
-    """0-based reference indices of the blocks rank `rank` owns, in internal order."""
+def block_costs(level) -> np.ndarray:
+    """Mirror of ludwig_block_costs (csrc/abi.cu): relative cost of every block, reference order, float32."""
+    nb = level.n_blocks
+    obs = (np.asarray(level.obstacle).reshape(nb, 512) != 0)
+    n_obs = obs.sum(axis=1)
+    sp = (np.asarray(level.sponge).reshape(nb, 512) > 0).any(axis=1)
+    wdv = np.asarray(level.wall_dist).reshape(nb, 512)
+    wd = ((wdv > 0) & (wdv < 10)).any(axis=1)
+    miss = (np.asarray(level.neighbor_table) == 0).any(axis=0)
+    c = np.ones(nb, np.float32)
+    c[(n_obs > 0) | sp | wd] += np.float32(1.0)
+    c[n_obs == 512] = np.float32(0.6)
+    c[miss] += np.float32(1.0)
+    if level.bouzidi_enabled and level.cell_block is not None:
+        for b in np.asarray(level.cell_block) - 1:          # sequential float32 adds, like the library
+            c[b] = np.float32(c[b] + np.float32(0.004))
+    return c
+
+
+def weighted_starts(costs_morton: np.ndarray, world: int) -> np.ndarray:
+    """Cut points of `world` contiguous ranges of (approximately) equal cost — ludwig_level_create's rule."""
+    n = len(costs_morton)
+    pre = np.concatenate([[0.0], np.cumsum(costs_morton.astype(np.float64))])
+    st = np.zeros(world + 1, np.int64)
+    if world == 1:
+        st[1] = n
+        return st
+    for r in range(1, world):
+        target = pre[n] * r / world
+        cut = int(np.searchsorted(pre, target, side="left"))
+        cut = max(cut, int(st[r - 1]) + 1)
+        cut = min(cut, n - (world - r))
+        st[r] = cut
+    st[world] = n
+    return st
+
+
+def _starts(coords_1based, world, level=None):
     order = morton_order(coords_1based)
-    st = partition_starts(len(order), world)
+    if level is None or world == 1:
+        return order, partition_starts(len(order), world)
+    return order, weighted_starts(block_costs(level)[order], world)
+
+
+def local_blocks(coords_1based: np.ndarray, rank: int, world: int, level=None) -> np.ndarray:
+    """0-based reference indices of the blocks rank `rank` owns, in internal order.  With `level` the cut is
+    cost-weighted exactly as the library does it; without, equal block counts."""
+    order, st = _starts(coords_1based, world, level)
     return order[st[rank]:st[rank + 1]]
 
 
-def owner_of_ref(coords_1based: np.ndarray, world: int) -> np.ndarray:
+def owner_of_ref(coords_1based: np.ndarray, world: int, level=None) -> np.ndarray:
     """owner rank of every block, indexed by reference index."""
-    order = morton_order(coords_1based)
-    st = partition_starts(len(order), world)
+    order, st = _starts(coords_1based, world, level)
     own = np.empty(len(order), np.int32)
     for r in range(world):
         own[order[st[r]:st[r + 1]]] = r
     return own
 
 
-def remote_neighbours(neighbor_table: np.ndarray, coords_1based: np.ndarray, rank: int, world: int) -> np.ndarray:
+def remote_neighbours(neighbor_table: np.ndarray, coords_1based: np.ndarray, rank: int, world: int, level=None) -> np.ndarray:
     """Sorted reference indices (0-based) of the blocks owned by other ranks that `rank` pulls from."""
-    own = owner_of_ref(coords_1based, world)
+    own = owner_of_ref(coords_1based, world, level)
     mine = np.nonzero(own == rank)[0]
     nb = neighbor_table[:, mine]            # [27, n_mine], 1-based, 0 = none
     refs = np.unique(nb[nb > 0]) - 1

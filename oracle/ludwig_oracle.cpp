@@ -836,6 +836,11 @@ int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts) {
     if (starts) for (int r = 0; r <= world; ++r) starts[r] = (int32_t)(((int64_t)n_blocks * r) / world);
     return LUDWIG_OK;
 }
+int ludwig_block_costs(const ludwig_level_desc* d, float* cost) {
+    if (!d || !cost) return LUDWIG_EINVAL;
+    for (int b = 0; b < d->n_blocks; ++b) cost[b] = 1.0f;     // the oracle never partitions
+    return LUDWIG_OK;
+}
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
     return (rank == 0 && world == 1) ? LUDWIG_OK : fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank");
 }

@@ -30,13 +30,40 @@ def test_partition_rule_matches_library(cuda_lib, oracle_lib):
 
 
 def test_bench_box_partition_gives_cubes():
-    """bench.py's weak-scaling box (64 N x 64 x 64 blocks): every rank's Morton range is one 64^3 cube
-    (checked at 1/8 scale: 8 N x 8 x 8)."""
+    """bench.py's weak-scaling box (64 N x 64 x 64 blocks): with equal counts every rank's Morton range is one 64^3
+    cube (checked at 1/8 scale: 8 N x 8 x 8); the library's cost-weighted cut moves the two end ranks' boundaries
+    inwards (inlet / outlet blocks run the slower boundary kernel) and balances the estimated cost to a few percent."""
     for world in (2, 4, 8):
         lv = syn.make_box_level(8 * world, 8, 8)
+        cost = partition.block_costs(lv)
+        assert cost.min() == 1.0 and cost.max() == 2.0 and int((cost == 2.0).sum()) == 128     # the two open x faces
+        per_rank = []
         for r in range(world):
             c = lv.active_block_coords[partition.local_blocks(lv.active_block_coords, r, world)]
             assert len(c) == 512 and c[:, 0].min() == 8 * r + 1 and c[:, 0].max() == 8 * r + 8
+            per_rank.append(float(cost[partition.local_blocks(lv.active_block_coords, r, world, level=lv)].sum()))
+        assert max(per_rank) / min(per_rank) < 1.03
+
+
+def test_block_costs_match_library(cuda_lib):
+    """ludwig_block_costs is host code (no GPU needed): the NumPy mirror must agree on a case with every feature."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_k1_features_gpu as T
+    lib = cabi.load_library(cuda_lib)
+    for lv in T.build_case():
+        nb = lv.n_blocks
+        keep = [np.ascontiguousarray(a) for a in (lv.neighbor_table, lv.obstacle, lv.sponge, lv.wall_dist)]
+        d = cabi.LevelDesc()
+        d.n_blocks = nb
+        d.neighbor_table, d.obstacle, d.sponge, d.wall_dist = (a.ctypes.data_as(C.c_void_p) for a in keep)
+        d.bouzidi_enabled = int(lv.bouzidi_enabled)
+        d.n_boundary_cells = lv.n_boundary_cells
+        cb = np.ascontiguousarray(lv.cell_block, np.int32) if lv.cell_block is not None else None
+        d.cell_block = cb.ctypes.data_as(C.c_void_p) if cb is not None else None
+        out = np.zeros(nb, np.float32)
+        assert lib.ludwig_block_costs(C.byref(d), out.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out, partition.block_costs(lv))
 
 
 def _worker(rank, world, tmp):
@@ -50,7 +77,7 @@ def _worker(rank, world, tmp):
         levels = T.build_case()
         dev = torch.device("cpu")
         for lv in levels:
-            mine = partition.local_blocks(lv.active_block_coords, rank, world)
+            mine = partition.local_blocks(lv.active_block_coords, rank, world, level=lv)
             # 1. disjoint cover, same order on every rank
             sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([len(mine)]))
@@ -62,8 +89,8 @@ def _worker(rank, world, tmp):
             assert sorted(cat.tolist()) == list(range(lv.n_blocks))
             assert np.array_equal(cat, partition.morton_order(lv.active_block_coords))
             # 2. halo symmetry: every remote block I pull from is owned by the peer, and the peer pulls from me too
-            rem = partition.remote_neighbours(lv.neighbor_table, lv.active_block_coords, rank, world)
-            own = partition.owner_of_ref(lv.active_block_coords, world)
+            rem = partition.remote_neighbours(lv.neighbor_table, lv.active_block_coords, rank, world, level=lv)
+            own = partition.owner_of_ref(lv.active_block_coords, world, level=lv)
             assert np.all(own[rem] != rank) and len(rem) > 0
             cnt = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(cnt, torch.tensor([len(rem)]))

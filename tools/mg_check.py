@@ -33,7 +33,7 @@ def run_box(partitioned, steps=9):
         mg.attach_peers(ctx, dev)
         loc = ctx.local_blocks(0)
         from open_ludwig_b200 import partition
-        assert np.array_equal(loc, partition.local_blocks(lv.active_block_coords, rank, world)), "library partition != host mirror"
+        assert np.array_equal(loc, partition.local_blocks(lv.active_block_coords, rank, world, level=lv)), "library partition != host mirror"
         ctx.upload_local(0, cabi.F, f[:, loc]); ctx.upload_local(0, cabi.F_TEMP, f[:, loc])
         ctx.upload_local(0, cabi.VEL, vel[:, loc]); ctx.upload_local(0, cabi.VEL_TEMP, vel[:, loc]); ctx.upload_local(0, cabi.RHO, rho[loc])
     else:

@@ -1,0 +1,68 @@
+"""Strong scaling of a named case over N GPUs (one process per GPU; launch with torchrun, or plain python for N = 1).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/run_case_mg.py bunny_fine 6
+
+Every rank builds the (identical) domain on the host, creates a partitioned context, attaches the peers and steps in
+lock-step; forces are reduced over the ranks.  Prints true MLUPS (max time over ranks, CUDA events on the library's stream).
+"""
+import os, sys, time
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
+os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))     # host-side domain build
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+from open_ludwig_b200 import cabi, multigpu as mg
+from open_ludwig_b200.host import domain as D
+from open_ludwig_b200.host.cases import CASE_OVERRIDES, case_dir
+from open_ludwig_b200.solver import make_params, ramp_velocity
+
+name, steps = sys.argv[1], int(sys.argv[2])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+case, ov = CASE_OVERRIDES[name]
+t0 = time.time()
+dom = D.load_case(case_dir(case), ov, verbose=(rank == 0), build_tri_map=False)
+if rank == 0:
+    print(f"domain build {time.time()-t0:.1f}s cells {dom.total_cells/1e6:.1f}M updates/coarse step {dom.cell_updates_per_coarse_step/1e6:.0f}M", flush=True)
+ctx = cabi.Context(device=lr)
+if world > 1:
+    ctx.set_partition(rank, world)
+t0 = time.time()
+for lv in dom.levels:
+    ctx.add_level(lv)
+if world > 1:
+    mg.attach_peers(ctx, dev)
+m = dom.mesh
+mesh = ctx.create_mesh(m.centers, m.normals, m.areas)
+p = dom.params
+forces = ctx.create_forces(mesh, p.rho_physical, p.u_physical, p.reference_area, p.reference_chord, p.moment_center, dom.cfg.symmetric)
+ctx.init_equilibrium()
+params = make_params(dom, strict=False)
+ctx.sync()
+if rank == 0:
+    print(f"upload {time.time()-t0:.1f}s device GB (rank 0) {ctx.device_bytes()/1e9:.1f}", flush=True)
+stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+u = ramp_velocity(dom.cfg.u_target, 8, dom.cfg.ramp_steps)
+ctx.step_batch(1, 2, u, params); ctx.sync()            # warm-up (builds the fast-mode tables)
+if world > 1: dist.barrier()
+e0.record(stream)
+ctx.step_batch(3, steps, u, params)
+e1.record(stream)
+ctx.sync()
+if world > 1: dist.barrier()
+ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+aero = ctx.compute_aerodynamics(forces, len(dom.levels) - 1, p.mesh_offset, p.velocity_scale, p.rho_physical, 5)
+stats = ctx.flow_stats(0)
+if world > 1:
+    aero = mg.reduce_aero(aero, dev); stats = mg.reduce_stats(stats, dev)
+if rank == 0:
+    sec = float(ms[0]) * 1e-3
+    print(f"RESULT case={name} n_gpus={world} steps={steps} s/step={sec/steps:.4f} true_MLUPS={dom.cell_updates_per_coarse_step*steps/sec/1e6:.0f} "
+          f"ref_MLUPS={dom.total_cells*steps/sec/1e6:.0f} Cd={aero['Cd']:.6e} Cl={aero['Cl']:.6e} rho_min={stats['rho_min']:.6f} rho_max={stats['rho_max']:.6f}", flush=True)
+if world > 1: dist.barrier()
+ctx.close()
+if world > 1: dist.destroy_process_group()
