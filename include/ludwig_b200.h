@@ -220,6 +220,9 @@ int64_t ludwig_launch_count(const ludwig_ctx* ctx);
  * duration [ms], the number of bracketed launches and the lattice cells they updated, and resets the counters. */
 int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on);
 int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, int64_t* cells);
+/* Device time [ms] per launch class accumulated by the last ludwig_profile_read: 0 K1 plain, 1 K1 plain+ghost,
+ * 2 K1 feature, 3 K1 full, 4 interface pre-pass, 5 Bouzidi (classes 1-3 only when launched on the main stream). */
+int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]);
 
 #ifdef __cplusplus
 }

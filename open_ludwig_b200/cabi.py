@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_mesh_create", "ludwig_mesh_destroy", "ludwig_forces_create", "ludwig_forces_destroy",
     "ludwig_init_equilibrium", "ludwig_step_batch", "ludwig_level_step", "ludwig_level_snapshot_old",
     "ludwig_compute_aerodynamics", "ludwig_forces_download_maps", "ludwig_flow_stats", "ludwig_device_bytes",
-    "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read",
+    "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read", "ludwig_profile_classes",
     "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
 )
@@ -103,6 +103,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_launch_count": (C.c_int64, [vp]),
         "ludwig_profile_enable": (C.c_int, [vp, i32]),
         "ludwig_profile_read": (C.c_int, [vp, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
+        "ludwig_profile_classes": (C.c_int, [vp, C.POINTER(f64)]),
         "ludwig_partition_starts": (C.c_int, [i32, i32, vp]),
         "ludwig_block_costs": (C.c_int, [C.POINTER(LevelDesc), vp]),
         "ludwig_ctx_set_partition": (C.c_int, [vp, i32, i32]),
@@ -234,6 +235,14 @@ class Context:
         ms, n, cells = C.c_double(), C.c_int64(), C.c_int64()
         self._check(self.lib.ludwig_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(cells)), "ludwig_profile_read")
         return ms.value, n.value, cells.value
+
+    PROFILE_CLASSES = ("k1_plain", "k1_plain_ghost", "k1_feature", "k1_full", "interface_prepass", "bouzidi", "-", "-")
+
+    def profile_classes(self) -> dict:
+        """Device ms per launch class of the last profile_read()."""
+        out = (C.c_double * 8)()
+        self._check(self.lib.ludwig_profile_classes(self._h, out), "ludwig_profile_classes")
+        return {k: v for k, v in zip(self.PROFILE_CLASSES, list(out)) if k != "-"}
 
     # -- multi-GPU (one process per GPU) ----------------------------------------------------
     def set_partition(self, rank: int, world: int):

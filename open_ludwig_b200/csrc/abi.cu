@@ -241,6 +241,28 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     return LUDWIG_OK;
 }
 
+// Profiling brackets (ludwig_profile_enable): CUDA events on the main stream around one launch, tagged with a class:
+// 0 K1 plain, 1 K1 plain+ghost, 2 K1 feature, 3 K1 full (missing neighbours), 4 interface pre-pass, 5 Bouzidi.
+int prof_begin(ludwig_ctx* ctx, int cls, bool active) {
+    if (!ctx->profiling || !active) return LUDWIG_OK;
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
+    }
+    if (ctx->ev_class.size() < ctx->ev_pool.size() / 2) ctx->ev_class.resize(ctx->ev_pool.size() / 2);
+    ctx->ev_class[ctx->ev_used / 2] = cls;
+    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    return LUDWIG_OK;
+}
+int prof_end(ludwig_ctx* ctx, bool active, int64_t cells) {
+    if (!ctx->profiling || !active) return LUDWIG_OK;
+    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+    ctx->ev_used += 2;
+    ctx->prof_cells += cells;
+    return LUDWIG_OK;
+}
+
 // Active Bouzidi links of the local boundary cells for a given q_min (bouzidi_kernel.jl:36-38: q > q_min && q <= 1).
 int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
     if (L.links_qmin == q_min) return LUDWIG_OK;
@@ -317,7 +339,9 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             }
             g.pptr = pv->P->d_ptr; g.pdimx = pv->P->dimx; g.pdimy = pv->P->dimy; g.pdimz = pv->P->dimz;
             g.tau = L.tau; g.tau_parent = pv->P->tau; g.tw = tw; g.use_temporal = p.use_temporal;
+            if ((rc = prof_begin(ctx, 4, true))) return rc;
             launch_ghost_interp(g, ctx->stream);
+            if ((rc = prof_end(ctx, true, 0))) return rc;
             ctx->launches += 1;
         }
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
@@ -339,24 +363,20 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             ctx->launches += 1;
             return LUDWIG_OK;
         };
-        const bool prof = ctx->profiling && L.n_plain > 0;
-        if (prof) {
-            if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
-                cudaEvent_t e0, e1;
-                CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-                ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
-            }
-            CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
-        }
+        if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
         if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true))) return rc;
-        if (prof) {
-            CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
-            ctx->ev_used += 2;
-            ctx->prof_cells += (int64_t)L.n_plain * BS3;
-        }
+        if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
+        // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
+        const bool pc = ctx->profiling && !fork;
+        if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
         if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0))) return rc;
+        if ((rc = prof_end(ctx, pc && L.n_plain_g > 0, 0))) return rc;
+        if ((rc = prof_begin(ctx, 2, pc && L.n_feat > 0))) return rc;
         if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0))) return rc;
+        if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
+        if ((rc = prof_begin(ctx, 3, pc && L.n_full > 0))) return rc;
         if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0))) return rc;
+        if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
     }
     const bool mg = ctx->world > 1 && ctx->barrier_cb;
@@ -366,9 +386,14 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if (mg) ctx->barrier_cb(ctx->barrier_user);
         int rcb = ensure_bouzidi_links(ctx, L, p.q_min_threshold);
         if (rcb) return rcb;
+        int rcp;
+        if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
         launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 1, ctx->stream);
+        if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
         if (mg) ctx->barrier_cb(ctx->barrier_user);
+        if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
         launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 2, ctx->stream);
+        if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
         if (L.n_links > 0) ctx->launches += 2;
     }
     if (mg) ctx->barrier_cb(ctx->barrier_user);   // every rank finished this level step
@@ -459,15 +484,25 @@ int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, in
     if (!ctx) return LUDWIG_EINVAL;
     CU(cudaStreamSynchronize(ctx->stream));
     double tot = 0;
+    int64_t n0 = 0;
+    for (int c = 0; c < 8; ++c) ctx->prof_class_ms[c] = 0;
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
-        tot += ms;
+        const int c = ctx->ev_class[i / 2];
+        ctx->prof_class_ms[c & 7] += ms;
+        if (c == 0) { tot += ms; ++n0; }
     }
-    if (ms_total) *ms_total = tot;
-    if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+    if (ms_total) *ms_total = tot;            // class 0 only: the dominant plain K1 kernel
+    if (launches) *launches = n0;
     if (cells) *cells = ctx->prof_cells;
     ctx->ev_used = 0; ctx->prof_cells = 0;
+    return LUDWIG_OK;
+}
+
+int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]) {
+    if (!ctx || !out) return LUDWIG_EINVAL;
+    for (int c = 0; c < 8; ++c) out[c] = ctx->prof_class_ms[c];   // filled by the last ludwig_profile_read
     return LUDWIG_OK;
 }
 

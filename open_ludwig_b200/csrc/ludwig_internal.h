@@ -179,6 +179,8 @@ struct ludwig_ctx {
     // K1 profiling (ludwig_profile_enable)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)
+    std::vector<int> ev_class;          // launch class of each pair
+    double prof_class_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t ev_used = 0;
     int64_t prof_cells = 0;
 };

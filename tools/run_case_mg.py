@@ -48,10 +48,18 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 u = ramp_velocity(dom.cfg.u_target, 8, dom.cfg.ramp_steps)
 ctx.step_batch(1, 2, u, params); ctx.sync()            # warm-up (builds the fast-mode tables)
 if world > 1: dist.barrier()
+prof = os.environ.get("LUDWIG_PROFILE") is not None      # with LUDWIG_SINGLE_STREAM=1: per-class device time of every rank
+if prof:
+    ctx.profile_enable(True)
 e0.record(stream)
 ctx.step_batch(3, steps, u, params)
 e1.record(stream)
 ctx.sync()
+if prof:
+    ctx.profile_read(); cls = ctx.profile_classes()
+    loc = [len(ctx.local_blocks(i)) for i in range(len(dom.levels))]
+    print(f"rank {rank}: local blocks/level {loc} total {e0.elapsed_time(e1):.1f} ms busy {sum(cls.values()):.1f} ms " +
+          " ".join(f"{k}={v:.1f}" for k, v in cls.items()), flush=True)
 if world > 1: dist.barrier()
 ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
 if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
