@@ -198,6 +198,12 @@ int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* 
  * Morton curve into `world` ranges of equal cost (host code, callable without a GPU). */
 int ludwig_block_costs(const ludwig_level_desc* desc, float* cost /* [n_blocks] */);
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
+/* Optional, multi-level cases: a spatially aligned plan.  ludwig_partition_plan (host code) takes the descriptors of ALL
+ * levels and returns world+1 cut keys on the Morton axis of the finest level such that every interval carries the same
+ * estimated cost (block cost x 2^(level-1) sub-steps); with ludwig_ctx_set_partition_keys every level is cut at the same
+ * places in space, so a fine block, its parent cells and its neighbours live on one GPU except at the cut surfaces. */
+int ludwig_partition_plan(const ludwig_level_desc* const* descs, int32_t n_levels, int32_t world, uint64_t* keys /* [world+1] */);
+int ludwig_ctx_set_partition_keys(ludwig_ctx* ctx, const uint64_t* keys /* [world+1] */, int32_t n_levels);
 int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user);
 /* Reference (1-based) indices of the blocks this rank owns on `level`, in the library's internal order. */
 int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices /* or NULL */);

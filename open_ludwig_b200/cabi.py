@@ -31,7 +31,8 @@ EXPORTED_SYMBOLS = (
     "ludwig_init_equilibrium", "ludwig_step_batch", "ludwig_level_step", "ludwig_level_snapshot_old",
     "ludwig_compute_aerodynamics", "ludwig_forces_download_maps", "ludwig_flow_stats", "ludwig_device_bytes",
     "ludwig_ctx_stream", "ludwig_launch_count", "ludwig_profile_enable", "ludwig_profile_read", "ludwig_profile_classes",
-    "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
+    "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_partition_plan",
+    "ludwig_ctx_set_partition_keys", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
 )
 
@@ -107,6 +108,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_partition_starts": (C.c_int, [i32, i32, vp]),
         "ludwig_block_costs": (C.c_int, [C.POINTER(LevelDesc), vp]),
         "ludwig_ctx_set_partition": (C.c_int, [vp, i32, i32]),
+        "ludwig_partition_plan": (C.c_int, [vp, i32, i32, vp]),
+        "ludwig_ctx_set_partition_keys": (C.c_int, [vp, vp, i32]),
         "ludwig_set_barrier_callback": (C.c_int, [vp, BARRIER_CB, vp]),
         "ludwig_level_local_blocks": (C.c_int, [vp, i32, C.POINTER(i32), vp]),
         "ludwig_level_upload_local": (C.c_int, [vp, i32, i32, vp]),
@@ -285,7 +288,9 @@ class Context:
         self._check(self.lib.ludwig_ipc_attach(self._h, buf, bytes_per_rank), "ludwig_ipc_attach")
 
     # -- upload (main.jl:98,101,145) ---------------------------------------------------
-    def add_level(self, lv: BlockLevel) -> int:
+    @staticmethod
+    def make_desc(lv: BlockLevel):
+        """ludwig_level_desc for a host BlockLevel + the arrays that must stay alive while it is used."""
         nb = lv.n_blocks
         bp = _as(lv.block_pointer, np.int32)
         nt = _as(lv.neighbor_table, np.int32)
@@ -314,11 +319,27 @@ class Context:
             d.q_map_f16, d.cell_block = _ptr(q), _ptr(cb)
             d.cell_x, d.cell_y, d.cell_z = _ptr(cx), _ptr(cy), _ptr(cz)
             keep += [q, cb, cx, cy, cz]
+        return d, keep
+
+    def add_level(self, lv: BlockLevel) -> int:
+        d, keep = self.make_desc(lv)
         idx = C.c_int32(-1)
         self._check(self.lib.ludwig_level_create(self._h, C.byref(d), C.byref(idx)), "ludwig_level_create")
         del keep
-        self.n_blocks.append(nb)
+        self.n_blocks.append(lv.n_blocks)     # blocks of the whole level (this rank's share: local_blocks())
         return idx.value
+
+    def set_partition_plan(self, levels):
+        """Spatially aligned, cost-balanced cut of all levels (call after set_partition, before add_level)."""
+        descs, keeps = zip(*[self.make_desc(lv) for lv in levels])
+        arr = (C.POINTER(LevelDesc) * len(descs))(*[C.pointer(d) for d in descs])
+        keys = (C.c_uint64 * (self.world + 1))()
+        rc = self.lib.ludwig_partition_plan(arr, len(descs), self.world, keys)
+        if rc != 0:
+            raise LudwigError(f"ludwig_partition_plan failed ({rc})")
+        self._check(self.lib.ludwig_ctx_set_partition_keys(self._h, keys, len(descs)), "ludwig_ctx_set_partition_keys")
+        del keeps
+        return list(keys)
 
     def upload(self, level: int, which: int, arr: np.ndarray):
         nb = self.n_blocks[level]

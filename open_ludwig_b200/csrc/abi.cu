@@ -238,6 +238,9 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     CU(cudaStreamSynchronize(ctx->stream));
     L.fast_dom[0] = p.domain_nx; L.fast_dom[1] = p.domain_ny; L.fast_dom[2] = p.domain_nz;
     L.fast_ready = true;
+    if (getenv("LUDWIG_VERBOSE"))
+        fprintf(stderr, "[ludwig rank %d] level %d: %d local blocks (plain %d, plain+ghost %d, feature %d, full %d), %d remote, %d ghost blocks, %d ghost cells\n",
+                ctx->rank, L.level_id, nb, L.n_plain, L.n_plain_g, L.n_feat, L.n_full, L.n_remote, ng, L.n_gcell);
     return LUDWIG_OK;
 }
 
@@ -548,7 +551,21 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     // follows the kernel class it will run in (measured on Wing_5_deg / bunny: feature blocks ~2x a plain block).
     L.part_starts.assign(ctx->world + 1, 0);
     if (ctx->world == 1) { L.part_starts[1] = nbg; }
-    else {
+    else if (ctx->has_plan) {
+        // spatially aligned cut (ludwig_partition_plan): a block belongs to the rank whose key interval holds its Morton
+        // key scaled to the finest level, so parents, children and neighbours of one region live on one GPU
+        if (d->level_id > ctx->plan_levels) return fail(ctx, LUDWIG_EINVAL, "level beyond the partition plan");
+        const int sh = 3 * (ctx->plan_levels - d->level_id);
+        std::vector<uint64_t> sk(nbg);
+        for (int gi = 0; gi < nbg; ++gi) sk[gi] = key[L.int2ref[gi]] << sh;
+        for (int r = 1; r < ctx->world; ++r) {
+            int cut = (int)(std::lower_bound(sk.begin(), sk.end(), ctx->plan_keys[r]) - sk.begin());
+            cut = std::max(cut, L.part_starts[r - 1] + 1);       // every rank keeps at least one block of every level
+            cut = std::min(cut, nbg - (ctx->world - r));
+            L.part_starts[r] = cut;
+        }
+        L.part_starts[ctx->world] = nbg;
+    } else {
         std::vector<float> cost(nbg);
         ludwig_block_costs(d, cost.data());                    // reference order
         std::vector<double> pre(nbg + 1, 0.0);
@@ -991,6 +1008,45 @@ int ludwig_block_costs(const ludwig_level_desc* d, float* cost) {
             const int b = d->cell_block[i] - 1;
             if (b >= 0 && b < nb) cost[b] += 0.004f;
         }
+    return LUDWIG_OK;
+}
+
+// Cut keys for a spatially aligned, cost-balanced partition of ALL levels: every block contributes its cost x 2^(l-1)
+// sub-steps at its Morton key scaled to the finest level; the key axis is cut into `world` intervals of equal weight.
+int ludwig_partition_plan(const ludwig_level_desc* const* descs, int32_t n_levels, int32_t world, uint64_t* keys) {
+    if (!descs || !keys || n_levels < 1 || world < 1 || world > MAX_RANKS) return LUDWIG_EINVAL;
+    std::vector<std::pair<uint64_t, double>> items;
+    for (int l = 0; l < n_levels; ++l) {
+        const ludwig_level_desc* d = descs[l];
+        if (!d || d->n_blocks <= 0) return LUDWIG_EINVAL;
+        std::vector<float> cost(d->n_blocks);
+        int rc = ludwig_block_costs(d, cost.data());
+        if (rc) return rc;
+        const int sh = 3 * (n_levels - 1 - l);
+        const double sub = (double)(1u << l);
+        for (int b = 0; b < d->n_blocks; ++b)
+            items.emplace_back(morton3((uint32_t)(d->map_x[b] - 1), (uint32_t)(d->map_y[b] - 1), (uint32_t)(d->map_z[b] - 1)) << sh, cost[b] * sub);
+    }
+    std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    double total = 0;
+    for (auto& it : items) total += it.second;
+    keys[0] = 0; keys[world] = ~0ull;
+    double acc = 0; size_t i = 0;
+    for (int r = 1; r < world; ++r) {
+        const double target = total * r / world;
+        while (i < items.size() && acc + items[i].second <= target) { acc += items[i].second; ++i; }
+        keys[r] = i < items.size() ? items[i].first : ~0ull;
+        if (keys[r] < keys[r - 1]) keys[r] = keys[r - 1];
+    }
+    return LUDWIG_OK;
+}
+
+int ludwig_ctx_set_partition_keys(ludwig_ctx* ctx, const uint64_t* keys, int32_t n_levels) {
+    if (!ctx || !keys || n_levels < 1) return fail(ctx, LUDWIG_EINVAL, "bad partition keys");
+    if (!ctx->levels.empty()) return fail(ctx, LUDWIG_ESTATE, "set the partition plan before creating levels");
+    ctx->plan_keys.assign(keys, keys + ctx->world + 1);
+    ctx->plan_levels = n_levels;
+    ctx->has_plan = true;
     return LUDWIG_OK;
 }
 

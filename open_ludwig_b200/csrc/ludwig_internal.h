@@ -171,6 +171,9 @@ struct ludwig_ctx {
     double* h_stats = nullptr;   // pinned
     int num_sms = 148;
     int rank = 0, world = 1;
+    bool has_plan = false;                  // spatially aligned partition (ludwig_ctx_set_partition_keys)
+    std::vector<uint64_t> plan_keys;        // [world+1] cut keys at finest-level resolution
+    int plan_levels = 0;
     bool peers_attached = false;
     void (*barrier_cb)(void*) = nullptr;   // cross-rank barrier, stream-ordered or blocking (multi-GPU only)
     void* barrier_user = nullptr;

@@ -841,6 +841,12 @@ int ludwig_block_costs(const ludwig_level_desc* d, float* cost) {
     for (int b = 0; b < d->n_blocks; ++b) cost[b] = 1.0f;     // the oracle never partitions
     return LUDWIG_OK;
 }
+int ludwig_partition_plan(const ludwig_level_desc* const*, int32_t, int32_t world, uint64_t* keys) {
+    if (!keys || world != 1) return LUDWIG_EINVAL;
+    keys[0] = 0; keys[1] = ~0ull;
+    return LUDWIG_OK;
+}
+int ludwig_ctx_set_partition_keys(ludwig_ctx*, const uint64_t*, int32_t) { return LUDWIG_OK; }
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
     return (rank == 0 && world == 1) ? LUDWIG_OK : fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank");
 }

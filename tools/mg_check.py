@@ -49,11 +49,13 @@ def run_box(partitioned, steps=9):
     dist.barrier(); ctx.close()
     return out, st
 
-def run_two_level(partitioned, steps=10):
+def run_two_level(partitioned, steps=10, plan=False):
     levels = T.build_case()
     cells = tuple(8 * d for d in T.DIMS)
     p = default_params(cells, strict=0, wall_model_active=1, use_temporal=1, inlet_turbulence=0.02)
     ctx = mg.init_context(None, lr) if partitioned else cabi.Context(device=lr)
+    if partitioned and plan:
+        ctx.set_partition_plan(levels)
     for lv in levels:
         ctx.add_level(lv)
     if partitioned:
@@ -79,11 +81,14 @@ for k in ref:
     ok &= same
     if rank == 0: print(f"box {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
 if rank == 0: print("box stats", sref["n_fluid"] == sgot["n_fluid"], abs(sref["rho_mean"] - sgot["rho_mean"]) < 1e-12, sref["rho_min"] == sgot["rho_min"], flush=True)
-ref, aref = run_two_level(False); got, agot = run_two_level(True)
-for k in ref:
-    same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
-    ok &= same
-    if rank == 0: print(f"two-level {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
+ref, aref = run_two_level(False)
+for plan in (False, True):       # per-level cost-weighted cut, and the spatially aligned plan over all levels
+    got, agot = run_two_level(True, plan=plan)
+    for k in ref:
+        same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
+        ok &= same
+        if rank == 0: print(f"two-level plan={plan} {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
+    ok &= abs(aref["Cd"] - agot["Cd"]) <= 1e-9 * abs(aref["Cd"]) + 1e-15
 if rank == 0:
     print("aero Cd", aref["Cd"], agot["Cd"], "rel", abs(aref["Cd"] - agot["Cd"]) / abs(aref["Cd"]), flush=True)
     print("MG_CHECK", "PASS" if ok and abs(aref["Cd"] - agot["Cd"]) <= 1e-9 * abs(aref["Cd"]) + 1e-15 else "FAIL", flush=True)

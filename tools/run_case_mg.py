@@ -29,6 +29,8 @@ if rank == 0:
 ctx = cabi.Context(device=lr)
 if world > 1:
     ctx.set_partition(rank, world)
+    if not os.environ.get("LUDWIG_NO_PLAN"):
+        ctx.set_partition_plan(dom.levels)       # parents, children and neighbours of one region on one GPU
 t0 = time.time()
 for lv in dom.levels:
     ctx.add_level(lv)
