@@ -62,7 +62,7 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full,
+    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
@@ -152,10 +152,10 @@ ParentView make_parent_view(const Level& P, int64_t parent_t_sub, bool explicit_
 int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
     CU(cudaStreamSynchronize(ctx->stream));
-    for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_list_plain,
+    for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_gcells8, (void*)L.d_list_plain,
                     (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full})
         if (q) cudaFree(q);
-    L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr;
+    L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr; L.d_gcells8 = nullptr;
     L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = nullptr;
     const int nb = L.nb;
     const int scale = 1 << (L.level_id - 1);
@@ -181,6 +181,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     // work list: ghost cell (g,c) must provide population k iff the cell that pulls it, c + c_k, lies in a real block
     std::vector<int32_t> gcell;
     std::vector<uint32_t> gmask;
+    std::vector<uint8_t> gcells8;
     auto real_at = [&](int x, int y, int z) {
         if (x < 0 || x >= L.dimx || y < 0 || y >= L.dimy || z < 0 || z >= L.dimz) return false;
         return L.h_ptr[x + (size_t)L.dimx * (y + (size_t)L.dimy * z)] >= 0;
@@ -189,18 +190,21 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         const int gx = gcoord[(size_t)g * 4], gy = gcoord[(size_t)g * 4 + 1], gz = gcoord[(size_t)g * 4 + 2];
         bool realn[27];
         for (int d = 0; d < 27; ++d) realn[d] = real_at(gx + d % 3 - 1, gy + (d / 3) % 3 - 1, gz + d / 9 - 1);
-        for (int c = 0; c < BS3; ++c) {
-            const int x = c & 7, y = (c >> 3) & 7, z = c >> 6;
-            if (x > 0 && x < 7 && y > 0 && y < 7 && z > 0 && z < 7) continue;
-            uint32_t m = 0;
-            for (int k = 0; k < 27; ++k) {
-                if (k == 13) continue;
-                int dx = x + (k % 3 - 1), dy = y + ((k / 3) % 3 - 1), dz = z + (k / 9 - 1);
-                int ox = dx < 0 ? -1 : (dx > 7 ? 1 : 0), oy = dy < 0 ? -1 : (dy > 7 ? 1 : 0), oz = dz < 0 ? -1 : (dz > 7 ? 1 : 0);
-                if (ox == 0 && oy == 0 && oz == 0) continue;
-                if (realn[(ox + 1) + (oy + 1) * 3 + (oz + 1) * 9]) m |= 1u << k;
+        for (int q = 0; q < 64; ++q) {                  // 2x2x2 groups sharing one parent cell
+            const int x0 = (q & 3) * 2, y0 = ((q >> 2) & 3) * 2, z0 = (q >> 4) * 2;
+            if (x0 > 0 && x0 < 6 && y0 > 0 && y0 < 6 && z0 > 0 && z0 < 6) continue;
+            uint32_t km = 0; uint8_t cm = 0;
+            for (int m = 0; m < 8; ++m) {
+                const int x = x0 + (m & 1), y = y0 + ((m >> 1) & 1), z = z0 + ((m >> 2) & 1);
+                for (int k = 0; k < 27; ++k) {
+                    if (k == 13) continue;
+                    int dx = x + (k % 3 - 1), dy = y + ((k / 3) % 3 - 1), dz = z + (k / 9 - 1);
+                    int ox = dx < 0 ? -1 : (dx > 7 ? 1 : 0), oy = dy < 0 ? -1 : (dy > 7 ? 1 : 0), oz = dz < 0 ? -1 : (dz > 7 ? 1 : 0);
+                    if (ox == 0 && oy == 0 && oz == 0) continue;
+                    if (realn[(ox + 1) + (oy + 1) * 3 + (oz + 1) * 9]) { km |= 1u << k; cm |= (uint8_t)(1u << m); }
+                }
             }
-            if (m) { gcell.push_back(g * BS3 + c); gmask.push_back(m); }
+            if (cm) { gcell.push_back(g * 64 + q); gmask.push_back(km); gcells8.push_back(cm); }
         }
     }
     // K1 work lists
@@ -222,12 +226,13 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     CU(memcpy_sync(ctx->stream, L.d_nbr_fast, nbrf.data(), nbrf.size() * 4, cudaMemcpyHostToDevice));
     if (ng > 0) {
         CU(dalloc(ctx, &L.d_gcoord, gcoord.size())); CU(dalloc(ctx, &L.d_fghost, (size_t)ng * Q * BS3));
-        CU(dalloc(ctx, &L.d_gcell, gcell.size())); CU(dalloc(ctx, &L.d_gmask, gmask.size()));
+        CU(dalloc(ctx, &L.d_gcell, gcell.size())); CU(dalloc(ctx, &L.d_gmask, gmask.size())); CU(dalloc(ctx, &L.d_gcells8, gcells8.size()));
         CU(memcpy_sync(ctx->stream, L.d_gcoord, gcoord.data(), gcoord.size() * 4, cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(L.d_fghost, 0, (size_t)ng * Q * BS3 * 4, ctx->stream));
         if (!gcell.empty()) {
             CU(memcpy_sync(ctx->stream, L.d_gcell, gcell.data(), gcell.size() * 4, cudaMemcpyHostToDevice));
             CU(memcpy_sync(ctx->stream, L.d_gmask, gmask.data(), gmask.size() * 4, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_gcells8, gcells8.data(), gcells8.size(), cudaMemcpyHostToDevice));
         }
     }
     struct { std::vector<int32_t>* v; int32_t** d; } lists[4] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}};
@@ -239,7 +244,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     L.fast_dom[0] = p.domain_nx; L.fast_dom[1] = p.domain_ny; L.fast_dom[2] = p.domain_nz;
     L.fast_ready = true;
     if (getenv("LUDWIG_VERBOSE"))
-        fprintf(stderr, "[ludwig rank %d] level %d: %d local blocks (plain %d, plain+ghost %d, feature %d, full %d), %d remote, %d ghost blocks, %d ghost cells\n",
+        fprintf(stderr, "[ludwig rank %d] level %d: %d local blocks (plain %d, plain+ghost %d, feature %d, full %d), %d remote, %d ghost blocks, %d ghost groups\n",
                 ctx->rank, L.level_id, nb, L.n_plain, L.n_plain_g, L.n_feat, L.n_full, L.n_remote, ng, L.n_gcell);
     return LUDWIG_OK;
 }
@@ -333,7 +338,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         a.ghost_delta = L.d_fghost ? (long long)(L.d_fghost - L.d_f[in]) : 0;
         if (L.n_gcell > 0 && pv) {   // interface halo pre-pass: fills the ghost blocks K1 is about to pull from
             GhostArgs g{};
-            g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
+            g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.gcells8 = L.d_gcells8; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
             const Level& P = *pv->P;
             g.pf_new = peers_of(P.peer_f[pv->out]); g.pvel_new = peers_of(P.peer_vel[pv->out]); g.prho_new = peers_of(P.peer_rho[pv->rho_new_i]);
             g.pf_old = peers_of(P.peer_f[pv->in]); g.pvel_old = peers_of(P.peer_vel[pv->in]); g.prho_old = peers_of(P.peer_rho[pv->rho_old_i]);

@@ -115,47 +115,47 @@ __device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, 
 // Interface halo pre-pass.  In the reference every missing-neighbour population of a fine block is interpolated
 // inside the stream-collide thread that needs it (interpolate_with_rescaling, physics_interpolation.jl:16-138):
 // 8 parent corners x (f_k, rho, u) x (new, old) scattered loads per population, serialised in a handful of
-// divergent lanes.  Here the missing in-domain neighbour blocks of a level exist as GHOST blocks; one thread per
-// ghost CELL computes the 8-corner rho/u blend once and then every population some real cell will pull from it
-// (a static bit mask built with the topology), writing f_ghost[g][k][cell].  K1 then treats ghost blocks as
-// ordinary neighbours, so interface blocks run the plain kernel.  Same arithmetic per population as the
-// reference (the rho/u interpolation it repeats per direction is direction-independent).
+// divergent lanes.  Here the missing in-domain neighbour blocks of a level exist as GHOST blocks, filled before K1,
+// which then treats them as ordinary neighbours (interface blocks run the plain kernel).
+// The 2x2x2 fine cells inside one parent cell share their 8 parent corners (p0 = (g-1) >> 1) and differ only in the
+// weights (0.25 / 0.75 per axis), so one thread handles such a GROUP: the 8-corner rho/u/f_k loads are done once and
+// reused for up to 8 ghost cells (4 on a face layer) — ~4x fewer scattered loads than one thread per cell.
+// Same arithmetic per population as the reference (its per-direction rho/u interpolation is direction-independent).
 __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
+    // (dealing a group's populations to 4 lanes was measured: 2.7x slower — the kernel is bound by DRAM sectors of the
+    // scattered parent values, not by its load chains)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const int gc = a.gcell[i];
-    const uint32_t mask = a.gmask[i];
-    const int g = gc >> 9, c = gc & 511;
+    const int gq = a.gcell[i];               // ghost block * 64 + group (qz*16 + qy*4 + qx)
+    const uint32_t word = a.gmask[i];        // bits 0..26: populations needed by some cell of the group; 27..31 unused
+    const uint32_t cells = a.gcells8[i];     // bit (dz*4 + dy*2 + dx): that cell of the group is pulled from
+    const int g = gq >> 6, q = gq & 63;
+    const int x0 = (q & 3) * 2, y0 = ((q >> 2) & 3) * 2, z0 = (q >> 4) * 2;
     const int4 gb = *reinterpret_cast<const int4*>(a.gcoord + (size_t)g * 4);
-    const int fine_gx = gb.x * BS + (c & 7) + 1, fine_gy = gb.y * BS + ((c >> 3) & 7) + 1, fine_gz = gb.z * BS + (c >> 6) + 1;
+    // 1-based fine coordinates of the group's first cell (odd) and its shared parent corner p0
+    const int fgx = gb.x * BS + x0 + 1, fgy = gb.y * BS + y0 + 1, fgz = gb.z * BS + z0 + 1;
+    const int p0x = (fgx - 1) >> 1, p0y = (fgy - 1) >> 1, p0z = (fgz - 1) >> 1;   // floor((g - 0.5) * 0.5) for both cells of a pair
+    const int cx0 = max(1, p0x), cy0 = max(1, p0y), cz0 = max(1, p0z);             // :44-46 (clamped AFTER p1 = p0 + 1)
+    const int cx1 = p0x + 1, cy1 = p0y + 1, cz1 = p0z + 1;
 
-    float px_cont = ((float)fine_gx - 0.5f) * 0.5f;
-    float py_cont = ((float)fine_gy - 0.5f) * 0.5f;
-    float pz_cont = ((float)fine_gz - 0.5f) * 0.5f;
-    int px0 = (int)floorf(px_cont), py0 = (int)floorf(py_cont), pz0 = (int)floorf(pz_cont);
-    const int px1 = px0 + 1, py1 = py0 + 1, pz1 = pz0 + 1;
-    const float wx = px_cont - (float)px0, wy = py_cont - (float)py0, wz = pz_cont - (float)pz0;
-    px0 = max(1, px0); py0 = max(1, py0); pz0 = max(1, pz0);
-
-    // corner order: 000,100,010,110,001,101,011,111 (x fastest)
-    int pb[8], loc[8];
+    int pb[8], loc[8];   // corner order 000,100,010,110,001,101,011,111 (x fastest)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int pgx = (q & 1) ? px1 : px0, pgy = (q & 2) ? py1 : py0, pgz = (q & 4) ? pz1 : pz0;
+    for (int c = 0; c < 8; ++c) {
+        const int pgx = (c & 1) ? cx1 : cx0, pgy = (c & 2) ? cy1 : cy0, pgz = (c & 4) ? cz1 : cz0;
         const int bx = (pgx - 1) >> 3, by = (pgy - 1) >> 3, bz = (pgz - 1) >> 3;
-        pb[q] = -1;   // (owner rank << 24) | owner-local block index
-        if (bx >= 0 && bx < a.pdimx && by >= 0 && by < a.pdimy && bz >= 0 && bz < a.pdimz) pb[q] = a.pptr[bx + a.pdimx * (by + a.pdimy * bz)];
-        loc[q] = ((pgx - 1) & 7) + 8 * ((pgy - 1) & 7) + 64 * ((pgz - 1) & 7);
+        pb[c] = -1;   // (owner rank << 24) | owner-local block index
+        if (bx >= 0 && bx < a.pdimx && by >= 0 && by < a.pdimy && bz >= 0 && bz < a.pdimz) pb[c] = a.pptr[bx + a.pdimx * (by + a.pdimy * bz)];
+        loc[c] = ((pgx - 1) & 7) + 8 * ((pgy - 1) & 7) + 64 * ((pgz - 1) & 7);
     }
     const bool blend = a.use_temporal == 1 && a.tw < 0.99f;
     const float tw = a.tw;
     // rho, u at the corners (invalid corner: (1,0,0,0); corners 1..7 then fall back to corner 0, valid or not)
     float cr[8], cux[8], cuy[8], cuz[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (pb[q] >= 0) {
-            const int pr = pb[q] >> PTR_RANK_SHIFT, pl = pb[q] & PTR_LOCAL_MASK;
-            const size_t ri = (size_t)pl * BS3 + loc[q], vi = (size_t)pl * 3 * BS3 + loc[q];
+    for (int c = 0; c < 8; ++c) {
+        if (pb[c] >= 0) {
+            const int pr = pb[c] >> PTR_RANK_SHIFT, pl = pb[c] & PTR_LOCAL_MASK;
+            const size_t ri = (size_t)pl * BS3 + loc[c], vi = (size_t)pl * 3 * BS3 + loc[c];
             const float* __restrict__ vn = a.pvel_new.p[pr];
             float r = a.prho_new.p[pr][ri], x = vn[vi], y = vn[vi + BS3], z = vn[vi + 2 * BS3];
             if (blend) {
@@ -163,14 +163,15 @@ __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
                 const float ro = a.prho_old.p[pr][ri], xo = vo[vi], yo = vo[vi + BS3], zo = vo[vi + 2 * BS3];
                 r = ro * (1.0f - tw) + r * tw; x = xo * (1.0f - tw) + x * tw; y = yo * (1.0f - tw) + y * tw; z = zo * (1.0f - tw) + z * tw;
             }
-            cr[q] = r; cux[q] = x; cuy[q] = y; cuz[q] = z;
-        } else if (q == 0) {
-            cr[q] = 1.0f; cux[q] = 0.0f; cuy[q] = 0.0f; cuz[q] = 0.0f;
+            cr[c] = r; cux[c] = x; cuy[c] = y; cuz[c] = z;
+        } else if (c == 0) {
+            cr[c] = 1.0f; cux[c] = 0.0f; cuy[c] = 0.0f; cuz[c] = 0.0f;
         } else {
-            cr[q] = cr[0]; cux[q] = cux[0]; cuy[q] = cuy[0]; cuz[q] = cuz[0];
+            cr[c] = cr[0]; cux[c] = cux[0]; cuy[c] = cuy[0]; cuz[c] = cuz[0];
         }
     }
-    auto trilin = [&](const float* v) {
+    // trilinear interpolation in the reference's order x, y, z (:110-118); w = 0.25 for the first cell of a pair, 0.75 for the second
+    auto trilin = [](const float* v, float wx, float wy, float wz) {
         float c00 = v[0] * (1.0f - wx) + v[1] * wx;
         float c01 = v[4] * (1.0f - wx) + v[5] * wx;
         float c10 = v[2] * (1.0f - wx) + v[3] * wx;
@@ -179,31 +180,44 @@ __global__ void __launch_bounds__(128) ghost_interp_kernel(const GhostArgs a) {
         float c1 = c01 * (1.0f - wy) + c11 * wy;
         return c0 * (1.0f - wz) + c1 * wz;
     };
-    const float rho_int = trilin(cr), ux_int = trilin(cux), uy_int = trilin(cuy), uz_int = trilin(cuz);
+    float rho_i[8], ux_i[8], uy_i[8], uz_i[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (cells & (1u << m)) {
+            const float wx = (m & 1) ? 0.75f : 0.25f, wy = (m & 2) ? 0.75f : 0.25f, wz = (m & 4) ? 0.75f : 0.25f;
+            rho_i[m] = trilin(cr, wx, wy, wz); ux_i[m] = trilin(cux, wx, wy, wz); uy_i[m] = trilin(cuy, wx, wy, wz); uz_i[m] = trilin(cuz, wx, wy, wz);
+        }
+    }
     const float tau_c = a.tau_parent - 0.5f, tau_f = a.tau - 0.5f;
     const float scale = tau_c > 1.0e-6f ? fminf(fmaxf(tau_f / tau_c, 0.01f), 100.0f) : 1.0f;
 
-    float* __restrict__ dst = a.f_ghost + (size_t)g * (Q * BS3) + c;
-    for (uint32_t m = mask; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
+    float* __restrict__ dst = a.f_ghost + (size_t)g * (Q * BS3) + (z0 * 64 + y0 * 8 + x0);
+    for (uint32_t km = word & 0x7FFFFFFu; km; km &= km - 1) {
+        const int k = __ffs(km) - 1;
         const int kx = k % 3 - 1, ky = (k / 3) % 3 - 1, kz = k / 9 - 1;
         const int d2 = kx * kx + ky * ky + kz * kz;
         const float w_k = d2 == 0 ? 8.0f / 27.0f : d2 == 1 ? 2.0f / 27.0f : d2 == 2 ? 1.0f / 54.0f : 1.0f / 216.0f;
         float cf[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (pb[q] >= 0) {
-                const int pr = pb[q] >> PTR_RANK_SHIFT, pl = pb[q] & PTR_LOCAL_MASK;
-                const size_t fi = ((size_t)pl * Q + k) * BS3 + loc[q];
+        for (int c = 0; c < 8; ++c) {
+            if (pb[c] >= 0) {
+                const int pr = pb[c] >> PTR_RANK_SHIFT, pl = pb[c] & PTR_LOCAL_MASK;
+                const size_t fi = ((size_t)pl * Q + k) * BS3 + loc[c];
                 float v = a.pf_new.p[pr][fi];
                 if (blend) v = a.pf_old.p[pr][fi] * (1.0f - tw) + v * tw;
-                cf[q] = v;
-            } else cf[q] = q == 0 ? w_k : cf[0];
+                cf[c] = v;
+            } else cf[c] = c == 0 ? w_k : cf[0];
         }
-        const float f_int = trilin(cf);
-        const float feq_int = calc_eq(rho_int, ux_int, uy_int, uz_int, w_k, (float)kx, (float)ky, (float)kz);
-        const float f_neq = f_int - feq_int;
-        dst[k * BS3] = feq_int + f_neq * scale;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if (cells & (1u << m)) {
+                const float wx = (m & 1) ? 0.75f : 0.25f, wy = (m & 2) ? 0.75f : 0.25f, wz = (m & 4) ? 0.75f : 0.25f;
+                const float f_int = trilin(cf, wx, wy, wz);
+                const float feq_int = calc_eq(rho_i[m], ux_i[m], uy_i[m], uz_i[m], w_k, (float)kx, (float)ky, (float)kz);
+                const float f_neq = f_int - feq_int;
+                dst[k * BS3 + ((m >> 2) & 1) * 64 + ((m >> 1) & 1) * 8 + (m & 1)] = feq_int + f_neq * scale;
+            }
+        }
     }
 }
 

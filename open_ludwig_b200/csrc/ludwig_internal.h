@@ -104,6 +104,7 @@ struct Level {
     float* d_fghost = nullptr;           // [n_ghost][27][512]
     int32_t* d_gcell = nullptr;          // interface pre-pass work list
     uint32_t* d_gmask = nullptr;
+    uint8_t* d_gcells8 = nullptr;
     int n_gcell = 0;
     int32_t* d_list_plain = nullptr;     // all 26 neighbours real, no feature flag
     int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
@@ -214,8 +215,9 @@ struct K1Args {
 void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
 // Arguments of the interface-halo pre-pass (k1_fast.cu ghost_interp_kernel)
 struct GhostArgs {
-    const int32_t* gcell;    // [n] ghost cell id  g*512 + z*64 + y*8 + x
-    const uint32_t* gmask;   // [n] bit k set: some real cell pulls population k from this ghost cell
+    const int32_t* gcell;    // [n] ghost group id  g*64 + qz*16 + qy*4 + qx  (a group = the 2x2x2 fine cells of one parent cell)
+    const uint32_t* gmask;   // [n] bit k set: some real cell pulls population k from a cell of this group
+    const uint8_t* gcells8;  // [n] bit (dz*4+dy*2+dx) set: that cell of the group is pulled from
     int n;
     const int32_t* gcoord;   // [n_ghost][4] ghost block coords (0-based)
     float* f_ghost;          // [n_ghost][27][512]

@@ -21,6 +21,10 @@ CASE_OVERRIDES = {
     "ball1m_coarse": ("ball1m", {"basic": {"surface_resolution": 7, "num_levels": 1, "simulation": {"steps": 500}},
                                  "advanced": {"diagnostics": {"freq": 100}}}),
     "wing5": ("Wing_5_deg", None),
+    # config 4 at a size the CPU oracle can afford: same case file (symmetric half model, WMLES, inlet turbulence,
+    # 63 196 triangles), 3 levels, 300 steps
+    "wing5_small": ("Wing_5_deg", {"basic": {"surface_resolution": 150, "num_levels": 3, "simulation": {"steps": 300, "ramp_steps": 400}},
+                                   "advanced": {"diagnostics": {"freq": 100}}}),
     "bunny": ("Stanford_bunny", None),
     # config 5: the bunny scaled to fine resolution: 6 levels, 339 M cells, 9.4 G cell-updates per coarse step
     "bunny_fine": ("Stanford_bunny", {"basic": {"surface_resolution": 1300, "num_levels": 6}}),
