@@ -33,9 +33,11 @@ def sphere_mesh(n=400, seed=3, centre=(20.0, 16.0, 16.0), radius=3.65):
     return centers, nrm, areas
 
 
-def run(lib, levels, steps, strict, wall_model=True, fine_grained=False):
+def run(lib, levels, steps, strict, wall_model=True, fine_grained=False, **overrides):
     cells = tuple(8 * d for d in DIMS)
-    p = default_params(cells, strict=strict, wall_model_active=int(wall_model), use_temporal=1, inlet_turbulence=0.02)
+    kw = dict(strict=strict, wall_model_active=int(wall_model), use_temporal=1, inlet_turbulence=0.02)
+    kw.update(overrides)
+    p = default_params(cells, **kw)
     with cabi.Context(lib) as c:
         for lv in levels:
             c.add_level(lv)
@@ -100,3 +102,25 @@ def test_fast_two_level(oracle_lib, cuda_lib):
         e_rho, e_u = rel_err_rho_u(ref[lvl], got[lvl])
         assert e_rho <= 1e-5 and e_u <= 5e-5, (lvl, e_rho, e_u)
     assert agot["Cd"] == pytest.approx(aref["Cd"], rel=1e-3)     # north_star: Cd within 0.1 %
+
+
+@pytest.mark.parametrize("overrides", [dict(use_temporal=0), dict(sponge_blend=0), dict(inlet_turbulence=0.0, symmetric=1),
+                                       dict(q_min_threshold=0.3), dict(c_wale=0.2, nu_sgs_bg=0.0)])
+def test_parameter_variants(oracle_lib, cuda_lib, overrides):
+    """Every scalar argument of perform_timestep_v2! that switches a code path: temporal blending off (new parent
+    state only), sponge without population blending, no inlet noise + symmetric flag, a high Bouzidi q threshold
+    (different active-link set), WALE without the background viscosity floor."""
+    levels = build_case()
+    ref, *_ = run(oracle_lib, levels, 8, 1, False, **overrides)
+    got, *_ = run(cuda_lib, levels, 8, 1, False, **overrides)
+    for lvl in ref:
+        for name in ref[lvl]:
+            assert np.array_equal(ref[lvl][name].view(np.int32), got[lvl][name].view(np.int32)), (overrides, lvl, name)
+    fast, *_ = run(cuda_lib, levels, 8, 0, False, **overrides)
+    for lvl in ref:
+        # after 8 steps the fine level is still at rest (max|u| ~ 3e-5), so the error is bounded in absolute terms:
+        # a few ulp of a population, i.e. FP32 round-off of the regrouped sums
+        e_rho, _ = rel_err_rho_u(ref[lvl], fast[lvl])
+        assert e_rho <= 1e-5, (overrides, lvl, e_rho)
+        assert float(np.abs(ref[lvl]["vel"] - fast[lvl]["vel"]).max()) <= 1e-6, (overrides, lvl)
+        assert float(np.abs(ref[lvl]["f"] - fast[lvl]["f"]).max()) <= 2e-6, (overrides, lvl)
