@@ -62,7 +62,7 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full,
+    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
@@ -153,10 +153,10 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
     CU(cudaStreamSynchronize(ctx->stream));
     for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_gcells8, (void*)L.d_list_plain,
-                    (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full})
+                    (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full, (void*)L.d_list_nonplain})
         if (q) cudaFree(q);
     L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr; L.d_gcells8 = nullptr;
-    L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = nullptr;
+    L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = L.d_list_nonplain = nullptr;
     const int nb = L.nb;
     const int scale = 1 << (L.level_id - 1);
     const int ext[3] = {p.domain_nx * scale / BS, p.domain_ny * scale / BS, p.domain_nz * scale / BS};   // blocks per axis
@@ -235,7 +235,10 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
             CU(memcpy_sync(ctx->stream, L.d_gcells8, gcells8.data(), gcells8.size(), cudaMemcpyHostToDevice));
         }
     }
-    struct { std::vector<int32_t>* v; int32_t** d; } lists[4] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}};
+    std::vector<int32_t> ln(lg);
+    ln.insert(ln.end(), le.begin(), le.end()); ln.insert(ln.end(), lf.begin(), lf.end());
+    std::sort(ln.begin(), ln.end());   // Morton order
+    struct { std::vector<int32_t>* v; int32_t** d; } lists[5] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}, {&ln, &L.d_list_nonplain}};
     for (auto& l : lists) {
         CU(dalloc(ctx, l.d, l.v->size()));
         if (!l.v->empty()) CU(memcpy_sync(ctx->stream, *l.d, l.v->data(), l.v->size() * 4, cudaMemcpyHostToDevice));
@@ -328,9 +331,25 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         return fail(ctx, LUDWIG_ESTATE, !ctx->peers_attached ? "multi-GPU context: call ludwig_ipc_attach before stepping"
                                                             : "multi-GPU stepping supports fast mode only (strict_fp = 0)");
     if (p.strict_fp) {
-        a.list = nullptr; a.n_list = L.nb;
-        launch_k1_generic_strict(a, ctx->stream);
-        ctx->launches += 1;
+        // parity build: reference operation order, no FMA.  Plain interior blocks run the packed two-cells-per-thread
+        // kernel (same bits), everything else the generic one-thread-per-cell kernel with in-kernel interpolation.
+        static const bool generic_only = getenv("LUDWIG_STRICT_GENERIC") != nullptr;
+        int rc = generic_only ? LUDWIG_OK : ensure_fast_tables(ctx, L, p);
+        if (rc) return rc;
+        if (generic_only) {
+            a.list = nullptr; a.n_list = L.nb;
+            launch_k1_generic_strict(a, ctx->stream);
+            ctx->launches += 1;
+        } else {
+            a.list = L.d_list_plain; a.n_list = L.n_plain;
+            if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
+            launch_k1_strict_packed(a, ctx->stream);
+            if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
+            if (L.n_plain > 0) ctx->launches += 1;
+            a.list = L.d_list_nonplain; a.n_list = L.nb - L.n_plain;
+            launch_k1_generic_strict(a, ctx->stream);
+            if (a.n_list > 0) ctx->launches += 1;
+        }
     } else {
         int rc = ensure_fast_tables(ctx, L, p);
         if (rc) return rc;

@@ -110,6 +110,7 @@ struct Level {
     int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
     int32_t* d_list_feat = nullptr;      // all 26 neighbours present, some feature flag
     int32_t* d_list_full = nullptr;      // some neighbour missing (domain face)
+    int32_t* d_list_nonplain = nullptr;  // plain_g + feat + full (strict mode: the generic strict kernel)
     int n_plain = 0, n_plain_g = 0, n_feat = 0, n_full = 0;
 
     // static fields (device)
@@ -213,6 +214,8 @@ struct K1Args {
 
 // k1_generic_strict.cu (compiled with -fmad=false): the parity build, one thread per cell, reference operation order
 void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
+// k1_strict_packed.cu (-fmad=false): the same bits for plain interior blocks, two cells per thread, packed FP32x2
+void launch_k1_strict_packed(const K1Args& a, cudaStream_t s);
 // Arguments of the interface-halo pre-pass (k1_fast.cu ghost_interp_kernel)
 struct GhostArgs {
     const int32_t* gcell;    // [n] ghost group id  g*64 + qz*16 + qy*4 + qx  (a group = the 2x2x2 fine cells of one parent cell)
