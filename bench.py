@@ -225,6 +225,19 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # ---- timed region 3: the same steps in the STRICT build (reference operation order, no FMA: bit-exact against the
+    # CPU oracle) — reported beside the fast-mode headline, not instead of it
+    strict_ms = None
+    if world == 1 and not args.strict:
+        ps = cabi.Params.from_buffer_copy(bytes(p)); ps.strict_fp = 1
+        ctx.step_batch(t, 2, 0.03, ps); t += 2
+        barrier()
+        ev0.record(stream)
+        ctx.step_batch(t, args.steps, 0.03, ps); t += args.steps
+        ev1.record(stream)
+        barrier()
+        strict_ms = ev0.elapsed_time(ev1)
+
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     ncell = torch.tensor([cells_per_rank], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -257,6 +270,9 @@ def run_ours(args, rank, local_rank, world):
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
             "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": int(64), "d2h_bytes_per_step": int(stats_parts * 48),
                     "what": "ludwig_step_batch(1 step, host params) + ludwig_flow_stats (device reduction, D2H, host sync) every step"},
+            "strict_mode": ({"value": total_cells * args.steps / (strict_ms * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": strict_ms / args.steps,
+                             "what": "same workload with strict_fp = 1: the reference's FP32 operation order without FMA contraction, "
+                                     "bit-exact against the CPU oracle (tests/test_large_sizes_gpu.py)"} if strict_ms else None),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "setup_s": setup_s,
