@@ -190,7 +190,10 @@ int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
  * populations and velocities of neighbour blocks owned by another GPU directly through the peer mapping (NVLink
  * loads inside the stream-collide kernel: no halo packing, no exchange phase), the interface pre-pass and K3 read
  * remote parents / cells the same way.  The only collective the data path needs is a cross-rank barrier after every
- * level step (registered with ludwig_set_barrier_callback; may be stream-ordered).  ludwig_flow_stats and
+ * level step.  By default the library runs it itself: a one-warp kernel on the context's stream stores this rank's epoch
+ * into every peer's flag slots over NVLink and spins on its own slots (stream-ordered, no host round trip, no NCCL; a
+ * ~20 s time-out is reported by ludwig_sync).  ludwig_set_barrier_callback replaces it with a caller-supplied barrier
+ * (e.g. a stream-ordered NCCL all-reduce).  ludwig_flow_stats and
  * ludwig_compute_aerodynamics return the calling rank's PARTIAL result (triangles dealt round-robin); all 18
  * aerodynamic outputs are linear in the partial sums, so the caller adds them over the ranks.  Fast mode only. */
 int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* [world+1] or NULL */);  /* equal-count rule */
@@ -213,6 +216,9 @@ int ludwig_level_upload_local(ludwig_ctx* ctx, int32_t level, int32_t which, con
 int ludwig_level_download_local(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst);
 int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_t* needed_bytes);
 int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_per_rank);
+/* The same attach for contexts that live in ONE process (a single host thread driving several GPUs, or several virtual
+ * ranks on one GPU for profiling): peers[r] = the context of rank r, peers[rank] == ctx.  No IPC handles involved. */
+int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const* peers, int32_t n_peers);
 
 /* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */
 
@@ -227,8 +233,10 @@ int64_t ludwig_launch_count(const ludwig_ctx* ctx);
 int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on);
 int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, int64_t* cells);
 /* Device time [ms] per launch class accumulated by the last ludwig_profile_read: 0 K1 plain, 1 K1 plain+ghost,
- * 2 K1 feature, 3 K1 full, 4 interface pre-pass, 5 Bouzidi (classes 1-3 only when launched on the main stream). */
+ * 2 K1 feature, 3 K1 full, 4 interface pre-pass, 5 Bouzidi, 6 cross-rank barriers, 7 whole level steps (classes 1-3 only when
+ * launched on the main stream).  ludwig_profile_levels: the same split per level, out[level * 8 + class]. */
 int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]);
+int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity /* >= 8 * levels */);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_partition_plan",
     "ludwig_ctx_set_partition_keys", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
+    "ludwig_attach_inprocess", "ludwig_profile_levels",
 )
 
 BARRIER_CB = C.CFUNCTYPE(None, C.c_void_p)
@@ -116,6 +117,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_level_download_local": (C.c_int, [vp, i32, i32, vp]),
         "ludwig_ipc_export": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
         "ludwig_ipc_attach": (C.c_int, [vp, vp, i64]),
+        "ludwig_attach_inprocess": (C.c_int, [vp, C.POINTER(vp), i32]),
+        "ludwig_profile_levels": (C.c_int, [vp, C.POINTER(f64), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -239,13 +242,20 @@ class Context:
         self._check(self.lib.ludwig_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(cells)), "ludwig_profile_read")
         return ms.value, n.value, cells.value
 
-    PROFILE_CLASSES = ("k1_plain", "k1_plain_ghost", "k1_feature", "k1_full", "interface_prepass", "bouzidi", "-", "-")
+    PROFILE_CLASSES = ("k1_plain", "k1_plain_ghost", "k1_feature", "k1_full", "interface_prepass", "bouzidi", "barrier", "level_step")
 
     def profile_classes(self) -> dict:
         """Device ms per launch class of the last profile_read()."""
         out = (C.c_double * 8)()
         self._check(self.lib.ludwig_profile_classes(self._h, out), "ludwig_profile_classes")
         return {k: v for k, v in zip(self.PROFILE_CLASSES, list(out)) if k != "-"}
+
+    def profile_levels(self) -> list:
+        """Device ms per (level, launch class) of the last profile_read(): one dict per level."""
+        n = int(self.lib.ludwig_num_levels(self._h))
+        out = (C.c_double * (8 * n))()
+        self._check(self.lib.ludwig_profile_levels(self._h, out, 8 * n), "ludwig_profile_levels")
+        return [{k: out[8 * l + i] for i, k in enumerate(self.PROFILE_CLASSES) if k != "-"} for l in range(n)]
 
     # -- multi-GPU (one process per GPU) ----------------------------------------------------
     def set_partition(self, rank: int, world: int):
@@ -286,6 +296,13 @@ class Context:
     def ipc_attach(self, all_handles: bytes, bytes_per_rank: int):
         buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
         self._check(self.lib.ludwig_ipc_attach(self._h, buf, bytes_per_rank), "ludwig_ipc_attach")
+
+    @staticmethod
+    def attach_inprocess(contexts):
+        """Peers living in this process: contexts[r] is rank r of len(contexts) (ludwig_attach_inprocess)."""
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        for c in contexts:
+            c._check(c.lib.ludwig_attach_inprocess(c._h, arr, len(contexts)), "ludwig_attach_inprocess")
 
     # -- upload (main.jl:98,101,145) ---------------------------------------------------
     @staticmethod

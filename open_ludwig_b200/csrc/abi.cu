@@ -253,7 +253,8 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
 }
 
 // Profiling brackets (ludwig_profile_enable): CUDA events on the main stream around one launch, tagged with a class:
-// 0 K1 plain, 1 K1 plain+ghost, 2 K1 feature, 3 K1 full (missing neighbours), 4 interface pre-pass, 5 Bouzidi.
+// 0 K1 plain, 1 K1 plain+ghost, 2 K1 feature, 3 K1 full (missing neighbours), 4 interface pre-pass, 5 Bouzidi, 6 barrier,
+// 7 whole level step.
 int prof_begin(ludwig_ctx* ctx, int cls, bool active) {
     if (!ctx->profiling || !active) return LUDWIG_OK;
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
@@ -262,7 +263,7 @@ int prof_begin(ludwig_ctx* ctx, int cls, bool active) {
         ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
     }
     if (ctx->ev_class.size() < ctx->ev_pool.size() / 2) ctx->ev_class.resize(ctx->ev_pool.size() / 2);
-    ctx->ev_class[ctx->ev_used / 2] = cls;
+    ctx->ev_class[ctx->ev_used / 2] = cls | (ctx->prof_level << 3);
     CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
     return LUDWIG_OK;
 }
@@ -272,6 +273,18 @@ int prof_end(ludwig_ctx* ctx, bool active, int64_t cells) {
     ctx->ev_used += 2;
     ctx->prof_cells += cells;
     return LUDWIG_OK;
+}
+
+// Cross-rank barrier after a level step: the registered callback if any, else the native peer-flag kernel.
+// Profiling class 6 = device time spent in barriers (mostly waiting for the slowest rank of that level step).
+int rank_barrier(ludwig_ctx* ctx) {
+    if (ctx->world <= 1) return LUDWIG_OK;
+    int rc;
+    if ((rc = prof_begin(ctx, 6, true))) return rc;
+    if (ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);
+    else if (ctx->peers_attached && ctx->d_bar)
+        launch_peer_barrier(ctx->peer_bar, ctx->d_bar, ctx->rank, ctx->world, ++ctx->bar_epoch, ctx->d_bar_err, ctx->stream);
+    return prof_end(ctx, true, 0);
 }
 
 // Active Bouzidi links of the local boundary cells for a given q_min (bouzidi_kernel.jl:36-38: q > q_min && q <= 1).
@@ -303,6 +316,14 @@ int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
 // perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2.
 int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p) {
     const int in = (t_sub % 2 == 0) ? 0 : 1, out = 1 - in;   // solver_control.jl:35-41
+    ctx->prof_level = L.level_id - 1;
+    // class 7: the whole level step on the main stream (its kernels, side-stream joins and barriers)
+    size_t p7 = (size_t)-1;
+    if (ctx->profiling) {
+        int rc7 = prof_begin(ctx, 7, true);
+        if (rc7) return rc7;
+        p7 = ctx->ev_used; ctx->ev_used += 2;
+    }
     int rho_out = L.rho_cur;
     if (L.d_rho[1]) rho_out = 1 - L.rho_cur;   // keep the pre-step density for the children
     K1Args a{};
@@ -355,6 +376,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if (rc) return rc;
         a.nbr = L.d_nbr_fast;
         a.ghost_delta = L.d_fghost ? (long long)(L.d_fghost - L.d_f[in]) : 0;
+        bool overlap_pre = false;
         if (L.n_gcell > 0 && pv) {   // interface halo pre-pass: fills the ghost blocks K1 is about to pull from
             GhostArgs g{};
             g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.gcells8 = L.d_gcells8; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
@@ -366,9 +388,20 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             }
             g.pptr = pv->P->d_ptr; g.pdimx = pv->P->dimx; g.pdimy = pv->P->dimy; g.pdimz = pv->P->dimz;
             g.tau = L.tau; g.tau_parent = pv->P->tau; g.tw = tw; g.use_temporal = p.use_temporal;
-            if ((rc = prof_begin(ctx, 4, true))) return rc;
-            launch_ghost_interp(g, ctx->stream);
-            if ((rc = prof_end(ctx, true, 0))) return rc;
+            // The plain K1 launch never touches a ghost block: with side streams the pre-pass runs on its own stream
+            // CONCURRENTLY with it, and only the launches that may pull from ghost blocks wait for it.  (The ghost buffer
+            // was last read by the previous step's K1 launches, all ordered before ev_pre_fork on the main stream.)
+            overlap_pre = ctx->pre_stream != nullptr && L.n_plain > 0;
+            if (overlap_pre) {
+                CU(cudaEventRecord(ctx->ev_pre_fork, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->pre_stream, ctx->ev_pre_fork, 0));
+                launch_ghost_interp(g, ctx->pre_stream);
+                CU(cudaEventRecord(ctx->ev_pre, ctx->pre_stream));
+            } else {
+                if ((rc = prof_begin(ctx, 4, true))) return rc;
+                launch_ghost_interp(g, ctx->stream);
+                if ((rc = prof_end(ctx, true, 0))) return rc;
+            }
             ctx->launches += 1;
         }
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
@@ -379,10 +412,13 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
-            if (!fork || main_stream) fn(a, ctx->stream);
-            else {
+            if (!fork || main_stream) {
+                if (overlap_pre && list != L.d_list_plain) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
+                fn(a, ctx->stream);
+            } else {
                 cudaStream_t st = ctx->side[used];
                 CU(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+                if (overlap_pre) CU(cudaStreamWaitEvent(st, ctx->ev_pre, 0));
                 fn(a, st);
                 CU(cudaEventRecord(ctx->ev_join[used], st));
                 ++used;
@@ -405,28 +441,42 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+        if (overlap_pre) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));   // nothing on the main stream consumed it yet
     }
-    const bool mg = ctx->world > 1 && ctx->barrier_cb;
+    const bool mg = ctx->world > 1;
     if (L.bouzidi) {
         // K2 reads f_out of x_ff cells that may belong to another GPU: K1 must be complete everywhere before the
         // gather, and every gather before any scatter (the same two-phase argument as on one GPU, across ranks).
-        if (mg) ctx->barrier_cb(ctx->barrier_user);
+        if (mg) rank_barrier(ctx);
         int rcb = ensure_bouzidi_links(ctx, L, p.q_min_threshold);
         if (rcb) return rcb;
         int rcp;
         if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
         launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 1, ctx->stream);
         if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
-        if (mg) ctx->barrier_cb(ctx->barrier_user);
+        if (mg) rank_barrier(ctx);
         if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
         launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 2, ctx->stream);
         if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
         if (L.n_links > 0) ctx->launches += 2;
     }
-    if (mg) ctx->barrier_cb(ctx->barrier_user);   // every rank finished this level step
+    if (mg) rank_barrier(ctx);   // every rank finished this level step
+    if (p7 != (size_t)-1) CU(cudaEventRecord(ctx->ev_pool[p7 + 1], ctx->stream));
     L.rho_cur = rho_out;
     L.last_t_sub = t_sub;
     CU(cudaGetLastError());
+    return LUDWIG_OK;
+}
+
+// Multi-GPU: build every lazily built host table (fast-mode lists, ghost blocks, compacted Bouzidi links) BEFORE the first
+// cross-rank barrier of a call, so that no rank sits in a barrier kernel while a peer is still doing seconds of host work.
+int prepare_tables(ludwig_ctx* ctx, const ludwig_params& p) {
+    if (ctx->world <= 1 || p.strict_fp) return LUDWIG_OK;
+    for (Level* L : ctx->levels) {
+        int rc = ensure_fast_tables(ctx, *L, p);
+        if (rc) return rc;
+        if (L->bouzidi && (rc = ensure_bouzidi_links(ctx, *L, p.q_min_threshold))) return rc;
+    }
     return LUDWIG_OK;
 }
 
@@ -441,6 +491,28 @@ int recursive_step(ludwig_ctx* ctx, size_t lvl, int64_t t_sub, const ParentView*
         if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub, &me, 0.0f, u, p))) return rc;
         if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p))) return rc;
     }
+    return LUDWIG_OK;
+}
+
+// Remote-block offset tables, relative to the local buffers (K1 adds them to f_in / vel_in); last step of an attach.
+int finish_attach(ludwig_ctx* ctx) {
+    for (Level* Lp : ctx->levels) {
+        Level& L = *Lp;
+        set_own_peers(ctx, L);
+        if (L.n_remote == 0) continue;
+        for (int par = 0; par < 2; ++par) {
+            std::vector<long long> of(L.n_remote), ov(L.n_remote);
+            for (int i = 0; i < L.n_remote; ++i) {
+                const int ow = L.remote_owner[i];
+                of[i] = (long long)((L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3) - L.d_f[par]);
+                ov[i] = (long long)((L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3) - L.d_vel[par]);
+            }
+            CU(dalloc(ctx, &L.d_roff_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_roff_v[par], (size_t)L.n_remote));
+            CU(memcpy_sync(ctx->stream, L.d_roff_f[par], of.data(), of.size() * 8, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_roff_v[par], ov.data(), ov.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    ctx->peers_attached = true;
     return LUDWIG_OK;
 }
 
@@ -468,7 +540,11 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
         for (int i = 0; i < 3 && ok; ++i)
             ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_pre_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
+        if (getenv("LUDWIG_SERIAL_PREPASS")) { cudaStreamDestroy(ctx->pre_stream); ctx->pre_stream = nullptr; }
         if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
@@ -486,6 +562,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (Level* L : ctx->levels) free_level(L);
+    if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -513,11 +590,13 @@ int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, in
     double tot = 0;
     int64_t n0 = 0;
     for (int c = 0; c < 8; ++c) ctx->prof_class_ms[c] = 0;
+    ctx->prof_level_ms.assign(ctx->levels.size() * 8, 0.0);
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
-        const int c = ctx->ev_class[i / 2];
-        ctx->prof_class_ms[c & 7] += ms;
+        const int c = ctx->ev_class[i / 2] & 7, lv = ctx->ev_class[i / 2] >> 3;
+        ctx->prof_class_ms[c] += ms;
+        if ((size_t)lv < ctx->levels.size()) ctx->prof_level_ms[(size_t)lv * 8 + c] += ms;
         if (c == 0) { tot += ms; ++n0; }
     }
     if (ms_total) *ms_total = tot;            // class 0 only: the dominant plain K1 kernel
@@ -533,9 +612,20 @@ int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]) {
     return LUDWIG_OK;
 }
 
+int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity) {
+    if (!ctx || !out || capacity < (int32_t)ctx->prof_level_ms.size()) return fail(ctx, LUDWIG_EINVAL, "profile_levels: need 8 doubles per level");
+    for (size_t i = 0; i < ctx->prof_level_ms.size(); ++i) out[i] = ctx->prof_level_ms[i];   // [level][class], last ludwig_profile_read
+    return LUDWIG_OK;
+}
+
 int ludwig_sync(ludwig_ctx* ctx) {
     if (!ctx) return LUDWIG_EINVAL;
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_bar_err) {
+        int e = 0;
+        CU(memcpy_sync(ctx->stream, &e, ctx->d_bar_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) return fail(ctx, LUDWIG_ESTATE, "cross-GPU barrier timed out (a peer stopped, or the ranks issued different call sequences)");
+    }
     return LUDWIG_OK;
 }
 
@@ -872,9 +962,11 @@ int ludwig_init_equilibrium(ludwig_ctx* ctx) {
 int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params) {
     if (!ctx || !params || ctx->levels.empty() || batch_size < 0) return fail(ctx, LUDWIG_EINVAL, "bad step args");
     CU(cudaSetDevice(ctx->device));
-    if (ctx->world > 1 && !ctx->barrier_cb) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: register ludwig_set_barrier_callback first");
+    if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach first");
+    int rcp = prepare_tables(ctx, *params);
+    if (rcp) return rcp;
     // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
-    if (ctx->world > 1) ctx->barrier_cb(ctx->barrier_user);
+    rank_barrier(ctx);
     for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
         int rc = recursive_step(ctx, 0, t_start + t_offset, nullptr, 0.0f, u_curr, *params);
         if (rc) return rc;
@@ -887,7 +979,9 @@ int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t par
     if (!level_ok(ctx, level) || !params) return fail(ctx, LUDWIG_EINVAL, "bad level");
     CU(cudaSetDevice(ctx->device));
     Level& L = *ctx->levels[level];
-    if (ctx->world > 1 && ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);
+    int rcp = prepare_tables(ctx, *params);
+    if (rcp) return rcp;
+    rank_barrier(ctx);
     if (level == 0) return step_level(ctx, L, nullptr, t_sub, temporal_weight, u_curr, *params);
     Level& P = *ctx->levels[level - 1];
     if (params->use_temporal && !P.temporal) return fail(ctx, LUDWIG_ESTATE, "parent has no temporal storage");
@@ -921,7 +1015,7 @@ int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* F, int32_t level
     const float pscale = (float)(rho_phys * velocity_scale * velocity_scale);   // forces/surface.jl:402-403
     const float offx = (float)mesh_offset[0], offy = (float)mesh_offset[1], offz = (float)mesh_offset[2];
     // K3 reads level.rho and level.vel (NOT vel_temp) whatever the parity — forces/surface.jl:412
-    if (ctx->world > 1 && ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);   // K3 reads cells owned by other GPUs
+    rank_barrier(ctx);   // K3 reads cells owned by other GPUs
     // multi-GPU: triangles are dealt round-robin to the ranks; each rank returns PARTIAL sums (every output of this
     // call is linear in them), the caller adds the 18 numbers over the ranks.
     PeerBytes obs;
@@ -1084,6 +1178,12 @@ int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
     if (!ctx || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world) return fail(ctx, LUDWIG_EINVAL, "bad rank/world (max 8 ranks)");
     if (!ctx->levels.empty()) return fail(ctx, LUDWIG_ESTATE, "set the partition before creating levels");
     ctx->rank = rank; ctx->world = world;
+    if (world > 1 && !ctx->d_bar) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMalloc((void**)&ctx->d_bar, 2 * 1024 * 1024));        // own allocation granule: IPC exports whole allocations
+        CU(cudaMemset(ctx->d_bar, 0, 2 * 1024 * 1024));
+        ctx->d_bar_err = (int*)(ctx->d_bar + 64);
+    }
     return LUDWIG_OK;
 }
 
@@ -1105,7 +1205,7 @@ int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, 
 int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_t* needed_bytes) {
     if (!ctx) return LUDWIG_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    const int64_t need = (int64_t)ctx->levels.size() * 7 * (int64_t)sizeof(cudaIpcMemHandle_t);
+    const int64_t need = ((int64_t)ctx->levels.size() * 7 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);   // + the barrier slots
     if (needed_bytes) *needed_bytes = need;
     if (!out) return LUDWIG_OK;
     if (capacity_bytes < need) return fail(ctx, LUDWIG_EINVAL, "ipc export buffer too small");
@@ -1118,6 +1218,7 @@ int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_
         for (int i = 0; i < 7; ++i)
             if (ptrs[i]) CU(cudaIpcGetMemHandle(&h[l * 7 + i], ptrs[i]));
     }
+    if (ctx->d_bar) CU(cudaIpcGetMemHandle(&h[ctx->levels.size() * 7], ctx->d_bar));
     return LUDWIG_OK;
 }
 
@@ -1125,11 +1226,17 @@ int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_
 int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_per_rank) {
     if (!ctx || !all_handles) return fail(ctx, LUDWIG_EINVAL, "bad attach args");
     CU(cudaSetDevice(ctx->device));
-    const int64_t need = (int64_t)ctx->levels.size() * 7 * (int64_t)sizeof(cudaIpcMemHandle_t);
+    const int64_t need = ((int64_t)ctx->levels.size() * 7 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);
     if (bytes_per_rank != need) return fail(ctx, LUDWIG_EINVAL, "ipc attach: handle buffer size mismatch (same levels on every rank?)");
     for (int r = 0; r < ctx->world; ++r) {
         if (r == ctx->rank) continue;
         const auto* h = (const cudaIpcMemHandle_t*)((const char*)all_handles + (size_t)r * need);
+        if (ctx->d_bar) {
+            void* m = nullptr;
+            CU(cudaIpcOpenMemHandle(&m, h[ctx->levels.size() * 7], cudaIpcMemLazyEnablePeerAccess));
+            ctx->ipc_opened.push_back(m);
+            ctx->peer_bar[r] = (unsigned int*)m;
+        }
         for (size_t l = 0; l < ctx->levels.size(); ++l) {
             Level& L = *ctx->levels[l];
             void* own[7] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle};
@@ -1145,25 +1252,39 @@ int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_pe
             L.peer_obstacle[r] = (const uint8_t*)mapped[6];
         }
     }
-    // remote-block offset tables, relative to the local buffers (K1 adds them to f_in / vel_in)
-    for (Level* Lp : ctx->levels) {
-        Level& L = *Lp;
-        set_own_peers(ctx, L);
-        if (L.n_remote == 0) continue;
-        for (int par = 0; par < 2; ++par) {
-            std::vector<long long> of(L.n_remote), ov(L.n_remote);
-            for (int i = 0; i < L.n_remote; ++i) {
-                const int ow = L.remote_owner[i];
-                of[i] = (long long)((L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3) - L.d_f[par]);
-                ov[i] = (long long)((L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3) - L.d_vel[par]);
-            }
-            CU(dalloc(ctx, &L.d_roff_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_roff_v[par], (size_t)L.n_remote));
-            CU(memcpy_sync(ctx->stream, L.d_roff_f[par], of.data(), of.size() * 8, cudaMemcpyHostToDevice));
-            CU(memcpy_sync(ctx->stream, L.d_roff_v[par], ov.data(), ov.size() * 8, cudaMemcpyHostToDevice));
+    return finish_attach(ctx);
+}
+
+// Peers that live in THIS process (one host thread driving several contexts, on one device or on several): the peer
+// tables are filled from the other contexts directly, no IPC handles.  peers[r] is the context of rank r (peers[rank] ==
+// ctx).  With contexts on different devices, peer access is enabled here.  The native peer-flag barrier works unchanged as
+// long as the caller enqueues the same level step on every context before any barrier's ~20 s time-out (tools/emulate_ranks.py
+// registers a no-op barrier instead and runs one virtual rank at a time to measure its share of a partitioned case).
+int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const* peers, int32_t n_peers) {
+    if (!ctx || !peers || n_peers != ctx->world) return fail(ctx, LUDWIG_EINVAL, "attach_inprocess: one context per rank");
+    CU(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->world; ++r) {
+        ludwig_ctx* o = peers[r];
+        if (r == ctx->rank) { if (o != ctx) return fail(ctx, LUDWIG_EINVAL, "attach_inprocess: peers[rank] must be this context"); continue; }
+        if (!o || o->world != ctx->world || o->rank != r || o->levels.size() != ctx->levels.size())
+            return fail(ctx, LUDWIG_EINVAL, "attach_inprocess: peer context has a different partition / level count");
+        if (o->device != ctx->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctx->device, o->device));
+            if (!can) return fail(ctx, LUDWIG_ECUDA, "attach_inprocess: no peer access between the two devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+            cudaGetLastError();
+        }
+        ctx->peer_bar[r] = o->d_bar;
+        for (size_t l = 0; l < ctx->levels.size(); ++l) {
+            Level& L = *ctx->levels[l];
+            const Level& O = *o->levels[l];
+            for (int i = 0; i < 2; ++i) { L.peer_f[i][r] = O.d_f[i]; L.peer_vel[i][r] = O.d_vel[i]; L.peer_rho[i][r] = O.d_rho[i]; }
+            L.peer_obstacle[r] = O.d_obstacle;
         }
     }
-    ctx->peers_attached = true;
-    return LUDWIG_OK;
+    return finish_attach(ctx);
 }
 
 }  // extern "C"

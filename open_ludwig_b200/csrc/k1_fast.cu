@@ -80,30 +80,30 @@ __device__ __forceinline__ void acc_pair(Moments& m, v2 fk, v2 fo) {
     if (cz * cx == 1) m.Pzx = vadd(m.Pzx, s); else if (cz * cx == -1) m.Pzx = vsub(m.Pzx, s);
 }
 
-// Wall-model force of one cell (physics_kernels.jl:206-236), scalar: only near-wall cells get here.
-__device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, float uy, float uz, float tau) {
+// Wall-model force of one cell (physics_kernels.jl:206-236), scalar: only near-wall cells get here.  Fast mode: the
+// 1/7 power and the logarithm are MUFU lg2/ex2 sequences (relative error ~1e-7, far below the model's own accuracy and
+// the fast-mode round-off budget), divisions are reciprocal multiplies, (2 * 8.3)^(-1/7) is a constant; inlined, so a
+// warp with near-wall lanes spends ~60 instructions per cell here instead of two libdevice powf calls and five IEEE divides.
+__device__ __forceinline__ float3 wall_force(float dist_wall, float rho, float ux, float uy, float uz, float tau) {
     float3 F = make_float3(0.f, 0.f, 0.f);
     if (dist_wall > 0.0f && dist_wall < 10.0f) {
-        float u_mag = sqrtf(ux * ux + uy * uy + uz * uz);
-        float nu_visc = (tau - 0.5f) / 3.0f;
+        const float u_mag = sqrt_approx(ux * ux + uy * uy + uz * uz);
+        const float nu_visc = (tau - 0.5f) * (1.0f / 3.0f);
         if (u_mag > 1.0e-6f && nu_visc > 1.0e-10f) {
-            float u_tau = u_mag * powf(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * powf(2.0f * 8.3f, -1.0f / 7.0f);
+            const float inv_d = rcp_approx(dist_wall), inv_nu = rcp_approx(nu_visc);
+            const float ratio = nu_visc * rcp_approx(dist_wall * u_mag + 1.0e-10f);
+            float u_tau = u_mag * exp2f((1.0f / 7.0f) * __log2f(ratio)) * 0.66942024f;   // (2 * 8.3)^(-1/7)
             u_tau = fmaxf(u_tau, 1.0e-6f);
-            float y_p = u_tau * dist_wall / nu_visc;
+            const float y_p = u_tau * dist_wall * inv_nu;
             if (y_p > 11.81f) {
-                float u_plus_law = (1.0f / KAPPA) * logf(y_p) + 5.2f;
-                if (u_plus_law > 0.1f) {
-                    u_tau = u_tau * ((u_mag / u_tau) / u_plus_law);
-                    u_tau = fmaxf(u_tau, 1.0e-6f);
-                }
+                const float u_plus_law = (1.0f / KAPPA) * (0.69314718f * __log2f(y_p)) + 5.2f;
+                if (u_plus_law > 0.1f) u_tau = fmaxf(u_mag * rcp_approx(u_plus_law), 1.0e-6f);   // u_tau (u_mag / u_tau) / u_plus
             }
-            float tau_wall = rho * u_tau * u_tau;
-            float tau_res = rho * nu_visc * (u_mag / dist_wall);
+            const float tau_wall = rho * u_tau * u_tau;
+            const float tau_res = rho * nu_visc * (u_mag * inv_d);
             if (tau_wall > tau_res) {
-                float force_mag = (tau_wall - tau_res) / dist_wall;
-                F.x = -force_mag * ux / u_mag;
-                F.y = -force_mag * uy / u_mag;
-                F.z = -force_mag * uz / u_mag;
+                const float s = -(tau_wall - tau_res) * inv_d * rcp_approx(u_mag);
+                F.x = s * ux; F.y = s * uy; F.z = s * uz;
             }
         }
     }
@@ -308,31 +308,18 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
     float* __restrict__ rout = a.rho_out + (size_t)b * BS3 + c0;
 
     // Full-way bounce-back (physics_kernels.jl:154-166): an obstacle cell returns every pulled population in the
-    // opposite direction, f_out[26-k] = pulled f_k.  No arithmetic: pull again and store (4-byte stores into the
-    // obstacle cell only).  Threads whose two cells are both solid do nothing else — solid blocks are a pure copy.
-    auto bounce_back = [&]() {
-#pragma unroll
-        for (int jz = 0; jz < 3; ++jz) {
-#pragma unroll
-            for (int jy = 0; jy < 3; ++jy) {
-                v2 fm, f0, fp;
-                pull3(jy, jz, fm, f0, fp);
-                const int k0 = 1 + 3 * jy + 9 * jz;
-                if (obsA && obsB) {
-                    st2(fout + (26 - (k0 - 1)) * BS3, fm); st2(fout + (26 - k0) * BS3, f0); st2(fout + (26 - (k0 + 1)) * BS3, fp);
-                } else if (obsA) {
-                    fout[(26 - (k0 - 1)) * BS3] = fm.x; fout[(26 - k0) * BS3] = f0.x; fout[(26 - (k0 + 1)) * BS3] = fp.x;
-                } else {
-                    fout[(26 - (k0 - 1)) * BS3 + 1] = fm.y; fout[(26 - k0) * BS3 + 1] = f0.y; fout[(26 - (k0 + 1)) * BS3 + 1] = fp.y;
-                }
-            }
-        }
+    // opposite direction, f_out[26-k] = pulled f_k.  No arithmetic: the values are stored straight from the pull loop below
+    // (one pass over f_in for every thread, solid or fluid); a thread with ONE obstacle cell stores its fluid cell with
+    // 4-byte stores at the end, a thread whose two cells are both solid skips the collision.
+    const bool anyobs = FULL && (obsA || obsB);
+    auto bounce3 = [&](int jy, int jz, const v2& fm, const v2& f0, const v2& fp) {
+        if (!anyobs) return;
+        const int k0 = 1 + 3 * jy + 9 * jz;
+        float* __restrict__ o = fout + (26 - (k0 + 1)) * BS3;   // slots 26-(k0+1), 26-k0, 26-(k0-1) are consecutive directions
+        if (obsA && obsB) { st2(o, fp); st2(o + BS3, f0); st2(o + 2 * BS3, fm); }
+        else if (obsA) { o[0] = fp.x; o[BS3] = f0.x; o[2 * BS3] = fm.x; }
+        else { o[1] = fp.y; o[BS3 + 1] = f0.y; o[2 * BS3 + 1] = fm.y; }
     };
-    if (FULL && obsA && obsB) {
-        bounce_back();
-        st2(vout, V(0.f)); st2(vout + BS3, V(0.f)); st2(vout + 2 * BS3, V(0.f)); st2(rout, V(1.0f));
-        return;
-    }
 
     Moments m;
     m.jx = m.jy = m.jz = m.Pxx = m.Pyy = m.Pzz = m.Pxy = m.Pyz = m.Pzx = V(0.f);
@@ -340,6 +327,7 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
         // combos c = jy + 3 jz; combo c and 8-c hold opposite directions: (km,k0,kp)(c) <-> (kp,k0,km)(8-c)
         v2 am, a0, ap, bm, b0, bp;
         pull3(1, 1, am, a0, ap);          // centre combo: k = 12,13,14
+        bounce3(1, 1, am, a0, ap);
         // moments are accumulated for f - w_k.  The FP32 weights all carry the same relative error, sum_k w_k =
         // 1 + 7.45e-9 (the reference's equilibrium therefore creates that much mass per step); adding it back here
         // keeps rho = sum_k f_k exactly as the reference computes it, and makes the shifted second moments
@@ -349,6 +337,8 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
 #define LUDWIG_COMBO(JY, JZ)                                                   \
         pull3(JY, JZ, am, a0, ap);                                             \
         pull3(2 - (JY), 2 - (JZ), bm, b0, bp);                                 \
+        bounce3(JY, JZ, am, a0, ap);                                           \
+        bounce3(2 - (JY), 2 - (JZ), bm, b0, bp);                               \
         acc_pair<3 * (JY) + 9 * (JZ)>(m, am, bp);                              \
         acc_pair<3 * (JY) + 9 * (JZ) + 1>(m, a0, b0);                          \
         acc_pair<3 * (JY) + 9 * (JZ) + 2>(m, ap, bm);
@@ -357,6 +347,11 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
         LUDWIG_COMBO(2, 0)
         LUDWIG_COMBO(0, 1)
 #undef LUDWIG_COMBO
+    }
+
+    if (FULL && obsA && obsB) {       // both cells solid: bounce-back done, vel = 0, rho = 1 (:155-158)
+        st2(vout, V(0.f)); st2(vout + BS3, V(0.f)); st2(vout + 2 * BS3, V(0.f)); st2(rout, V(1.0f));
+        return;
     }
 
     // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
@@ -488,6 +483,12 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
         uF = vfma(uz, Fz, vfma(uy, Fy, vmul(ux, Fx)));
     }
 
+    // the obstacle cell of a half-solid thread already holds its bounced-back populations: store the fluid cell only
+    auto store_f = [&](int k, v2 v) {
+        if (!anyobs) st2(fout + k * BS3, v);
+        else if (obsA) fout[k * BS3 + 1] = v.y;
+        else fout[k * BS3] = v.x;
+    };
 #pragma unroll
     for (int k = 0; k < 13; ++k) {
         const int cx = lat_cx(k), cy = lat_cy(k), cz = lat_cz(k);
@@ -518,16 +519,15 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const K1Args a) {
             odd = vfma(hw, cF, odd);
         }
         even = vmul(even, V(w)); odd = vmul(odd, V(w));
-        st2(fout + k * BS3, vadd(even, odd));
-        st2(fout + (26 - k) * BS3, vsub(even, odd));
+        store_f(k, vadd(even, odd));
+        store_f(26 - k, vsub(even, odd));
     }
     {
         v2 even = vfma(g, vneg(T), A);
         if (FULL && has_force) even = vfma(hw, vneg(uF), even);
         even = vmul(even, V(W0));
-        st2(fout + 13 * BS3, even);
+        store_f(13, even);
     }
-    if (FULL && (obsA || obsB)) bounce_back();   // overwrite the one obstacle cell of this thread
 }
 
 }  // namespace k1f

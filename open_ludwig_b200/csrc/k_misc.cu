@@ -177,6 +177,33 @@ void launch_bouzidi(const Level& L, float* f_out, const long long* roff, bool st
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-GPU barrier (multi-GPU, one process per GPU): every rank owns MAX_RANKS epoch slots in device memory that its
+// peers have mapped through CUDA IPC.  Lane r writes this rank's epoch into peer r's slot [my rank] (a store over
+// NVLink), then spins on the local slot [r] until peer r has done the same.  Stream-ordered, no host round trip, ~5 us.
+// Each rank runs on its OWN GPU, so the spinning kernels never wait for a kernel queued behind them; a ~20 s time-out
+// (a peer died or the ranks issued different numbers of barriers) sets an error flag instead of hanging the GPU.
+struct BarrierPeers { unsigned int* slot[MAX_RANKS]; };
+__global__ void peer_barrier_kernel(BarrierPeers peers, unsigned int* own, int rank, int world, unsigned int epoch, int* err) {
+    const int r = threadIdx.x;
+    if (r < world && r != rank) {
+        __threadfence_system();
+        *((volatile unsigned int*)(peers.slot[r] + rank)) = epoch;
+        __threadfence_system();
+        const long long t0 = clock64();
+        while ((int)(*((volatile unsigned int*)(own + r)) - epoch) < 0) {
+            if (clock64() - t0 > 40000000000LL) { *err = 1; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+}
+void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s) {
+    BarrierPeers p;
+    for (int r = 0; r < MAX_RANKS; ++r) p.slot[r] = peer_slots[r];
+    peer_barrier_kernel<<<1, 32, 0, s>>>(p, own, rank, world, epoch, err);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3  nearest-fluid-cell search per triangle + pressure / shear (forces/surface.jl:32-124,138-266).
 // The arithmetic is written with explicit _rn intrinsics so that it matches the oracle without FMA.
 __global__ void map_stresses_kernel(const PeerPtrs rho, const PeerPtrs vel, const PeerBytes obstacle,

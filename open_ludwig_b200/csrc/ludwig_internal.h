@@ -165,6 +165,8 @@ struct ludwig_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // concurrent K1 launches of one level step on small levels
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t pre_stream = nullptr;       // interface pre-pass, concurrent with the plain K1 launch
+    cudaEvent_t ev_pre_fork = nullptr, ev_pre = nullptr;
     int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
     std::vector<ludwig::Level*> levels;
     std::string err;
@@ -180,12 +182,19 @@ struct ludwig_ctx {
     void (*barrier_cb)(void*) = nullptr;   // cross-rank barrier, stream-ordered or blocking (multi-GPU only)
     void* barrier_user = nullptr;
     std::vector<void*> ipc_opened;
+    // native peer-flag barrier (used when no callback is registered)
+    unsigned int* d_bar = nullptr;            // [MAX_RANKS] epoch slots, written by the peers
+    unsigned int* peer_bar[ludwig::MAX_RANKS] = {};   // the peers' slot arrays (IPC mappings)
+    int* d_bar_err = nullptr;
+    unsigned int bar_epoch = 0;
     int64_t launches = 0;
     // K1 profiling (ludwig_profile_enable)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)
     std::vector<int> ev_class;          // launch class of each pair
     double prof_class_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> prof_level_ms;  // [level][8]
+    int prof_level = 0;                 // level index the next bracket is tagged with
     size_t ev_used = 0;
     int64_t prof_cells = 0;
 };
@@ -247,6 +256,7 @@ void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2re
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_block_flags(Level& L, cudaStream_t s);
+void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s);
 void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
                          ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,
                          int tri_first, int tri_stride, cudaStream_t s);

@@ -254,3 +254,41 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
 def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False, build_tri_map: bool = True) -> Domain:
     """load_case_configuration + setup_multilevel_domain (main.jl:259-260, :90)."""
     return setup_multilevel_domain(load_case_configuration(case_dir, overrides), verbose=verbose, build_tri_map=build_tri_map)
+
+
+# ---- domain cache (multi-rank launches: one rank builds, the others map the arrays) -------------------
+
+_LEVEL_ARRAYS = ("block_pointer", "neighbor_table", "active_block_coords", "obstacle", "sponge", "wall_dist",
+                 "q_map", "tri_map", "cell_block", "cell_x", "cell_y", "cell_z")
+
+
+def save_domain(dom: Domain, folder: str) -> None:
+    """Write a built Domain to `folder`: every level array as its own .npy, the small host objects pickled.
+    The domain build is deterministic, so this is purely a cache: with N processes on one box (one per GPU) rank 0
+    builds with all host threads and the others load_domain() — page-cache shared, read-only memory maps."""
+    import pickle
+    os.makedirs(folder, exist_ok=True)
+    meta = []
+    for i, lv in enumerate(dom.levels):
+        scal = {k: v for k, v in vars(lv).items() if k not in _LEVEL_ARRAYS}
+        have = []
+        for k in _LEVEL_ARRAYS:
+            a = getattr(lv, k)
+            if a is not None:
+                np.save(os.path.join(folder, f"L{i}_{k}.npy"), np.ascontiguousarray(a))
+                have.append(k)
+        meta.append((scal, have))
+    with open(os.path.join(folder, "domain.pkl.tmp"), "wb") as f:
+        pickle.dump({"cfg": dom.cfg, "params": dom.params, "mesh": dom.mesh, "reports": dom.reports, "levels": meta}, f, protocol=5)
+    os.replace(os.path.join(folder, "domain.pkl.tmp"), os.path.join(folder, "domain.pkl"))   # written last: marks the cache complete
+
+
+def load_domain(folder: str) -> Domain:
+    import pickle
+    with open(os.path.join(folder, "domain.pkl"), "rb") as f:
+        d = pickle.load(f)
+    levels = []
+    for i, (scal, have) in enumerate(d["levels"]):
+        arrs = {k: (np.load(os.path.join(folder, f"L{i}_{k}.npy"), mmap_mode="r") if k in have else None) for k in _LEVEL_ARRAYS}
+        levels.append(BlockLevel(**scal, **arrs))
+    return Domain(cfg=d["cfg"], params=d["params"], mesh=d["mesh"], levels=levels, reports=d["reports"])

@@ -21,9 +21,14 @@ def init_context(lib_path=None, local_rank=None) -> cabi.Context:
     return ctx
 
 
-def attach_peers(ctx: cabi.Context, device: torch.device):
-    """Exchange the IPC handles of every rank's state and register the cross-rank barrier.  Call after the last
-    ctx.add_level()."""
+def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = None):
+    """Exchange the IPC handles of every rank's state.  Call after the last ctx.add_level().
+
+    barrier = "native" (default): the library's own peer-flag barrier kernel (flag stores over NVLink, stream-ordered,
+    no host call per barrier).  barrier = "nccl": a stream-ordered NCCL all-reduce of one float registered through
+    ludwig_set_barrier_callback (the round-1 path, kept for A/B measurements; LUDWIG_BARRIER=nccl selects it)."""
+    import os
+    barrier = barrier or os.environ.get("LUDWIG_BARRIER", "native")
     world = dist.get_world_size()
     mine = ctx.ipc_export()
     t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
@@ -31,6 +36,9 @@ def attach_peers(ctx: cabi.Context, device: torch.device):
     dist.all_gather(allt, t)
     blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allt)
     ctx.ipc_attach(blob, len(mine))
+    dist.barrier()          # every rank has opened every peer mapping before anyone steps
+    if barrier == "native":
+        return None
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
     flag = torch.zeros(1, device=device)
 

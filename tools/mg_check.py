@@ -22,7 +22,7 @@ def gather_field(ctx, level, which, lv):
     dist.all_reduce(a)
     return a.cpu().numpy()
 
-def run_box(partitioned, steps=9):
+def run_box(partitioned, steps=9, barrier="native"):
     dims = (6, 4, 4)
     lv = syn.make_box_level(*dims)
     f, rho, vel = syn.noise_state(lv)
@@ -30,7 +30,7 @@ def run_box(partitioned, steps=9):
     ctx = mg.init_context(None, lr) if partitioned else cabi.Context(device=lr)
     ctx.add_level(lv)
     if partitioned:
-        mg.attach_peers(ctx, dev)
+        mg.attach_peers(ctx, dev, barrier)
         loc = ctx.local_blocks(0)
         from open_ludwig_b200 import partition
         assert np.array_equal(loc, partition.local_blocks(lv.active_block_coords, rank, world, level=lv)), "library partition != host mirror"
@@ -75,11 +75,13 @@ def run_two_level(partitioned, steps=10, plan=False):
     return out, aero
 
 ok = True
-ref, sref = run_box(False); got, sgot = run_box(True)
-for k in ref:
-    same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
-    ok &= same
-    if rank == 0: print(f"box {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
+ref, sref = run_box(False)
+for barrier in ("native", "nccl"):       # the library's peer-flag barrier kernel, and the NCCL callback
+    got, sgot = run_box(True, barrier=barrier)
+    for k in ref:
+        same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
+        ok &= same
+        if rank == 0: print(f"box barrier={barrier} {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
 if rank == 0: print("box stats", sref["n_fluid"] == sgot["n_fluid"], abs(sref["rho_mean"] - sgot["rho_mean"]) < 1e-12, sref["rho_min"] == sgot["rho_min"], flush=True)
 ref, aref = run_two_level(False)
 for plan in (False, True):       # per-level cost-weighted cut, and the spatially aligned plan over all levels

@@ -8,7 +8,6 @@ lock-step; forces are reduced over the ranks.  Prints true MLUPS (max time over 
 """
 import os, sys, time
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
-os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))     # host-side domain build
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
@@ -23,7 +22,19 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 case, ov = CASE_OVERRIDES[name]
 t0 = time.time()
-dom = D.load_case(case_dir(case), ov, verbose=(rank == 0), build_tri_map=False)
+if world > 1:
+    # rank 0 builds the domain with every host thread and caches it in shared memory; the others map the arrays
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 8)
+    cache = f"/dev/shm/ludwig_domain_{name}_{os.getppid()}"
+    if rank == 0:
+        dom = D.load_case(case_dir(case), ov, verbose=True, build_tri_map=False)
+        D.save_domain(dom, cache)
+    else:
+        while not os.path.exists(os.path.join(cache, "domain.pkl")):
+            time.sleep(0.5)
+        dom = D.load_domain(cache)
+else:
+    dom = D.load_case(case_dir(case), ov, verbose=True, build_tri_map=False)
 if rank == 0:
     print(f"domain build {time.time()-t0:.1f}s cells {dom.total_cells/1e6:.1f}M updates/coarse step {dom.cell_updates_per_coarse_step/1e6:.0f}M", flush=True)
 ctx = cabi.Context(device=lr)
@@ -75,4 +86,8 @@ if rank == 0:
           f"ref_MLUPS={dom.total_cells*steps/sec/1e6:.0f} Cd={aero['Cd']:.6e} Cl={aero['Cl']:.6e} rho_min={stats['rho_min']:.6f} rho_max={stats['rho_max']:.6f}", flush=True)
 if world > 1: dist.barrier()
 ctx.close()
-if world > 1: dist.destroy_process_group()
+if world > 1:
+    dist.destroy_process_group()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(cache, ignore_errors=True)
