@@ -267,6 +267,10 @@ class Context:
         self._barrier_thunk = BARRIER_CB(lambda _user: fn())
         self._check(self.lib.ludwig_set_barrier_callback(self._h, self._barrier_thunk, None), "ludwig_set_barrier_callback")
 
+    def clear_barrier(self):
+        """Back to the library's own peer-flag barrier."""
+        self._check(self.lib.ludwig_set_barrier_callback(self._h, C.cast(None, BARRIER_CB), None), "ludwig_set_barrier_callback")
+
     def local_blocks(self, level: int) -> np.ndarray:
         """0-based reference indices of the blocks this rank owns, in the library's internal order."""
         n = C.c_int32()

@@ -7,6 +7,7 @@
 //     density is double-buffered on levels that have children (248 B/cell-update less traffic on parents);
 //   * no dense f_post_collision (K2 is two-phase, see k_misc.cu).
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,7 +63,8 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain,
+    void* ptrs[] = {L->d_hx, L->d_fmirror, L->d_vmirror, L->d_moff_f[0], L->d_moff_f[1], L->d_moff_v[0], L->d_moff_v[1], (void*)L->d_rsrc_f[0], (void*)L->d_rsrc_f[1],
+                    (void*)L->d_rsrc_v[0], (void*)L->d_rsrc_v[1], L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
@@ -220,6 +222,12 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         else if (all) le.push_back(b);
         else lf.push_back(b);
     }
+    // plain blocks without a remote neighbour first: they can run while the halo import is still in flight
+    auto has_remote = [&](int32_t b) {
+        for (int d = 0; d < 27; ++d) if (nbrf[(size_t)b * 27 + d] >= REMOTE_BASE) return true;
+        return false;
+    };
+    L.n_plain_int = (int)(std::stable_partition(lp.begin(), lp.end(), [&](int32_t b) { return !has_remote(b); }) - lp.begin());
     L.n_ghost = ng; L.n_gcell = (int)gcell.size();
     L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_feat = (int)le.size(); L.n_full = (int)lf.size();
     CU(dalloc(ctx, &L.d_nbr_fast, nbrf.size()));
@@ -302,6 +310,22 @@ int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
             if (q > q_min && q <= 1.0f) { lc.push_back(L.h_bc_cell[i]); lk.push_back((uint8_t)k); lq.push_back(q); }
         }
     L.n_links = (int)lc.size();
+    {
+        // Order the links by (block, direction, cell): the populations are stored direction-major inside a block, so
+        // consecutive threads then touch the same 2 KiB direction plane and x-adjacent boundary cells share 32-byte sectors
+        // (the per-cell order of the reference, 27 directions of one cell = 27 different sectors, is the worst case).
+        // K2 has no write conflicts and the two-phase kernel no read-after-write either: any order gives the same bits.
+        std::vector<int32_t> idx(lc.size());
+        std::iota(idx.begin(), idx.end(), 0);
+        __gnu_parallel::sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) {
+            const int64_t kx = ((int64_t)(lc[x] >> 9) << 14) | ((int64_t)lk[x] << 9) | (lc[x] & 511);
+            const int64_t ky = ((int64_t)(lc[y] >> 9) << 14) | ((int64_t)lk[y] << 9) | (lc[y] & 511);
+            return kx < ky;
+        });
+        std::vector<int32_t> lc2(lc.size()); std::vector<uint8_t> lk2(lk.size()); std::vector<float> lq2(lq.size());
+        for (size_t i = 0; i < idx.size(); ++i) { lc2[i] = lc[idx[i]]; lk2[i] = lk[idx[i]]; lq2[i] = lq[idx[i]]; }
+        lc.swap(lc2); lk.swap(lk2); lq.swap(lq2);
+    }
     if (L.n_links > 0) {
         CU(dalloc(ctx, &L.d_link_cell, lc.size())); CU(dalloc(ctx, &L.d_link_k, lk.size())); CU(dalloc(ctx, &L.d_link_q, lq.size()));
         CU(dalloc(ctx, &L.d_link_tmp, lq.size()));
@@ -404,21 +428,37 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             }
             ctx->launches += 1;
         }
+        // Multi-GPU halo import: refresh the local mirrors of the remote layers K1 pulls from, on its own stream, while the
+        // plain blocks without a remote neighbour (the first n_plain_int of the list) are processed.
+        const bool mirror = ctx->world > 1 && ctx->use_mirror && L.n_hx > 0;
+        bool wait_halo = false;
+        if (mirror) {
+            a.roff_f = L.d_moff_f[in]; a.roff_v = L.d_moff_v[in];
+            if (ctx->halo_stream && L.n_plain_int > 0) {
+                CU(cudaEventRecord(ctx->ev_halo_fork, ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_halo_fork, 0));
+                launch_halo_import(L, in, ctx->halo_stream);
+                CU(cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
+                wait_halo = true;
+            } else launch_halo_import(L, in, ctx->stream);
+            ctx->launches += 1;
+        }
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
         // levels, where each of them is a few waves of latency-bound CTAs, they run concurrently on side streams.
         const bool fork = ctx->side[0] != nullptr && L.nb <= ctx->fork_max_blocks;
         int used = 0;
         if (fork) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream) -> int {
+        auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream, bool ghosts) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
             if (!fork || main_stream) {
-                if (overlap_pre && list != L.d_list_plain) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
+                if (overlap_pre && ghosts) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
                 fn(a, ctx->stream);
             } else {
                 cudaStream_t st = ctx->side[used];
                 CU(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
                 if (overlap_pre) CU(cudaStreamWaitEvent(st, ctx->ev_pre, 0));
+                if (wait_halo) CU(cudaStreamWaitEvent(st, ctx->ev_halo, 0));
                 fn(a, st);
                 CU(cudaEventRecord(ctx->ev_join[used], st));
                 ++used;
@@ -427,18 +467,22 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             return LUDWIG_OK;
         };
         if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
-        if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true))) return rc;
+        if (wait_halo) {
+            if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain_int, true, false))) return rc;
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+            if ((rc = launch_on(launch_k1_plain, L.d_list_plain + L.n_plain_int, L.n_plain - L.n_plain_int, true, false))) return rc;
+        } else if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
         if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
         // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
         const bool pc = ctx->profiling && !fork;
         if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
-        if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0))) return rc;
+        if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_plain_g > 0, 0))) return rc;
         if ((rc = prof_begin(ctx, 2, pc && L.n_feat > 0))) return rc;
-        if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0))) return rc;
+        if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
         if ((rc = prof_begin(ctx, 3, pc && L.n_full > 0))) return rc;
-        if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0))) return rc;
+        if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         if (overlap_pre) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));   // nothing on the main stream consumed it yet
@@ -511,6 +555,31 @@ int finish_attach(ludwig_ctx* ctx) {
             CU(memcpy_sync(ctx->stream, L.d_roff_f[par], of.data(), of.size() * 8, cudaMemcpyHostToDevice));
             CU(memcpy_sync(ctx->stream, L.d_roff_v[par], ov.data(), ov.size() * 8, cudaMemcpyHostToDevice));
         }
+        if (!ctx->use_mirror) continue;
+        // halo mirrors: K1 addresses a local copy of the remote layers (halo_import_kernel refreshes it every level step)
+        CU(dalloc(ctx, &L.d_fmirror, (size_t)L.n_remote * Q * BS3)); CU(dalloc(ctx, &L.d_vmirror, (size_t)L.n_remote * 3 * BS3));
+        CU(cudaMemsetAsync(L.d_fmirror, 0, (size_t)L.n_remote * Q * BS3 * 4, ctx->stream));
+        CU(cudaMemsetAsync(L.d_vmirror, 0, (size_t)L.n_remote * 3 * BS3 * 4, ctx->stream));
+        L.n_hx = (int)L.h_hx.size();
+        CU(dalloc(ctx, &L.d_hx, L.h_hx.size()));
+        CU(memcpy_sync(ctx->stream, L.d_hx, L.h_hx.data(), L.h_hx.size() * 4, cudaMemcpyHostToDevice));
+        for (int par = 0; par < 2; ++par) {
+            std::vector<long long> mf(L.n_remote), mv(L.n_remote);
+            std::vector<const float*> sf(L.n_remote), sv(L.n_remote);
+            for (int i = 0; i < L.n_remote; ++i) {
+                const int ow = L.remote_owner[i];
+                mf[i] = (long long)((L.d_fmirror + (size_t)i * Q * BS3) - L.d_f[par]);
+                mv[i] = (long long)((L.d_vmirror + (size_t)i * 3 * BS3) - L.d_vel[par]);
+                sf[i] = L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3;
+                sv[i] = L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3;
+            }
+            CU(dalloc(ctx, &L.d_moff_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_moff_v[par], (size_t)L.n_remote));
+            CU(dalloc(ctx, &L.d_rsrc_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_rsrc_v[par], (size_t)L.n_remote));
+            CU(memcpy_sync(ctx->stream, L.d_moff_f[par], mf.data(), mf.size() * 8, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_moff_v[par], mv.data(), mv.size() * 8, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_rsrc_f[par], sf.data(), sf.size() * 8, cudaMemcpyHostToDevice));
+            CU(memcpy_sync(ctx->stream, L.d_rsrc_v[par], sv.data(), sv.size() * 8, cudaMemcpyHostToDevice));
+        }
     }
     ctx->peers_attached = true;
     return LUDWIG_OK;
@@ -544,9 +613,14 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
              cudaEventCreateWithFlags(&ctx->ev_pre_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
+        ok = cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_halo_fork, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { delete ctx; return LUDWIG_ECUDA; }
         if (getenv("LUDWIG_SERIAL_PREPASS")) { cudaStreamDestroy(ctx->pre_stream); ctx->pre_stream = nullptr; }
         if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
+    ctx->use_mirror = getenv("LUDWIG_NO_MIRROR") == nullptr;
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -722,6 +796,7 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
                         L.remote_owner.push_back(ow); L.remote_local.push_back(gj - L.part_starts[ow]);
                     } else id = it->second;
                     e = REMOTE_BASE + id;
+                    L.h_hx.push_back((id << 5) | dir);
                 }
             }
             nbr[(size_t)bi * 27 + dir] = e;
@@ -732,6 +807,8 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
         bcoord[(size_t)bi * 4 + 3] = 0;
     }
     L.n_remote = (int)remote_id.size();
+    std::sort(L.h_hx.begin(), L.h_hx.end());
+    L.h_hx.erase(std::unique(L.h_hx.begin(), L.h_hx.end()), L.h_hx.end());
     // block pointer of the WHOLE level, rank-encoded: (owner << 24) | owner-local index
     size_t nptr = (size_t)d->dim_x * d->dim_y * d->dim_z;
     std::vector<int32_t> ptr(nptr);

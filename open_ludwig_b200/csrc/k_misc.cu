@@ -177,6 +177,52 @@ void launch_bouzidi(const Level& L, float* f_out, const long long* roff, bool st
 }
 
 // ---------------------------------------------------------------------------------------------
+// Halo import (multi-GPU): copies, over NVLink, exactly the layer of a peer-owned neighbour block that this rank's K1 will
+// pull from — for the neighbour at offset d = (dx,dy,dz): the cells on its side facing the local block (x = 0 if dx = +1,
+// x = 7 if dx = -1, all 8 if dx = 0; same for y, z) and the populations that can cross that side (c_a = -d_a on every
+// axis with d_a != 0: 9 for a face, 3 for an edge, 1 for a corner), plus the three velocity components of a face layer
+// (WALE reads axis neighbours only) — into a LOCAL mirror of that block at the same in-block positions.  K1 then reads
+// local memory only; the import runs on a side stream concurrently with the K1 launch over the blocks that have no
+// remote neighbour, so NVLink latency is off the critical path.  One warp per (remote block, direction) entry.
+__global__ void __launch_bounds__(256) halo_import_kernel(const int32_t* __restrict__ hx, int n_hx, const float* const* __restrict__ src_f,
+                                                          const float* const* __restrict__ src_v, float* __restrict__ fmirror,
+                                                          float* __restrict__ vmirror) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n_hx) return;
+    const int lane = threadIdx.x & 31;
+    const int ent = hx[e];
+    const int rid = ent >> 5, dir = ent & 31;
+    const int dx = dir % 3 - 1, dy = (dir / 3) % 3 - 1, dz = dir / 9 - 1;
+    const int nx = dx ? 1 : 8, ny = dy ? 1 : 8, nz = dz ? 1 : 8;
+    const int x0 = dx > 0 ? 0 : (dx < 0 ? 7 : 0), y0 = dy > 0 ? 0 : (dy < 0 ? 7 : 0), z0 = dz > 0 ? 0 : (dz < 0 ? 7 : 0);
+    const int ncell = nx * ny * nz;
+    const int px = dx ? 1 : 3, py = dy ? 1 : 3, pz = dz ? 1 : 3;   // free lattice components per axis
+    const int npop = px * py * pz;
+    const float* __restrict__ sf = src_f[rid];
+    float* __restrict__ df = fmirror + (size_t)rid * (Q * BS3);
+    for (int i = lane; i < npop * ncell; i += 32) {
+        const int j = i / ncell, c = i - j * ncell;
+        const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
+        const int cx = dx ? -dx : j % px - 1, cy = dy ? -dy : (j / px) % py - 1, cz = dz ? -dz : j / (px * py) - 1;
+        const int off = ((cx + 1) + 3 * (cy + 1) + 9 * (cz + 1)) * BS3 + z * 64 + y * 8 + x;
+        df[off] = sf[off];
+    }
+    if (dx * dx + dy * dy + dz * dz == 1) {
+        const float* __restrict__ sv = src_v[rid];
+        float* __restrict__ dv = vmirror + (size_t)rid * (3 * BS3);
+        for (int i = lane; i < 3 * ncell; i += 32) {
+            const int j = i / ncell, c = i - j * ncell;
+            const int off = j * BS3 + (z0 + c / (nx * ny)) * 64 + (y0 + (c / nx) % ny) * 8 + x0 + c % nx;
+            dv[off] = sv[off];
+        }
+    }
+}
+void launch_halo_import(const Level& L, int parity, cudaStream_t s) {
+    if (L.n_hx <= 0) return;
+    halo_import_kernel<<<(L.n_hx + 7) / 8, 256, 0, s>>>(L.d_hx, L.n_hx, L.d_rsrc_f[parity], L.d_rsrc_v[parity], L.d_fmirror, L.d_vmirror);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cross-GPU barrier (multi-GPU, one process per GPU): every rank owns MAX_RANKS epoch slots in device memory that its
 // peers have mapped through CUDA IPC.  Lane r writes this rank's epoch into peer r's slot [my rank] (a store over
 // NVLink), then spins on the local slot [r] until peer r has done the same.  Stream-ordered, no host round trip, ~5 us.

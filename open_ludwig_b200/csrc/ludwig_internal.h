@@ -77,6 +77,17 @@ struct Level {
     int n_remote = 0;
     long long* d_roff_f[2] = {nullptr, nullptr};   // per parity (index = parity of the INPUT buffer)
     long long* d_roff_v[2] = {nullptr, nullptr};
+    // halo mirrors (built by the attach unless LUDWIG_NO_MIRROR): local copies of the layers K1 pulls from remote blocks,
+    // refreshed by halo_import_kernel before every level step; K1 then addresses the mirror instead of the peer mapping
+    std::vector<int32_t> h_hx;             // (remote id << 5) | direction of the remote block seen from a local block
+    int32_t* d_hx = nullptr; int n_hx = 0;
+    float* d_fmirror = nullptr;            // [n_remote][27][512]
+    float* d_vmirror = nullptr;            // [n_remote][3][512]
+    long long* d_moff_f[2] = {nullptr, nullptr};   // mirror block - local f_in (per input parity), K1's remote offsets
+    long long* d_moff_v[2] = {nullptr, nullptr};
+    const float** d_rsrc_f[2] = {nullptr, nullptr};   // [n_remote] peer block base pointers per parity (import sources)
+    const float** d_rsrc_v[2] = {nullptr, nullptr};
+    int n_plain_int = 0;                   // the first n_plain_int entries of d_list_plain have no remote neighbour
     // peer base pointers (index = rank); own pointers for this rank
     const float* peer_f[2][MAX_RANKS] = {};
     const float* peer_vel[2][MAX_RANKS] = {};
@@ -167,6 +178,9 @@ struct ludwig_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cudaStream_t pre_stream = nullptr;       // interface pre-pass, concurrent with the plain K1 launch
     cudaEvent_t ev_pre_fork = nullptr, ev_pre = nullptr;
+    cudaStream_t halo_stream = nullptr;      // halo import (multi-GPU), concurrent with the K1 launch over interior blocks
+    cudaEvent_t ev_halo = nullptr, ev_halo_fork = nullptr;
+    bool use_mirror = true;
     int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
     std::vector<ludwig::Level*> levels;
     std::string err;
@@ -256,6 +270,7 @@ void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2re
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_block_flags(Level& L, cudaStream_t s);
+void launch_halo_import(const Level& L, int parity, cudaStream_t s);
 void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s);
 void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
                          ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,

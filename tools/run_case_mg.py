@@ -57,31 +57,52 @@ ctx.sync()
 if rank == 0:
     print(f"upload {time.time()-t0:.1f}s device GB (rank 0) {ctx.device_bytes()/1e9:.1f}", flush=True)
 stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 u = ramp_velocity(dom.cfg.u_target, 8, dom.cfg.ramp_steps)
 ctx.step_batch(1, 2, u, params); ctx.sync()            # warm-up (builds the fast-mode tables)
-if world > 1: dist.barrier()
-prof = os.environ.get("LUDWIG_PROFILE") is not None      # with LUDWIG_SINGLE_STREAM=1: per-class device time of every rank
-if prof:
+
+
+def timed(n):
+    """max over ranks of the device time of n coarse steps (CUDA events on the library's stream)"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1: dist.barrier()
+    e0.record(stream)
+    ctx.step_batch(3, n, u, params)
+    e1.record(stream)
+    ctx.sync()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+ms = timed(steps)
+if world > 1 and os.environ.get("LUDWIG_AB"):
+    # A/B on the same processes: the round-1 barrier (stream-ordered NCCL all-reduce through the callback) against the
+    # library's own peer-flag barrier kernel
+    bstream, flag = stream, torch.zeros(1, device=dev)
+    def nccl_barrier():
+        with torch.cuda.stream(bstream):
+            dist.all_reduce(flag)
+    ctx.set_barrier(nccl_barrier)
+    ctx.step_batch(1, 1, u, params); ctx.sync()
+    ms_nccl = timed(steps)
+    ctx.clear_barrier()
+    if rank == 0:
+        print(f"AB barrier: native {ms/steps:.2f} ms/step, nccl callback {ms_nccl/steps:.2f} ms/step", flush=True)
+if os.environ.get("LUDWIG_PROFILE") is not None:   # per-level / per-class device time of every rank
     ctx.profile_enable(True)
-e0.record(stream)
-ctx.step_batch(3, steps, u, params)
-e1.record(stream)
-ctx.sync()
-if prof:
-    ctx.profile_read(); cls = ctx.profile_classes()
+    ctx.step_batch(3, steps, u, params); ctx.sync()
+    ctx.profile_read(); lv = ctx.profile_levels()
+    ctx.profile_enable(False)
     loc = [len(ctx.local_blocks(i)) for i in range(len(dom.levels))]
-    print(f"rank {rank}: local blocks/level {loc} total {e0.elapsed_time(e1):.1f} ms busy {sum(cls.values()):.1f} ms " +
-          " ".join(f"{k}={v:.1f}" for k, v in cls.items()), flush=True)
+    print(f"rank {rank}: blocks {loc} per level [ms/coarse step]: " + " | ".join(
+        f"L{i+1} {d['level_step']/steps:.2f} (k1p {d['k1_plain']/steps:.2f} bz {d['bouzidi']/steps:.2f} bar {d['barrier']/steps:.2f})" for i, d in enumerate(lv)), flush=True)
 if world > 1: dist.barrier()
-ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 aero = ctx.compute_aerodynamics(forces, len(dom.levels) - 1, p.mesh_offset, p.velocity_scale, p.rho_physical, 5)
 stats = ctx.flow_stats(0)
 if world > 1:
     aero = mg.reduce_aero(aero, dev); stats = mg.reduce_stats(stats, dev)
 if rank == 0:
-    sec = float(ms[0]) * 1e-3
+    sec = ms * 1e-3
     print(f"RESULT case={name} n_gpus={world} steps={steps} s/step={sec/steps:.4f} true_MLUPS={dom.cell_updates_per_coarse_step*steps/sec/1e6:.0f} "
           f"ref_MLUPS={dom.total_cells*steps/sec/1e6:.0f} Cd={aero['Cd']:.6e} Cl={aero['Cl']:.6e} rho_min={stats['rho_min']:.6f} rho_max={stats['rho_max']:.6f}", flush=True)
 if world > 1: dist.barrier()
