@@ -234,9 +234,10 @@ int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on);
 int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, int64_t* cells);
 /* Device time [ms] per launch class accumulated by the last ludwig_profile_read: 0 K1 plain, 1 K1 plain+ghost,
  * 2 K1 feature, 3 K1 full, 4 interface pre-pass, 5 Bouzidi, 6 cross-rank barriers, 7 whole level steps (classes 1-3 only when
- * launched on the main stream).  ludwig_profile_levels: the same split per level, out[level * 8 + class]. */
+ * launched on the main stream).  ludwig_profile_levels: per level, out[level * 12 + class], with two more
+ * classes: 8 halo unpack (multi-GPU import of the peers' layers), 9 halo pack. */
 int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]);
-int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity /* >= 8 * levels */);
+int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity /* >= 12 * levels */);
 
 #ifdef __cplusplus
 }

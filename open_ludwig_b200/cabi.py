@@ -253,9 +253,10 @@ class Context:
     def profile_levels(self) -> list:
         """Device ms per (level, launch class) of the last profile_read(): one dict per level."""
         n = int(self.lib.ludwig_num_levels(self._h))
-        out = (C.c_double * (8 * n))()
-        self._check(self.lib.ludwig_profile_levels(self._h, out, 8 * n), "ludwig_profile_levels")
-        return [{k: out[8 * l + i] for i, k in enumerate(self.PROFILE_CLASSES) if k != "-"} for l in range(n)]
+        names = self.PROFILE_CLASSES + ("halo_unpack", "halo_pack", "-", "-")
+        out = (C.c_double * (12 * n))()
+        self._check(self.lib.ludwig_profile_levels(self._h, out, 12 * n), "ludwig_profile_levels")
+        return [{k: out[12 * l + i] for i, k in enumerate(names) if k != "-"} for l in range(n)]
 
     # -- multi-GPU (one process per GPU) ----------------------------------------------------
     def set_partition(self, rank: int, world: int):

@@ -63,8 +63,7 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_hx, L->d_fmirror, L->d_vmirror, L->d_moff_f[0], L->d_moff_f[1], L->d_moff_v[0], L->d_moff_v[1], (void*)L->d_rsrc_f[0], (void*)L->d_rsrc_f[1],
-                    (void*)L->d_rsrc_v[0], (void*)L->d_rsrc_v[1], L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain,
+    void* ptrs[] = {L->d_pack, L->d_unpack, L->d_export, L->d_fmirror, L->d_vmirror, L->d_moff_f[0], L->d_moff_f[1], L->d_moff_v[0], L->d_moff_v[1], L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_gstart, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
@@ -154,10 +153,10 @@ ParentView make_parent_view(const Level& P, int64_t parent_t_sub, bool explicit_
 int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
     CU(cudaStreamSynchronize(ctx->stream));
-    for (void* q : {(void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_gcells8, (void*)L.d_list_plain,
+    for (void* q : {(void*)L.d_gstart, (void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_gcells8, (void*)L.d_list_plain,
                     (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full, (void*)L.d_list_nonplain})
         if (q) cudaFree(q);
-    L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr; L.d_gcells8 = nullptr;
+    L.d_gstart = nullptr; L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr; L.d_gcells8 = nullptr;
     L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = L.d_list_nonplain = nullptr;
     const int nb = L.nb;
     const int scale = 1 << (L.level_id - 1);
@@ -184,6 +183,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     std::vector<int32_t> gcell;
     std::vector<uint32_t> gmask;
     std::vector<uint8_t> gcells8;
+    std::vector<int32_t> gstart(1, 0);
     auto real_at = [&](int x, int y, int z) {
         if (x < 0 || x >= L.dimx || y < 0 || y >= L.dimy || z < 0 || z >= L.dimz) return false;
         return L.h_ptr[x + (size_t)L.dimx * (y + (size_t)L.dimy * z)] >= 0;
@@ -208,6 +208,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
             }
             if (cm) { gcell.push_back(g * 64 + q); gmask.push_back(km); gcells8.push_back(cm); }
         }
+        gstart.push_back((int32_t)gcell.size());
     }
     // K1 work lists
     std::vector<int32_t> lp, lg, le, lf;
@@ -236,6 +237,8 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         CU(dalloc(ctx, &L.d_gcoord, gcoord.size())); CU(dalloc(ctx, &L.d_fghost, (size_t)ng * Q * BS3));
         CU(dalloc(ctx, &L.d_gcell, gcell.size())); CU(dalloc(ctx, &L.d_gmask, gmask.size())); CU(dalloc(ctx, &L.d_gcells8, gcells8.size()));
         CU(memcpy_sync(ctx->stream, L.d_gcoord, gcoord.data(), gcoord.size() * 4, cudaMemcpyHostToDevice));
+        CU(dalloc(ctx, &L.d_gstart, gstart.size()));
+        CU(memcpy_sync(ctx->stream, L.d_gstart, gstart.data(), gstart.size() * 4, cudaMemcpyHostToDevice));
         CU(cudaMemsetAsync(L.d_fghost, 0, (size_t)ng * Q * BS3 * 4, ctx->stream));
         if (!gcell.empty()) {
             CU(memcpy_sync(ctx->stream, L.d_gcell, gcell.data(), gcell.size() * 4, cudaMemcpyHostToDevice));
@@ -263,7 +266,8 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
 // Profiling brackets (ludwig_profile_enable): CUDA events on the main stream around one launch, tagged with a class:
 // 0 K1 plain, 1 K1 plain+ghost, 2 K1 feature, 3 K1 full (missing neighbours), 4 interface pre-pass, 5 Bouzidi, 6 barrier,
 // 7 whole level step.
-int prof_begin(ludwig_ctx* ctx, int cls, bool active) {
+constexpr int NCLS = 12;   // 8 halo unpack (on the halo stream), 9 halo pack
+int prof_begin(ludwig_ctx* ctx, int cls, bool active, cudaStream_t st = nullptr) {
     if (!ctx->profiling || !active) return LUDWIG_OK;
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
         cudaEvent_t e0, e1;
@@ -271,13 +275,13 @@ int prof_begin(ludwig_ctx* ctx, int cls, bool active) {
         ctx->ev_pool.push_back(e0); ctx->ev_pool.push_back(e1);
     }
     if (ctx->ev_class.size() < ctx->ev_pool.size() / 2) ctx->ev_class.resize(ctx->ev_pool.size() / 2);
-    ctx->ev_class[ctx->ev_used / 2] = cls | (ctx->prof_level << 3);
-    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    ctx->ev_class[ctx->ev_used / 2] = cls | (ctx->prof_level << 4);
+    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used], st ? st : ctx->stream));
     return LUDWIG_OK;
 }
-int prof_end(ludwig_ctx* ctx, bool active, int64_t cells) {
+int prof_end(ludwig_ctx* ctx, bool active, int64_t cells, cudaStream_t st = nullptr) {
     if (!ctx->profiling || !active) return LUDWIG_OK;
-    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st ? st : ctx->stream));
     ctx->ev_used += 2;
     ctx->prof_cells += cells;
     return LUDWIG_OK;
@@ -404,6 +408,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if (L.n_gcell > 0 && pv) {   // interface halo pre-pass: fills the ghost blocks K1 is about to pull from
             GhostArgs g{};
             g.gcell = L.d_gcell; g.gmask = L.d_gmask; g.gcells8 = L.d_gcells8; g.n = L.n_gcell; g.gcoord = L.d_gcoord; g.f_ghost = L.d_fghost;
+            g.gstart = L.d_gstart; g.n_ghost = L.n_ghost;
             const Level& P = *pv->P;
             g.pf_new = peers_of(P.peer_f[pv->out]); g.pvel_new = peers_of(P.peer_vel[pv->out]); g.prho_new = peers_of(P.peer_rho[pv->rho_new_i]);
             g.pf_old = peers_of(P.peer_f[pv->in]); g.pvel_old = peers_of(P.peer_vel[pv->in]); g.prho_old = peers_of(P.peer_rho[pv->rho_old_i]);
@@ -419,7 +424,9 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             if (overlap_pre) {
                 CU(cudaEventRecord(ctx->ev_pre_fork, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->pre_stream, ctx->ev_pre_fork, 0));
+                if ((rc = prof_begin(ctx, 4, true, ctx->pre_stream))) return rc;
                 launch_ghost_interp(g, ctx->pre_stream);
+                if ((rc = prof_end(ctx, true, 0, ctx->pre_stream))) return rc;
                 CU(cudaEventRecord(ctx->ev_pre, ctx->pre_stream));
             } else {
                 if ((rc = prof_begin(ctx, 4, true))) return rc;
@@ -430,17 +437,23 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         }
         // Multi-GPU halo import: refresh the local mirrors of the remote layers K1 pulls from, on its own stream, while the
         // plain blocks without a remote neighbour (the first n_plain_int of the list) are processed.
-        const bool mirror = ctx->world > 1 && ctx->use_mirror && L.n_hx > 0;
+        const bool mirror = ctx->world > 1 && ctx->use_mirror && L.n_unpack > 0;
         bool wait_halo = false;
         if (mirror) {
             a.roff_f = L.d_moff_f[in]; a.roff_v = L.d_moff_v[in];
             if (ctx->halo_stream && L.n_plain_int > 0) {
                 CU(cudaEventRecord(ctx->ev_halo_fork, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_halo_fork, 0));
-                launch_halo_import(L, in, ctx->halo_stream);
+                if ((rc = prof_begin(ctx, 8, true, ctx->halo_stream))) return rc;
+                launch_halo_unpack(L, in, ctx->halo_stream);
+                if ((rc = prof_end(ctx, true, 0, ctx->halo_stream))) return rc;
                 CU(cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
                 wait_halo = true;
-            } else launch_halo_import(L, in, ctx->stream);
+            } else {
+                if ((rc = prof_begin(ctx, 8, true))) return rc;
+                launch_halo_unpack(L, in, ctx->stream);
+                if ((rc = prof_end(ctx, true, 0))) return rc;
+            }
             ctx->launches += 1;
         }
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
@@ -504,6 +517,13 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
         if (L.n_links > 0) ctx->launches += 2;
     }
+    if (mg && ctx->use_mirror && L.n_pack > 0) {   // the layers the peers pull at the start of the next step of this level
+        int rcq;
+        if ((rcq = prof_begin(ctx, 9, true))) return rcq;
+        launch_halo_pack(L, out, ctx->stream);
+        if ((rcq = prof_end(ctx, true, 0))) return rcq;
+        ctx->launches += 1;
+    }
     if (mg) rank_barrier(ctx);   // every rank finished this level step
     if (p7 != (size_t)-1) CU(cudaEventRecord(ctx->ev_pool[p7 + 1], ctx->stream));
     L.rho_cur = rho_out;
@@ -556,31 +576,22 @@ int finish_attach(ludwig_ctx* ctx) {
             CU(memcpy_sync(ctx->stream, L.d_roff_v[par], ov.data(), ov.size() * 8, cudaMemcpyHostToDevice));
         }
         if (!ctx->use_mirror) continue;
-        // halo mirrors: K1 addresses a local copy of the remote layers (halo_import_kernel refreshes it every level step)
+        // halo mirrors: K1 addresses a local copy of the remote layers (halo_unpack_kernel refreshes it every level step)
         CU(dalloc(ctx, &L.d_fmirror, (size_t)L.n_remote * Q * BS3)); CU(dalloc(ctx, &L.d_vmirror, (size_t)L.n_remote * 3 * BS3));
         CU(cudaMemsetAsync(L.d_fmirror, 0, (size_t)L.n_remote * Q * BS3 * 4, ctx->stream));
         CU(cudaMemsetAsync(L.d_vmirror, 0, (size_t)L.n_remote * 3 * BS3 * 4, ctx->stream));
-        L.n_hx = (int)L.h_hx.size();
-        CU(dalloc(ctx, &L.d_hx, L.h_hx.size()));
-        CU(memcpy_sync(ctx->stream, L.d_hx, L.h_hx.data(), L.h_hx.size() * 4, cudaMemcpyHostToDevice));
         for (int par = 0; par < 2; ++par) {
             std::vector<long long> mf(L.n_remote), mv(L.n_remote);
-            std::vector<const float*> sf(L.n_remote), sv(L.n_remote);
             for (int i = 0; i < L.n_remote; ++i) {
-                const int ow = L.remote_owner[i];
                 mf[i] = (long long)((L.d_fmirror + (size_t)i * Q * BS3) - L.d_f[par]);
                 mv[i] = (long long)((L.d_vmirror + (size_t)i * 3 * BS3) - L.d_vel[par]);
-                sf[i] = L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3;
-                sv[i] = L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3;
             }
             CU(dalloc(ctx, &L.d_moff_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_moff_v[par], (size_t)L.n_remote));
-            CU(dalloc(ctx, &L.d_rsrc_f[par], (size_t)L.n_remote)); CU(dalloc(ctx, &L.d_rsrc_v[par], (size_t)L.n_remote));
             CU(memcpy_sync(ctx->stream, L.d_moff_f[par], mf.data(), mf.size() * 8, cudaMemcpyHostToDevice));
             CU(memcpy_sync(ctx->stream, L.d_moff_v[par], mv.data(), mv.size() * 8, cudaMemcpyHostToDevice));
-            CU(memcpy_sync(ctx->stream, L.d_rsrc_f[par], sf.data(), sf.size() * 8, cudaMemcpyHostToDevice));
-            CU(memcpy_sync(ctx->stream, L.d_rsrc_v[par], sv.data(), sv.size() * 8, cudaMemcpyHostToDevice));
         }
     }
+    CU(cudaStreamSynchronize(ctx->stream));
     ctx->peers_attached = true;
     return LUDWIG_OK;
 }
@@ -613,14 +624,20 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
              cudaEventCreateWithFlags(&ctx->ev_pre_fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
-        ok = cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking) == cudaSuccess &&
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the halo import must not queue behind the interior K1 CTAs
+        ok = cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_halo_fork, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
         if (getenv("LUDWIG_SERIAL_PREPASS")) { cudaStreamDestroy(ctx->pre_stream); ctx->pre_stream = nullptr; }
         if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
-    ctx->use_mirror = getenv("LUDWIG_NO_MIRROR") == nullptr;
+    // Multi-GPU halo strategy.  Default: K1 pulls remote layers straight over NVLink inside the stream-collide kernel.
+    // LUDWIG_HALO_MIRROR=1: packed exchange into local mirrors (pack / unpack kernels, k_misc.cu) — measured SLOWER on
+    // 2 and 8 B200 (profiles/README.md, "halo strategies"): the extra kernels sit on the critical path of every level
+    // step while the in-kernel pulls hide behind the other CTAs of an HBM-bound kernel.
+    ctx->use_mirror = getenv("LUDWIG_HALO_MIRROR") != nullptr;
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -664,13 +681,13 @@ int ludwig_profile_read(ludwig_ctx* ctx, double* ms_total, int64_t* launches, in
     double tot = 0;
     int64_t n0 = 0;
     for (int c = 0; c < 8; ++c) ctx->prof_class_ms[c] = 0;
-    ctx->prof_level_ms.assign(ctx->levels.size() * 8, 0.0);
+    ctx->prof_level_ms.assign(ctx->levels.size() * NCLS, 0.0);
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
-        const int c = ctx->ev_class[i / 2] & 7, lv = ctx->ev_class[i / 2] >> 3;
-        ctx->prof_class_ms[c] += ms;
-        if ((size_t)lv < ctx->levels.size()) ctx->prof_level_ms[(size_t)lv * 8 + c] += ms;
+        const int c = ctx->ev_class[i / 2] & 15, lv = ctx->ev_class[i / 2] >> 4;
+        if (c < 8) ctx->prof_class_ms[c] += ms;
+        if ((size_t)lv < ctx->levels.size() && c < NCLS) ctx->prof_level_ms[(size_t)lv * NCLS + c] += ms;
         if (c == 0) { tot += ms; ++n0; }
     }
     if (ms_total) *ms_total = tot;            // class 0 only: the dominant plain K1 kernel
@@ -687,7 +704,7 @@ int ludwig_profile_classes(ludwig_ctx* ctx, double out[8]) {
 }
 
 int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity) {
-    if (!ctx || !out || capacity < (int32_t)ctx->prof_level_ms.size()) return fail(ctx, LUDWIG_EINVAL, "profile_levels: need 8 doubles per level");
+    if (!ctx || !out || capacity < (int32_t)ctx->prof_level_ms.size()) return fail(ctx, LUDWIG_EINVAL, "profile_levels: need 12 doubles per level");
     for (size_t i = 0; i < ctx->prof_level_ms.size(); ++i) out[i] = ctx->prof_level_ms[i];   // [level][class], last ludwig_profile_read
     return LUDWIG_OK;
 }
@@ -796,7 +813,6 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
                         L.remote_owner.push_back(ow); L.remote_local.push_back(gj - L.part_starts[ow]);
                     } else id = it->second;
                     e = REMOTE_BASE + id;
-                    L.h_hx.push_back((id << 5) | dir);
                 }
             }
             nbr[(size_t)bi * 27 + dir] = e;
@@ -807,8 +823,73 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
         bcoord[(size_t)bi * 4 + 3] = 0;
     }
     L.n_remote = (int)remote_id.size();
-    std::sort(L.h_hx.begin(), L.h_hx.end());
-    L.h_hx.erase(std::unique(L.h_hx.begin(), L.h_hx.end()), L.h_hx.end());
+    // --- packed halo exchange plan.  S(i,e) = the (block R owned by e, direction d) pairs for which some block of rank i has
+    // R as its neighbour in direction d, sorted by (R, d).  Every rank derives ALL the sets from the global tables, so the
+    // exporter's pack order and the importer's unpack order agree without any communication.  Rank e's export buffer is the
+    // concatenation of S(0,e), S(1,e), ... ; an entry takes 768 / 24 / 1 floats (face / edge / corner layer).
+    if (ctx->world > 1 && ctx->use_mirror) {
+        const int W = ctx->world;
+        std::vector<uint8_t> own(nbg);
+        for (int r = 0; r < W; ++r) for (int gi = L.part_starts[r]; gi < L.part_starts[r + 1]; ++gi) own[gi] = (uint8_t)r;
+        std::vector<std::vector<int64_t>> S((size_t)W * W);
+        for (int gi = 0; gi < nbg; ++gi) {
+            const int i = own[gi], br = L.int2ref[gi];
+            for (int dir = 0; dir < 27; ++dir) {
+                const int32_t v = d->neighbor_table[br + (size_t)nbg * dir];
+                if (v <= 0 || v > nbg) continue;
+                const int gj = L.ref2int[v - 1], e = own[gj];
+                if (e != i) S[(size_t)i * W + e].push_back((int64_t)gj * 32 + dir);
+            }
+        }
+        auto esz = [](int dir) { const int nzc = (dir % 3 != 1) + ((dir / 3) % 3 != 1) + (dir / 9 != 1); return nzc == 1 ? 768 : nzc == 2 ? 24 : 1; };
+        std::vector<size_t> seg((size_t)W * W, 0);
+        for (size_t k = 0; k < S.size(); ++k) {
+            std::sort(S[k].begin(), S[k].end());
+            S[k].erase(std::unique(S[k].begin(), S[k].end()), S[k].end());
+            for (int64_t key : S[k]) seg[k] += (size_t)esz((int)(key & 31));
+        }
+        for (int e = 0; e < W; ++e) {
+            size_t tot = 0;
+            for (int i = 0; i < W; ++i) tot += seg[(size_t)i * W + e];
+            L.peer_export_floats[e] = tot;
+        }
+        if (L.peer_export_floats[ctx->rank] >= (1ull << 31)) return fail(ctx, LUDWIG_EINVAL, "halo export buffer exceeds 2^31 floats");
+        // what this rank exports: importer-major
+        size_t off = 0;
+        for (int i = 0; i < W; ++i)
+            for (int64_t key : S[(size_t)i * W + ctx->rank]) {
+                const int gj = (int)(key >> 5), dir = (int)(key & 31);
+                L.h_pack.push_back(make_int4(gj - L.part_start, dir, (int)off, 0));
+                off += (size_t)esz(dir);
+            }
+        L.export_floats = off;
+        // what this rank imports: its segment of every exporter's buffer
+        for (int e = 0; e < W; ++e) {
+            if (e == ctx->rank) continue;
+            size_t base = 0;
+            for (int i = 0; i < ctx->rank; ++i) base += seg[(size_t)i * W + e];
+            for (int64_t key : S[(size_t)ctx->rank * W + e]) {
+                const int gj = (int)(key >> 5), dir = (int)(key & 31);
+                auto it = remote_id.find(gj);
+                if (it == remote_id.end()) return fail(ctx, LUDWIG_EINVAL, "halo plan: remote block not in the neighbour table");
+                L.h_unpack.push_back(make_int4(it->second, dir, (int)base, e));
+                base += (size_t)esz(dir);
+            }
+        }
+        L.n_pack = (int)L.h_pack.size(); L.n_unpack = (int)L.h_unpack.size();
+        if (L.n_pack > 0) {
+            CU(dalloc(ctx, &L.d_pack, L.h_pack.size()));
+            CU(memcpy_sync(ctx->stream, L.d_pack, L.h_pack.data(), L.h_pack.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
+        if (L.n_unpack > 0) {
+            CU(dalloc(ctx, &L.d_unpack, L.h_unpack.size()));
+            CU(memcpy_sync(ctx->stream, L.d_unpack, L.h_unpack.data(), L.h_unpack.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
+        // allocated even when empty-ish so that every rank exports the same number of IPC handles
+        CU(dalloc(ctx, &L.d_export, std::max<size_t>(2 * L.export_floats, 64)));
+        CU(cudaMemsetAsync(L.d_export, 0, std::max<size_t>(2 * L.export_floats, 64) * 4, ctx->stream));
+        L.peer_export[ctx->rank] = L.d_export;
+    }
     // block pointer of the WHOLE level, rank-encoded: (owner << 24) | owner-local index
     size_t nptr = (size_t)d->dim_x * d->dim_y * d->dim_z;
     std::vector<int32_t> ptr(nptr);
@@ -1042,6 +1123,13 @@ int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, floa
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach first");
     int rcp = prepare_tables(ctx, *params);
     if (rcp) return rcp;
+    // export the halo layers of the CURRENT state (it may have been uploaded or initialised since the last batch): level l's
+    // first sub-step is t_start * 2^l and reads the buffer of that parity
+    if (ctx->world > 1 && ctx->use_mirror)
+        for (size_t l = 0; l < ctx->levels.size(); ++l) {
+            const int64_t t0 = t_start << l;
+            launch_halo_pack(*ctx->levels[l], (t0 % 2 == 0) ? 0 : 1, ctx->stream);
+        }
     // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
     rank_barrier(ctx);
     for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
@@ -1058,6 +1146,7 @@ int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t par
     Level& L = *ctx->levels[level];
     int rcp = prepare_tables(ctx, *params);
     if (rcp) return rcp;
+    if (ctx->world > 1 && ctx->use_mirror) launch_halo_pack(L, (t_sub % 2 == 0) ? 0 : 1, ctx->stream);
     rank_barrier(ctx);
     if (level == 0) return step_level(ctx, L, nullptr, t_sub, temporal_weight, u_curr, *params);
     Level& P = *ctx->levels[level - 1];
@@ -1278,11 +1367,11 @@ int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, 
     return LUDWIG_OK;
 }
 
-// 7 handles per level: f, f_temp, vel, vel_temp, rho[0], rho[1] (zeros if absent), obstacle.
+// 8 handles per level: f, f_temp, vel, vel_temp, rho[0], rho[1] (zeros if absent), obstacle, halo export buffer.
 int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_t* needed_bytes) {
     if (!ctx) return LUDWIG_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    const int64_t need = ((int64_t)ctx->levels.size() * 7 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);   // + the barrier slots
+    const int64_t need = ((int64_t)ctx->levels.size() * 8 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);   // + the barrier slots
     if (needed_bytes) *needed_bytes = need;
     if (!out) return LUDWIG_OK;
     if (capacity_bytes < need) return fail(ctx, LUDWIG_EINVAL, "ipc export buffer too small");
@@ -1291,11 +1380,11 @@ int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_
     std::memset(out, 0, (size_t)need);
     for (size_t l = 0; l < ctx->levels.size(); ++l) {
         Level& L = *ctx->levels[l];
-        void* ptrs[7] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle};
-        for (int i = 0; i < 7; ++i)
-            if (ptrs[i]) CU(cudaIpcGetMemHandle(&h[l * 7 + i], ptrs[i]));
+        void* ptrs[8] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle, L.d_export};
+        for (int i = 0; i < 8; ++i)
+            if (ptrs[i]) CU(cudaIpcGetMemHandle(&h[l * 8 + i], ptrs[i]));
     }
-    if (ctx->d_bar) CU(cudaIpcGetMemHandle(&h[ctx->levels.size() * 7], ctx->d_bar));
+    if (ctx->d_bar) CU(cudaIpcGetMemHandle(&h[ctx->levels.size() * 8], ctx->d_bar));
     return LUDWIG_OK;
 }
 
@@ -1303,30 +1392,31 @@ int ludwig_ipc_export(ludwig_ctx* ctx, void* out, int64_t capacity_bytes, int64_
 int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_per_rank) {
     if (!ctx || !all_handles) return fail(ctx, LUDWIG_EINVAL, "bad attach args");
     CU(cudaSetDevice(ctx->device));
-    const int64_t need = ((int64_t)ctx->levels.size() * 7 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);
+    const int64_t need = ((int64_t)ctx->levels.size() * 8 + 1) * (int64_t)sizeof(cudaIpcMemHandle_t);
     if (bytes_per_rank != need) return fail(ctx, LUDWIG_EINVAL, "ipc attach: handle buffer size mismatch (same levels on every rank?)");
     for (int r = 0; r < ctx->world; ++r) {
         if (r == ctx->rank) continue;
         const auto* h = (const cudaIpcMemHandle_t*)((const char*)all_handles + (size_t)r * need);
         if (ctx->d_bar) {
             void* m = nullptr;
-            CU(cudaIpcOpenMemHandle(&m, h[ctx->levels.size() * 7], cudaIpcMemLazyEnablePeerAccess));
+            CU(cudaIpcOpenMemHandle(&m, h[ctx->levels.size() * 8], cudaIpcMemLazyEnablePeerAccess));
             ctx->ipc_opened.push_back(m);
             ctx->peer_bar[r] = (unsigned int*)m;
         }
         for (size_t l = 0; l < ctx->levels.size(); ++l) {
             Level& L = *ctx->levels[l];
-            void* own[7] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle};
-            void* mapped[7] = {};
-            for (int i = 0; i < 7; ++i) {
+            void* own[8] = {L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle, L.d_export};
+            void* mapped[8] = {};
+            for (int i = 0; i < 8; ++i) {
                 if (!own[i]) continue;   // same structure on every rank: absent here = absent there
-                CU(cudaIpcOpenMemHandle(&mapped[i], h[l * 7 + i], cudaIpcMemLazyEnablePeerAccess));
+                CU(cudaIpcOpenMemHandle(&mapped[i], h[l * 8 + i], cudaIpcMemLazyEnablePeerAccess));
                 ctx->ipc_opened.push_back(mapped[i]);
             }
             L.peer_f[0][r] = (const float*)mapped[0]; L.peer_f[1][r] = (const float*)mapped[1];
             L.peer_vel[0][r] = (const float*)mapped[2]; L.peer_vel[1][r] = (const float*)mapped[3];
             L.peer_rho[0][r] = (const float*)mapped[4]; L.peer_rho[1][r] = (const float*)mapped[5];
             L.peer_obstacle[r] = (const uint8_t*)mapped[6];
+            L.peer_export[r] = (const float*)mapped[7];
         }
     }
     return finish_attach(ctx);
@@ -1359,6 +1449,7 @@ int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const* peers, int32_t n
             const Level& O = *o->levels[l];
             for (int i = 0; i < 2; ++i) { L.peer_f[i][r] = O.d_f[i]; L.peer_vel[i][r] = O.d_vel[i]; L.peer_rho[i][r] = O.d_rho[i]; }
             L.peer_obstacle[r] = O.d_obstacle;
+            L.peer_export[r] = O.d_export;
         }
     }
     return finish_attach(ctx);

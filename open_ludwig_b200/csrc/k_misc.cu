@@ -177,49 +177,82 @@ void launch_bouzidi(const Level& L, float* f_out, const long long* roff, bool st
 }
 
 // ---------------------------------------------------------------------------------------------
-// Halo import (multi-GPU): copies, over NVLink, exactly the layer of a peer-owned neighbour block that this rank's K1 will
-// pull from — for the neighbour at offset d = (dx,dy,dz): the cells on its side facing the local block (x = 0 if dx = +1,
-// x = 7 if dx = -1, all 8 if dx = 0; same for y, z) and the populations that can cross that side (c_a = -d_a on every
-// axis with d_a != 0: 9 for a face, 3 for an edge, 1 for a corner), plus the three velocity components of a face layer
-// (WALE reads axis neighbours only) — into a LOCAL mirror of that block at the same in-block positions.  K1 then reads
-// local memory only; the import runs on a side stream concurrently with the K1 launch over the blocks that have no
-// remote neighbour, so NVLink latency is off the critical path.  One warp per (remote block, direction) entry.
-__global__ void __launch_bounds__(256) halo_import_kernel(const int32_t* __restrict__ hx, int n_hx, const float* const* __restrict__ src_f,
-                                                          const float* const* __restrict__ src_v, float* __restrict__ fmirror,
-                                                          float* __restrict__ vmirror) {
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= n_hx) return;
-    const int lane = threadIdx.x & 31;
-    const int ent = hx[e];
-    const int rid = ent >> 5, dir = ent & 31;
+// Packed halo exchange (multi-GPU).  What K1 pulls from a neighbour block owned by another GPU is one LAYER of it: for
+// the neighbour at offset d = (dx,dy,dz) the cells on its side facing the local block (x = 0 if dx = +1, x = 7 if dx = -1,
+// all 8 if dx = 0; same for y, z) and the populations that can cross that side (c_a = -d_a on every axis with d_a != 0:
+// 9 for a face, 3 for an edge, 1 for a corner), plus the three velocity components of a face layer (WALE reads axis
+// neighbours only): 768 / 24 / 1 floats.  Read in place over NVLink, an x-face costs a 32-byte sector per float.  So:
+//   * halo_pack_kernel (exporter, end of its level step): gathers every layer some peer needs from f_out / vel_out into a
+//     contiguous export buffer (local traffic), double-buffered by step parity;
+//   * halo_unpack_kernel (importer, start of the next level step, after the cross-rank barrier): pulls its segments of the
+//     peers' export buffers with fully coalesced loads over NVLink and scatters them into a LOCAL mirror of each remote
+//     block at the same in-block positions.  It runs on a high-priority side stream concurrently with the K1 launch over
+//     the blocks that have no remote neighbour; K1 itself only ever reads local memory.
+// Both sides derive the same entry order from the global tables (abi.cu, ludwig_level_create).  One warp per entry.
+__device__ __forceinline__ int halo_entry_size(int dir) {
+    const int dx = dir % 3 - 1, dy = (dir / 3) % 3 - 1, dz = dir / 9 - 1;
+    const int nz = (dx != 0) + (dy != 0) + (dz != 0);
+    return nz == 1 ? 768 : nz == 2 ? 24 : 1;
+}
+// element i of the entry for direction dir -> offset in the block's f array (i < npop * ncell) or, for the rest, in its
+// velocity array (returned negative minus one)
+__device__ __forceinline__ int halo_elem_offset(int dir, int i) {
     const int dx = dir % 3 - 1, dy = (dir / 3) % 3 - 1, dz = dir / 9 - 1;
     const int nx = dx ? 1 : 8, ny = dy ? 1 : 8, nz = dz ? 1 : 8;
-    const int x0 = dx > 0 ? 0 : (dx < 0 ? 7 : 0), y0 = dy > 0 ? 0 : (dy < 0 ? 7 : 0), z0 = dz > 0 ? 0 : (dz < 0 ? 7 : 0);
+    const int x0 = dx < 0 ? 7 : 0, y0 = dy < 0 ? 7 : 0, z0 = dz < 0 ? 7 : 0;
     const int ncell = nx * ny * nz;
     const int px = dx ? 1 : 3, py = dy ? 1 : 3, pz = dz ? 1 : 3;   // free lattice components per axis
-    const int npop = px * py * pz;
-    const float* __restrict__ sf = src_f[rid];
-    float* __restrict__ df = fmirror + (size_t)rid * (Q * BS3);
-    for (int i = lane; i < npop * ncell; i += 32) {
-        const int j = i / ncell, c = i - j * ncell;
-        const int x = x0 + c % nx, y = y0 + (c / nx) % ny, z = z0 + c / (nx * ny);
+    const int nf = px * py * pz * ncell;
+    const int ii = i < nf ? i : i - nf;
+    const int j = ii / ncell, c = ii - j * ncell;
+    const int cell = (z0 + c / (nx * ny)) * 64 + (y0 + (c / nx) % ny) * 8 + x0 + c % nx;
+    if (i < nf) {
         const int cx = dx ? -dx : j % px - 1, cy = dy ? -dy : (j / px) % py - 1, cz = dz ? -dz : j / (px * py) - 1;
-        const int off = ((cx + 1) + 3 * (cy + 1) + 9 * (cz + 1)) * BS3 + z * 64 + y * 8 + x;
-        df[off] = sf[off];
+        return ((cx + 1) + 3 * (cy + 1) + 9 * (cz + 1)) * BS3 + cell;
     }
-    if (dx * dx + dy * dy + dz * dz == 1) {
-        const float* __restrict__ sv = src_v[rid];
-        float* __restrict__ dv = vmirror + (size_t)rid * (3 * BS3);
-        for (int i = lane; i < 3 * ncell; i += 32) {
-            const int j = i / ncell, c = i - j * ncell;
-            const int off = j * BS3 + (z0 + c / (nx * ny)) * 64 + (y0 + (c / nx) % ny) * 8 + x0 + c % nx;
-            dv[off] = sv[off];
-        }
+    return -(j * BS3 + cell) - 1;
+}
+__global__ void __launch_bounds__(256) halo_pack_kernel(const int4* __restrict__ ent, int n, const float* __restrict__ f,
+                                                        const float* __restrict__ vel, float* __restrict__ exp_buf) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n) return;
+    const int4 q = ent[e];   // x: local block, y: direction, z: offset in the export buffer
+    const float* __restrict__ fb = f + (size_t)q.x * (Q * BS3);
+    const float* __restrict__ vb = vel + (size_t)q.x * (3 * BS3);
+    float* __restrict__ dst = exp_buf + q.z;
+    const int n_el = halo_entry_size(q.y);
+#pragma unroll 4
+    for (int i = threadIdx.x & 31; i < n_el; i += 32) {
+        const int off = halo_elem_offset(q.y, i);
+        dst[i] = off >= 0 ? fb[off] : vb[-off - 1];
     }
 }
-void launch_halo_import(const Level& L, int parity, cudaStream_t s) {
-    if (L.n_hx <= 0) return;
-    halo_import_kernel<<<(L.n_hx + 7) / 8, 256, 0, s>>>(L.d_hx, L.n_hx, L.d_rsrc_f[parity], L.d_rsrc_v[parity], L.d_fmirror, L.d_vmirror);
+struct HaloSrc { const float* p[MAX_RANKS]; };
+__global__ void __launch_bounds__(256) halo_unpack_kernel(const int4* __restrict__ ent, int n, HaloSrc src, float* __restrict__ fmirror,
+                                                          float* __restrict__ vmirror) {
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n) return;
+    const int4 q = ent[e];   // x: mirror slot (remote id), y: direction, z: offset in the exporter's buffer, w: exporter rank
+    const float* __restrict__ sp = src.p[q.w] + q.z;
+    float* __restrict__ fb = fmirror + (size_t)q.x * (Q * BS3);
+    float* __restrict__ vb = vmirror + (size_t)q.x * (3 * BS3);
+    const int n_el = halo_entry_size(q.y);
+#pragma unroll 4
+    for (int i = threadIdx.x & 31; i < n_el; i += 32) {
+        const float v = sp[i];
+        const int off = halo_elem_offset(q.y, i);
+        if (off >= 0) fb[off] = v; else vb[-off - 1] = v;
+    }
+}
+void launch_halo_pack(const Level& L, int buf, cudaStream_t s) {
+    if (L.n_pack <= 0) return;
+    halo_pack_kernel<<<(L.n_pack + 7) / 8, 256, 0, s>>>(L.d_pack, L.n_pack, L.d_f[buf], L.d_vel[buf], L.d_export + (size_t)buf * L.export_floats);
+}
+void launch_halo_unpack(const Level& L, int buf, cudaStream_t s) {
+    if (L.n_unpack <= 0) return;
+    HaloSrc src;
+    for (int r = 0; r < MAX_RANKS; ++r) src.p[r] = L.peer_export[r] ? L.peer_export[r] + (size_t)buf * L.peer_export_floats[r] : nullptr;
+    halo_unpack_kernel<<<(L.n_unpack + 7) / 8, 256, 0, s>>>(L.d_unpack, L.n_unpack, src, L.d_fmirror, L.d_vmirror);
 }
 
 // ---------------------------------------------------------------------------------------------

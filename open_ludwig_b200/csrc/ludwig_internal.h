@@ -77,16 +77,19 @@ struct Level {
     int n_remote = 0;
     long long* d_roff_f[2] = {nullptr, nullptr};   // per parity (index = parity of the INPUT buffer)
     long long* d_roff_v[2] = {nullptr, nullptr};
-    // halo mirrors (built by the attach unless LUDWIG_NO_MIRROR): local copies of the layers K1 pulls from remote blocks,
-    // refreshed by halo_import_kernel before every level step; K1 then addresses the mirror instead of the peer mapping
-    std::vector<int32_t> h_hx;             // (remote id << 5) | direction of the remote block seen from a local block
-    int32_t* d_hx = nullptr; int n_hx = 0;
+    // packed halo exchange (multi-GPU, opt-in with LUDWIG_HALO_MIRROR=1; see k_misc.cu): export buffer + pack list on the owner,
+    // unpack list + local mirrors of the remote blocks on the importer; K1 addresses the mirrors
+    std::vector<int4> h_pack, h_unpack;
+    int4* d_pack = nullptr; int n_pack = 0;       // {local block, direction, offset in the export buffer, 0}
+    int4* d_unpack = nullptr; int n_unpack = 0;   // {mirror slot, direction, offset in the exporter's buffer, exporter rank}
+    float* d_export = nullptr;                    // [2][export_floats], index = buffer (parity) the layers were taken from
+    size_t export_floats = 0;
+    size_t peer_export_floats[MAX_RANKS] = {};    // export_floats of every rank (both sides derive the same plan)
+    const float* peer_export[MAX_RANKS] = {};     // the peers' export buffers (IPC mappings)
     float* d_fmirror = nullptr;            // [n_remote][27][512]
     float* d_vmirror = nullptr;            // [n_remote][3][512]
     long long* d_moff_f[2] = {nullptr, nullptr};   // mirror block - local f_in (per input parity), K1's remote offsets
     long long* d_moff_v[2] = {nullptr, nullptr};
-    const float** d_rsrc_f[2] = {nullptr, nullptr};   // [n_remote] peer block base pointers per parity (import sources)
-    const float** d_rsrc_v[2] = {nullptr, nullptr};
     int n_plain_int = 0;                   // the first n_plain_int entries of d_list_plain have no remote neighbour
     // peer base pointers (index = rank); own pointers for this rank
     const float* peer_f[2][MAX_RANKS] = {};
@@ -113,6 +116,7 @@ struct Level {
     int n_ghost = 0;
     int32_t* d_gcoord = nullptr;         // [n_ghost][4]
     float* d_fghost = nullptr;           // [n_ghost][27][512]
+    int32_t* d_gstart = nullptr;         // [n_ghost + 1] offsets of every ghost block in the work list
     int32_t* d_gcell = nullptr;          // interface pre-pass work list
     uint32_t* d_gmask = nullptr;
     uint8_t* d_gcells8 = nullptr;
@@ -245,6 +249,8 @@ struct GhostArgs {
     const uint32_t* gmask;   // [n] bit k set: some real cell pulls population k from a cell of this group
     const uint8_t* gcells8;  // [n] bit (dz*4+dy*2+dx) set: that cell of the group is pulled from
     int n;
+    const int32_t* gstart;   // [n_ghost + 1] first work-list entry of every ghost block (block-cooperative variant)
+    int n_ghost;
     const int32_t* gcoord;   // [n_ghost][4] ghost block coords (0-based)
     float* f_ghost;          // [n_ghost][27][512]
     PeerPtrs pf_new, pf_old, prho_new, prho_old, pvel_new, pvel_old;   // parent state per owning rank
@@ -270,7 +276,8 @@ void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2re
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_block_flags(Level& L, cudaStream_t s);
-void launch_halo_import(const Level& L, int parity, cudaStream_t s);
+void launch_halo_pack(const Level& L, int buf, cudaStream_t s);
+void launch_halo_unpack(const Level& L, int buf, cudaStream_t s);
 void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s);
 void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
                          ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,

@@ -124,3 +124,24 @@ def test_parameter_variants(oracle_lib, cuda_lib, overrides):
         assert e_rho <= 1e-5, (overrides, lvl, e_rho)
         assert float(np.abs(ref[lvl]["vel"] - fast[lvl]["vel"]).max()) <= 1e-6, (overrides, lvl)
         assert float(np.abs(ref[lvl]["f"] - fast[lvl]["f"]).max()) <= 2e-6, (overrides, lvl)
+
+
+def test_block_prepass_variant_is_bit_identical(tmp_path):
+    """LUDWIG_PREPASS=block (one CTA per ghost block, parent cells staged in shared memory) performs the same arithmetic in
+    the same order as the default one-thread-per-group interface pre-pass: identical bits after 10 two-level steps.
+    The variant is selected once per process, hence the two subprocesses."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, sys.argv[2]); import numpy as np, test_k1_features_gpu as T\n"
+            "out, *_ = T.run(None, T.build_case(), 10, 0, True)\n"
+            "np.savez(sys.argv[1], **{f'{l}_{n}': a for l, d in out.items() for n, a in d.items()})\n")
+    res = {}
+    for mode in ("thread", "block"):
+        env = dict(os.environ, LUDWIG_PREPASS=mode, PYTHONPATH=root)
+        path = str(tmp_path / f"{mode}.npz")
+        r = subprocess.run([sys.executable, "-c", code, path, os.path.join(root, "tests")], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = np.load(path)
+    assert set(res["thread"].files) == set(res["block"].files) and len(res["thread"].files) >= 6
+    for k in res["thread"].files:
+        assert np.array_equal(res["thread"][k].view(np.int32), res["block"][k].view(np.int32)), k

@@ -76,10 +76,10 @@ def run_two_level(partitioned, steps=10, plan=False):
 
 ok = True
 ref, sref = run_box(False)
-for barrier in ("native", "nccl", "native-nomirror"):   # peer-flag barrier kernel / NCCL callback / direct NVLink pulls in K1
-    if barrier.endswith("nomirror"): os.environ["LUDWIG_NO_MIRROR"] = "1"
+for barrier in ("native", "nccl", "native-mirror"):   # peer-flag barrier kernel / NCCL callback / packed halo mirrors (opt-in)
+    if barrier.endswith("mirror"): os.environ["LUDWIG_HALO_MIRROR"] = "1"
     got, sgot = run_box(True, barrier=barrier.split("-")[0])
-    os.environ.pop("LUDWIG_NO_MIRROR", None)
+    os.environ.pop("LUDWIG_HALO_MIRROR", None)
     for k in ref:
         same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
         ok &= same

@@ -8,6 +8,9 @@ lock-step; forces are reduced over the ranks.  Prints true MLUPS (max time over 
 """
 import os, sys, time
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
+# host threads (set before anything loads an OpenMP runtime; torchrun exports OMP_NUM_THREADS=1): rank 0 builds the domain
+# with every core, the other ranks only map the cached arrays
+os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 8) if rank == 0 else "2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
@@ -24,7 +27,6 @@ case, ov = CASE_OVERRIDES[name]
 t0 = time.time()
 if world > 1:
     # rank 0 builds the domain with every host thread and caches it in shared memory; the others map the arrays
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 8)
     cache = f"/dev/shm/ludwig_domain_{name}_{os.getppid()}"
     if rank == 0:
         dom = D.load_case(case_dir(case), ov, verbose=True, build_tri_map=False)
@@ -95,7 +97,7 @@ if os.environ.get("LUDWIG_PROFILE") is not None:   # per-level / per-class devic
     ctx.profile_enable(False)
     loc = [len(ctx.local_blocks(i)) for i in range(len(dom.levels))]
     print(f"rank {rank}: blocks {loc} per level [ms/coarse step]: " + " | ".join(
-        f"L{i+1} {d['level_step']/steps:.2f} (k1p {d['k1_plain']/steps:.2f} bz {d['bouzidi']/steps:.2f} bar {d['barrier']/steps:.2f})" for i, d in enumerate(lv)), flush=True)
+        f"L{i+1} {d['level_step']/steps:.2f} (k1p {d['k1_plain']/steps:.2f} pg {d['k1_plain_ghost']/steps:.2f} ft {d['k1_feature']/steps:.2f} fu {d['k1_full']/steps:.2f} pre {d['interface_prepass']/steps:.2f} bz {d['bouzidi']/steps:.2f} bar {d['barrier']/steps:.2f} unp {d['halo_unpack']/steps:.2f} pk {d['halo_pack']/steps:.2f})" for i, d in enumerate(lv)), flush=True)
 if world > 1: dist.barrier()
 aero = ctx.compute_aerodynamics(forces, len(dom.levels) - 1, p.mesh_offset, p.velocity_scale, p.rho_physical, 5)
 stats = ctx.flow_stats(0)
