@@ -15,6 +15,8 @@ SEARCH = (os.path.join(_ROOT, "baseline", "_ref", "CASES"), "/root/reference/CAS
 CASE_OVERRIDES = {
     # config 3: the configuration RESULTS_SPHERE_RE1M.txt was produced with (N = 25 cells/L, U = 14.8 m/s; :38,:153)
     "sphere_re1m": ("ball1m", {"basic": {"surface_resolution": 25, "flow": {"velocity": 14.8}}}),
+    # the same grid at U = 4.0 m/s: the configuration of RESULTS_SPHERE_RE266K.txt (:37, tau_levels :146, rows :203-227)
+    "sphere_re266k": ("ball1m", {"basic": {"surface_resolution": 25, "flow": {"velocity": 4.0}}}),
     # the shipped ball1m case = RESULTS_SPHERE_RE10M.txt / CASES/ball1m/RESULTS/*.csv
     "sphere_re10m": ("ball1m", None),
     # config 1: coarsest single-level grid, 500 steps

@@ -137,4 +137,20 @@ end
 
 sync(ctx::Context) = check(ctx, ccall((:ludwig_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h), "ludwig_sync")
 
+# ---- more than one GPU: one process per GPU (INTEGRATION.md "More than one GPU") -----------------------------------
+# call right after Context(local_rank), before the first add_level!
+set_partition!(ctx::Context, rank::Integer, world::Integer) =
+    check(ctx, ccall((:ludwig_ctx_set_partition, LIB), Cint, (Ptr{Cvoid}, Int32, Int32), ctx.h, rank, world), "ludwig_ctx_set_partition")
+
+# after the last add_level!: `allgather(bytes) -> bytes of every rank concatenated` is the host's collective
+# (MPI.Allgather(buf, comm) with MPI.jl).  From then on the kernels read the peers' blocks over NVLink.
+function attach_peers!(ctx::Context, allgather::Function)
+    need = Ref{Int64}(0)
+    check(ctx, ccall((:ludwig_ipc_export, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}), ctx.h, C_NULL, 0, need), "ludwig_ipc_export")
+    buf = Vector{UInt8}(undef, need[])
+    GC.@preserve buf check(ctx, ccall((:ludwig_ipc_export, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}), ctx.h, pointer(buf), need[], need), "ludwig_ipc_export")
+    all = allgather(buf)
+    GC.@preserve all check(ctx, ccall((:ludwig_ipc_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, pointer(all), need[]), "ludwig_ipc_attach")
+end
+
 end # module

@@ -3,6 +3,7 @@ setup code must reproduce EVERY integer the reference's shipped console logs pri
 
   RESULTS_SPHERE_RE1M.txt:48,60-106,160-163     (ball1m with surface_resolution 25, velocity 14.8)
   RESULTS_SPHERE_RE10M.txt:48,60-116,181-185    (ball1m as shipped)
+  RESULTS_SPHERE_RE266K.txt:37,44,56-94,99,156-158  (ball1m with surface_resolution 25, velocity 4.0)
 """
 import numpy as np
 import pytest
@@ -57,6 +58,23 @@ def test_re10m_counts(re10m):
     assert r[3].n_boundary_cells == 28400                                                # :106
     assert [f"{t:.6f}" for t in p.tau_levels] == ["0.500008", "0.500004", "0.500002", "0.500001"]   # :116
     assert [round(v, 3) for v in p.mesh_offset] == [4.25, 4.655, 4.655]                  # :181
+
+
+def test_re266k_scaling_and_counts():
+    """The third shipped log: the Re = 1M grid at U = 4 m/s — same topology, different tau per level and force scales."""
+    case, ov = CASE_OVERRIDES["sphere_re266k"]
+    dom = D.load_case(case_dir(case), ov)
+    p, r = dom.params, dom.reports
+    assert p.num_levels == 3 and (p.bx_max, p.by_max, p.bz_max) == (8, 7, 7)            # RESULTS_SPHERE_RE266K.txt:44,56
+    assert round(p.re_number) == 266667                                                  # :44
+    assert [f"{t:.6f}" for t in p.tau_levels] == ["0.500034", "0.500017", "0.500008"]   # :99
+    assert [x.n_blocks for x in r] == [392, 1000, 1728]                                  # :56,:76,:93
+    assert [x.halo_added for x in r[1:]] == [988, 1660]                                  # :68,:80
+    assert [x.filled_voxels for x in r] == [28, 548, 6084]                               # :59,:71,:83
+    assert r[2].n_boundary_cells == 5824                                                 # :90
+    assert [round(v, 3) for v in p.mesh_offset] == [4.25, 4.48, 4.48]                    # :156
+    assert round(float(np.float32(p.rho_physical * p.velocity_scale ** 2)), 2) == 21777.78   # :158
+    assert p.u_physical == 4.0
 
 
 def test_tables_are_consistent(re1m):
