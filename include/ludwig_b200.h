@@ -124,6 +124,16 @@ int ludwig_num_levels(const ludwig_ctx* ctx);
 int ludwig_level_upload(ludwig_ctx* ctx, int32_t level, int32_t which, const void* src);
 int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* dst);
 
+/* io_vtk.jl:52-58,100-107 (export_merged_mesh_sync, steps "2. Gather data" and the field part of "3."): the reference copies
+ * the WHOLE rho / vel (or vel_temp) / obstacle arrays of every level to the host and then picks the blocks that are not
+ * covered by a finer level.  This call gathers only the listed blocks on the device, in the order given, straight into the
+ * arrays the VTK writer fills: rho_arr Float32[512 n], vel_mat Float32[3, 512 n] (component fastest, as Julia's
+ * Matrix{Float32}(3, N)), obst_arr UInt8[512 n] (0 / 1); NaN and +-Inf become 0 as in io_vtk.jl:110-111.  Cell order
+ * inside a block is x fastest (cidx of :95).  Velocity buffer by the parity of t_step as :56 (even -> vel_temp).
+ * blocks = 1-based reference block indices (b_idx of :27); in a multi-GPU context they must be blocks of this rank. */
+int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const int32_t* blocks, int32_t n_blocks,
+                         float* rho_arr, float* vel_mat, uint8_t* obst_arr);
+
 /* main.jl:101  Geometry.upload_mesh_to_gpu (geometry.jl:60-84): Float32 SoA. */
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n_triangles,
                        const float* cx, const float* cy, const float* cz,

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_partition_plan",
     "ludwig_ctx_set_partition_keys", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
-    "ludwig_attach_inprocess", "ludwig_profile_levels",
+    "ludwig_attach_inprocess", "ludwig_profile_levels", "ludwig_output_gather",
 )
 
 BARRIER_CB = C.CFUNCTYPE(None, C.c_void_p)
@@ -119,6 +119,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_ipc_attach": (C.c_int, [vp, vp, i64]),
         "ludwig_attach_inprocess": (C.c_int, [vp, C.POINTER(vp), i32]),
         "ludwig_profile_levels": (C.c_int, [vp, C.POINTER(f64), i32]),
+        "ludwig_output_gather": (C.c_int, [vp, i32, i64, vp, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -222,6 +223,15 @@ class Context:
 
     def sync(self):
         self._check(self.lib.ludwig_sync(self._h), "ludwig_sync")
+
+    def output_gather(self, level: int, t_step: int, blocks0: np.ndarray):
+        """io_vtk.jl:52-58,100-111 for the listed blocks (0-based reference indices): (rho_arr [512 n], vel_mat [512 n, 3]
+        = Julia's Matrix{Float32}(3, 512 n), obst_arr [512 n]) exactly as the VTK writer fills them."""
+        ids = _as(np.asarray(blocks0) + 1, np.int32)
+        n = ids.size
+        rho = np.empty(512 * n, np.float32); vel = np.empty((512 * n, 3), np.float32); obs = np.empty(512 * n, np.uint8)
+        self._check(self.lib.ludwig_output_gather(self._h, level, t_step, _ptr(ids), n, _ptr(rho), _ptr(vel), _ptr(obs)), "ludwig_output_gather")
+        return rho, vel, obs
 
     def device_bytes(self) -> int:
         return int(self.lib.ludwig_device_bytes(self._h))

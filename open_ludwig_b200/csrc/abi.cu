@@ -459,12 +459,15 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
         // levels, where each of them is a few waves of latency-bound CTAs, they run concurrently on side streams.
         const bool fork = ctx->side[0] != nullptr && L.nb <= ctx->fork_max_blocks;
+        // LUDWIG_FORK_FULL=1 (experiment for large levels, unmeasured): the domain-face blocks (128 registers, latency-bound,
+        // 8 GLUPS on the bench box's inlet / outlet faces) run on a side stream UNDER the HBM-bound plain launch
+        const bool fork_full = !fork && ctx->fork_full && ctx->side[0] != nullptr && L.n_full > 0 && L.n_plain > 0;
         int used = 0;
-        if (fork) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        if (fork || fork_full) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream, bool ghosts) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
-            if (!fork || main_stream) {
+            if ((!fork && !(fork_full && fn == launch_k1_full)) || main_stream) {
                 if (overlap_pre && ghosts) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
                 fn(a, ctx->stream);
             } else {
@@ -479,6 +482,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             ctx->launches += 1;
             return LUDWIG_OK;
         };
+        if (fork_full && (rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, false, true))) return rc;
         if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
         if (wait_halo) {
             if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain_int, true, false))) return rc;
@@ -487,7 +491,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         } else if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
         if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
         // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
-        const bool pc = ctx->profiling && !fork;
+        const bool pc = ctx->profiling && !fork && !fork_full;
         if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
         if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_plain_g > 0, 0))) return rc;
@@ -495,7 +499,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
         if ((rc = prof_begin(ctx, 3, pc && L.n_full > 0))) return rc;
-        if ((rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
+        if (!fork_full && (rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         if (overlap_pre) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));   // nothing on the main stream consumed it yet
@@ -630,6 +634,7 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
              cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_halo_fork, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
+        ctx->fork_full = getenv("LUDWIG_FORK_FULL") != nullptr;
         if (getenv("LUDWIG_SERIAL_PREPASS")) { cudaStreamDestroy(ctx->pre_stream); ctx->pre_stream = nullptr; }
         if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
@@ -1044,6 +1049,38 @@ int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* d
     int rc = resolve_field(ctx, L, which, false, &p, &ncomp);
     if (rc) return rc;
     return download_field(ctx, L, p, (float*)dst, ncomp);
+}
+
+// N3 (io_vtk.jl:52-58,100-111): device-side gather of the listed blocks into the VTK writer's arrays.
+int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const int32_t* blocks, int32_t n_blocks,
+                         float* rho_arr, float* vel_mat, uint8_t* obst_arr) {
+    if (!level_ok(ctx, level) || !blocks || n_blocks < 0 || !rho_arr || !vel_mat || !obst_arr) return fail(ctx, LUDWIG_EINVAL, "bad gather args");
+    if (n_blocks == 0) return LUDWIG_OK;
+    CU(cudaSetDevice(ctx->device));
+    Level& L = *ctx->levels[level];
+    std::vector<int32_t> sel(n_blocks);
+    for (int i = 0; i < n_blocks; ++i) {
+        const int br = blocks[i] - 1;
+        if (br < 0 || br >= L.nb_global) return fail(ctx, LUDWIG_EINVAL, "gather: block index out of range");
+        const int loc = L.ref2int[br] - L.part_start;
+        if (loc < 0 || loc >= L.nb) return fail(ctx, LUDWIG_EINVAL, "gather: block belongs to another rank");
+        sel[i] = loc;
+    }
+    const size_t nc = (size_t)n_blocks * BS3;
+    int32_t* d_sel = nullptr; float* d_out = nullptr; uint8_t* d_obs = nullptr;
+    struct Free { int32_t*& a; float*& b; uint8_t*& c; ~Free() { if (a) cudaFree(a); if (b) cudaFree(b); if (c) cudaFree(c); } } guard{d_sel, d_out, d_obs};
+    CU(cudaMalloc((void**)&d_sel, (size_t)n_blocks * 4));
+    CU(cudaMalloc((void**)&d_out, nc * 4 * sizeof(float)));   // rho [nc] followed by vel [3 nc]
+    CU(cudaMalloc((void**)&d_obs, nc));
+    CU(cudaMemcpyAsync(d_sel, sel.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const float* vel = (t_step % 2 == 0) ? L.d_vel[1] : L.d_vel[0];   // io_vtk.jl:56
+    launch_output_gather(d_sel, n_blocks, L.d_rho[L.rho_cur], vel, L.d_obstacle, d_out, d_out + nc, d_obs, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rho_arr, d_out, nc * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(vel_mat, d_out + nc, nc * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(obst_arr, d_obs, nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LUDWIG_OK;
 }
 
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n, const float* cx, const float* cy, const float* cz, const float* nx, const float* ny,

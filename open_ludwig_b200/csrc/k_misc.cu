@@ -177,6 +177,27 @@ void launch_bouzidi(const Level& L, float* f_out, const long long* roff, bool st
 }
 
 // ---------------------------------------------------------------------------------------------
+// N3 output gather (io_vtk.jl:52-58,100-111): the listed blocks only, written in the VTK writer's own array layout
+// (rho[N], vel[3][N] component-fastest, obstacle[N]; non-finite values -> 0).  One CTA per listed block.
+__global__ void __launch_bounds__(256) output_gather_kernel(const int32_t* __restrict__ sel, const float* __restrict__ rho,
+                                                            const float* __restrict__ vel, const uint8_t* __restrict__ obs,
+                                                            float* __restrict__ o_rho, float* __restrict__ o_vel, uint8_t* __restrict__ o_obs) {
+    const int i = blockIdx.x, b = sel[i];
+    for (int c = threadIdx.x; c < BS3; c += blockDim.x) {
+        const size_t s = (size_t)b * BS3 + c, o = (size_t)i * BS3 + c;
+        auto clean = [](float v) { return isfinite(v) ? v : 0.0f; };
+        o_rho[o] = clean(rho[s]);
+        const float* vb = vel + (size_t)b * 3 * BS3 + c;
+        o_vel[o * 3 + 0] = clean(vb[0]); o_vel[o * 3 + 1] = clean(vb[BS3]); o_vel[o * 3 + 2] = clean(vb[2 * BS3]);
+        o_obs[o] = obs[s] ? 1 : 0;
+    }
+}
+void launch_output_gather(const int32_t* sel, int n, const float* rho, const float* vel, const uint8_t* obs, float* o_rho, float* o_vel,
+                          uint8_t* o_obs, cudaStream_t s) {
+    if (n > 0) output_gather_kernel<<<n, 256, 0, s>>>(sel, rho, vel, obs, o_rho, o_vel, o_obs);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Packed halo exchange (multi-GPU).  What K1 pulls from a neighbour block owned by another GPU is one LAYER of it: for
 // the neighbour at offset d = (dx,dy,dz) the cells on its side facing the local block (x = 0 if dx = +1, x = 7 if dx = -1,
 // all 8 if dx = 0; same for y, z) and the populations that can cross that side (c_a = -d_a on every axis with d_a != 0:

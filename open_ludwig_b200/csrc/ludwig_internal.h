@@ -184,7 +184,8 @@ struct ludwig_ctx {
     cudaEvent_t ev_pre_fork = nullptr, ev_pre = nullptr;
     cudaStream_t halo_stream = nullptr;      // halo import (multi-GPU), concurrent with the K1 launch over interior blocks
     cudaEvent_t ev_halo = nullptr, ev_halo_fork = nullptr;
-    bool use_mirror = true;
+    bool use_mirror = false;
+    bool fork_full = false;                  // LUDWIG_FORK_FULL: domain-face K1 launch concurrent with the plain launch on large levels
     int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
     std::vector<ludwig::Level*> levels;
     std::string err;
@@ -276,6 +277,8 @@ void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2re
 void launch_ref_to_int_u8(const uint8_t* src_ref, uint8_t* dst, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_int_to_ref_u8(const uint8_t* src, uint8_t* dst_ref, const int32_t* int2ref, int nb, cudaStream_t s);
 void launch_block_flags(Level& L, cudaStream_t s);
+void launch_output_gather(const int32_t* sel, int n, const float* rho, const float* vel, const uint8_t* obs, float* o_rho, float* o_vel,
+                          uint8_t* o_obs, cudaStream_t s);
 void launch_halo_pack(const Level& L, int buf, cudaStream_t s);
 void launch_halo_unpack(const Level& L, int buf, cudaStream_t s);
 void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s);

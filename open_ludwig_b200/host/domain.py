@@ -30,7 +30,8 @@ _lib = None
 def host_lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        src = os.path.join(_HERE, "domain_build.cpp")
+        if not os.path.exists(_LIB_PATH) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)):
             subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
         lib = C.CDLL(_LIB_PATH)
         vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -46,6 +47,8 @@ def host_lib() -> C.CDLL:
         lib.ludwig_host_wall_distance.restype = i64
         lib.ludwig_host_qmap.argtypes = [vp, i64, vp, i32, f64, vp, i64, vp, vp, vp]
         lib.ludwig_host_qmap.restype = i64
+        lib.ludwig_host_scatter_qmap.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
+        lib.ludwig_host_scatter_qmap.restype = None
         _lib = lib
     return _lib
 
@@ -222,13 +225,10 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
             q_map = np.zeros((27, nb, 8, 8, 8), np.float16)
             # tri_map (bouzidi_setup.jl:85) is never read by a kernel: 108 B/cell of host memory, optional for huge levels
             tri_map = np.zeros((27, nb, 8, 8, 8), np.int32) if build_tri_map else None
-            b, x, y, z = cells[:, 0] - 1, cells[:, 1] - 1, cells[:, 2] - 1, cells[:, 3] - 1
             q16 = qv.astype(np.float16)               # Float16(q) round-to-nearest-even (bouzidi_setup.jl:128)
-            for k in range(27):
-                sel = qv[:, k] > 0.0
-                q_map[k, b[sel], z[sel], y[sel], x[sel]] = q16[sel, k]
-                if tri_map is not None:
-                    tri_map[k, b[sel], z[sel], y[sel], x[sel]] = tv[sel, k]
+            cells_c, qv_c, q16_c, tv_c = (np.ascontiguousarray(a) for a in (cells, qv, q16, tv))
+            lib.ludwig_host_scatter_qmap(_p(cells_c), _p(qv_c), _p(q16_c), _p(tv_c) if tri_map is not None else None, n_bc, nb,
+                                         _p(q_map), _p(tri_map) if tri_map is not None else None)
             cell_block = cells[:, 0].astype(np.int32)
             cell_x, cell_y, cell_z = (cells[:, i].astype(np.int8) for i in (1, 2, 3))
             qf = q16.astype(np.float32)

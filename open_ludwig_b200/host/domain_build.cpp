@@ -165,42 +165,87 @@ void ludwig_host_voxelize(const double* tris, int64_t n_tri, const int32_t* coor
 
 // domain_generation.jl:114-203.  block_ptr is the reference's [bx,by,bz] column-major pointer (1-based, 0 none).
 // Returns the number of filled voxels.
+// Same reachable set as the reference's cell-by-cell BFS from the non-obstacle cells of the min-bx blocks (6-connected),
+// computed at two granularities: a block without any obstacle cell is internally connected, so it is visited as ONE node
+// (reached as soon as any of its cells is, and it then reaches every non-obstacle cell on the facing layer of its six
+// neighbours); only the blocks that hold obstacle cells (the surface shell, a few % of a level) are walked cell by cell.
 int64_t ludwig_host_flood_fill(uint8_t* obstacle, const int32_t* coords, int nb, const int32_t* block_ptr, int dimx, int dimy, int dimz) {
-    const size_t n = (size_t)nb * 512;
-    std::vector<uint8_t> visited(n, 0);
+    std::vector<uint8_t> has_obs(nb, 0), bvis(nb, 0);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nb; ++b) {
+        uint8_t any = 0;
+        for (int c = 0; c < 512; ++c) any |= obstacle[(size_t)b * 512 + c];
+        has_obs[b] = any != 0;
+    }
+    std::vector<uint32_t> cell_slot(nb, 0xFFFFFFFFu);   // index of the block's 512 visited flags, shell blocks only
+    size_t n_shell = 0;
+    for (int b = 0; b < nb; ++b) if (has_obs[b]) cell_slot[b] = (uint32_t)n_shell++;
+    std::vector<uint8_t> visited(n_shell * 512, 0);
+    constexpr uint32_t BLOCK_NODE = 0x80000000u;
     std::vector<uint32_t> queue;
-    queue.reserve(n);
+    queue.reserve((size_t)nb + n_shell * 64);
+    auto visit_cell = [&](int b, int c) {
+        uint8_t& v = visited[(size_t)cell_slot[b] * 512 + c];
+        if (!v && !obstacle[(size_t)b * 512 + c]) { v = 1; queue.push_back(((uint32_t)b << 9) | (uint32_t)c); }
+    };
+    auto visit_block = [&](int b) {
+        if (!bvis[b]) { bvis[b] = 1; queue.push_back(BLOCK_NODE | (uint32_t)b); }
+    };
     int min_x = coords[0];
     for (int i = 0; i < nb; ++i) min_x = std::min(min_x, coords[3 * i]);
     for (int b = 0; b < nb; ++b)
-        if (coords[3 * b] == min_x)
-            for (int c = 0; c < 512; ++c)
-                if (!obstacle[(size_t)b * 512 + c]) { visited[(size_t)b * 512 + c] = 1; queue.push_back((uint32_t)((size_t)b * 512 + c)); }
+        if (coords[3 * b] == min_x) {
+            if (!has_obs[b]) visit_block(b);
+            else for (int c = 0; c < 512; ++c) visit_cell(b, c);
+        }
     const int ddx[6] = {1, -1, 0, 0, 0, 0}, ddy[6] = {0, 0, 1, -1, 0, 0}, ddz[6] = {0, 0, 0, 0, 1, -1};
+    auto neighbour_block = [&](int b, int i) -> int {
+        const int nbx = coords[3 * b] + ddx[i], nby = coords[3 * b + 1] + ddy[i], nbz = coords[3 * b + 2] + ddz[i];
+        if (nbx < 1 || nbx > dimx || nby < 1 || nby > dimy || nbz < 1 || nbz > dimz) return -1;
+        return block_ptr[(nbx - 1) + (size_t)dimx * ((nby - 1) + (size_t)dimy * (nbz - 1))] - 1;   // -1 = none
+    };
     size_t head = 0;
     while (head < queue.size()) {
-        uint32_t cur = queue[head++];
-        int b = (int)(cur >> 9), c = (int)(cur & 511);
-        int lx = c & 7, ly = (c >> 3) & 7, lz = c >> 6;
-        int bx = coords[3 * b], by = coords[3 * b + 1], bz = coords[3 * b + 2];
-        for (int i = 0; i < 6; ++i) {
-            int nx = lx + ddx[i], ny = ly + ddy[i], nz = lz + ddz[i];
-            size_t tgt;
-            if (nx >= 0 && nx < BS && ny >= 0 && ny < BS && nz >= 0 && nz < BS) {
-                tgt = (size_t)b * 512 + nz * 64 + ny * 8 + nx;
-            } else {
-                int nbx = bx + ddx[i], nby = by + ddy[i], nbz = bz + ddz[i];
-                if (nbx < 1 || nbx > dimx || nby < 1 || nby > dimy || nbz < 1 || nbz > dimz) continue;
-                int nbi = block_ptr[(nbx - 1) + (size_t)dimx * ((nby - 1) + (size_t)dimy * (nbz - 1))];
-                if (nbi <= 0) continue;
-                tgt = (size_t)(nbi - 1) * 512 + ((nz + BS) % BS) * 64 + ((ny + BS) % BS) * 8 + ((nx + BS) % BS);
+        const uint32_t cur = queue[head++];
+        if (cur & BLOCK_NODE) {
+            const int b = (int)(cur & ~BLOCK_NODE);
+            for (int i = 0; i < 6; ++i) {
+                const int t = neighbour_block(b, i);
+                if (t < 0) continue;
+                if (!has_obs[t]) { visit_block(t); continue; }
+                // the 64 cells of the neighbour's layer that faces this block
+                for (int u = 0; u < BS; ++u)
+                    for (int v = 0; v < BS; ++v) {
+                        const int x = ddx[i] ? (ddx[i] > 0 ? 0 : BS - 1) : u;
+                        const int y = ddy[i] ? (ddy[i] > 0 ? 0 : BS - 1) : (ddx[i] ? u : v);
+                        const int z = ddz[i] ? (ddz[i] > 0 ? 0 : BS - 1) : v;
+                        visit_cell(t, z * 64 + y * 8 + x);
+                    }
             }
-            if (!visited[tgt] && !obstacle[tgt]) { visited[tgt] = 1; queue.push_back((uint32_t)tgt); }
+            continue;
+        }
+        const int b = (int)(cur >> 9), c = (int)(cur & 511);
+        const int lx = c & 7, ly = (c >> 3) & 7, lz = c >> 6;
+        for (int i = 0; i < 6; ++i) {
+            const int nx = lx + ddx[i], ny = ly + ddy[i], nz = lz + ddz[i];
+            if (nx >= 0 && nx < BS && ny >= 0 && ny < BS && nz >= 0 && nz < BS) { visit_cell(b, nz * 64 + ny * 8 + nx); continue; }
+            const int t = neighbour_block(b, i);
+            if (t < 0) continue;
+            if (!has_obs[t]) visit_block(t);
+            else visit_cell(t, ((nz + BS) % BS) * 64 + ((ny + BS) % BS) * 8 + ((nx + BS) % BS));
         }
     }
     int64_t filled = 0;
-    for (size_t i = 0; i < n; ++i)
-        if (!obstacle[i] && !visited[i]) { obstacle[i] = 1; ++filled; }
+#pragma omp parallel for schedule(static) reduction(+ : filled)
+    for (int b = 0; b < nb; ++b) {
+        if (!has_obs[b]) {
+            if (!bvis[b]) { std::memset(obstacle + (size_t)b * 512, 1, 512); filled += 512; }
+            continue;
+        }
+        const uint8_t* v = visited.data() + (size_t)cell_slot[b] * 512;
+        for (int c = 0; c < 512; ++c)
+            if (!obstacle[(size_t)b * 512 + c] && !v[c]) { obstacle[(size_t)b * 512 + c] = 1; ++filled; }
+    }
     return filled;
 }
 
@@ -282,8 +327,33 @@ int64_t ludwig_host_wall_distance(const int32_t* coords, int nb, const uint8_t* 
 // Pruning: a hit with q <= 1 lies within one dx of the cell centre on every axis, so triangles whose offset AABB
 // misses [centre - 1.001 dx, centre + 1.001 dx] cannot change the result (min_t of the reference is taken over
 // all hits, but if its nearest hit has q > 1 every hit has).
+// The caller asks twice (count, then fill): the counting call keeps its result for the fill call with the same arguments.
+namespace {
+struct QmapCache {
+    const void *tris = nullptr, *coords = nullptr;
+    int64_t n_tri = 0; int nb = 0; double dx = 0;
+    std::vector<int32_t> cells, tri;
+    std::vector<double> q;
+    bool matches(const double* t, int64_t nt, const int32_t* c, int n, double d) const {
+        return tris == t && coords == c && n_tri == nt && nb == n && dx == d && !cells.empty();
+    }
+    void clear() { tris = coords = nullptr; cells.clear(); cells.shrink_to_fit(); tri.clear(); tri.shrink_to_fit(); q.clear(); q.shrink_to_fit(); }
+} g_qmap_cache;
+}  // namespace
+
 int64_t ludwig_host_qmap(const double* tris, int64_t n_tri, const int32_t* coords, int nb, double dx, const double* off,
                          int64_t capacity, int32_t* out_cells /*[n][4]*/, double* out_q /*[n][27]*/, int32_t* out_tri /*[n][27]*/) {
+    if (out_cells && out_q && out_tri && g_qmap_cache.matches(tris, n_tri, coords, nb, dx)) {
+        const int64_t n = (int64_t)g_qmap_cache.cells.size() / 4;
+        if (capacity >= n) {
+            std::memcpy(out_cells, g_qmap_cache.cells.data(), (size_t)n * 4 * sizeof(int32_t));
+            std::memcpy(out_q, g_qmap_cache.q.data(), (size_t)n * 27 * sizeof(double));
+            std::memcpy(out_tri, g_qmap_cache.tri.data(), (size_t)n * 27 * sizeof(int32_t));
+            g_qmap_cache.clear();
+            return n;
+        }
+    }
+    g_qmap_cache.clear();
     std::vector<std::vector<int32_t>> map;
     build_block_triangle_map(tris, n_tri, coords, nb, dx, off, dx * 2.5, true, map);
     std::vector<std::vector<int32_t>> cells(nb);
@@ -349,7 +419,18 @@ int64_t ludwig_host_qmap(const double* tris, int64_t n_tri, const int32_t* coord
     }
     int64_t n = 0;
     for (int b = 0; b < nb; ++b) n += (int64_t)cells[b].size() / 4;
-    if (!out_cells || !out_q || !out_tri || capacity < n) return n;
+    if (!out_cells || !out_q || !out_tri || capacity < n) {
+        if (n > 0) {   // counting call: keep the result for the fill call
+            g_qmap_cache.tris = tris; g_qmap_cache.coords = coords; g_qmap_cache.n_tri = n_tri; g_qmap_cache.nb = nb; g_qmap_cache.dx = dx;
+            g_qmap_cache.cells.reserve((size_t)n * 4); g_qmap_cache.q.reserve((size_t)n * 27); g_qmap_cache.tri.reserve((size_t)n * 27);
+            for (int b = 0; b < nb; ++b) {
+                g_qmap_cache.cells.insert(g_qmap_cache.cells.end(), cells[b].begin(), cells[b].end());
+                g_qmap_cache.q.insert(g_qmap_cache.q.end(), qs[b].begin(), qs[b].end());
+                g_qmap_cache.tri.insert(g_qmap_cache.tri.end(), tr[b].begin(), tr[b].end());
+            }
+        }
+        return n;
+    }
     int64_t o = 0;
     for (int b = 0; b < nb; ++b) {
         int64_t m = (int64_t)cells[b].size() / 4;
@@ -360,6 +441,22 @@ int64_t ludwig_host_qmap(const double* tris, int64_t n_tri, const int32_t* coord
         o += m;
     }
     return n;
+}
+
+// Dense q_map / tri_map of the reference layout ([k][b][z][y][x], bouzidi_setup.jl:82-85,128-129) from the sparse boundary-cell rows.
+// q16 holds the Float16 bit patterns of the rows (converted by the caller), q > 0 selects the written entries.
+void ludwig_host_scatter_qmap(const int32_t* cells /*[n][4] 1-based*/, const double* q /*[n][27]*/, const uint16_t* q16 /*[n][27]*/,
+                              const int32_t* tri /*[n][27] or NULL*/, int64_t n, int64_t nb, uint16_t* q_map, int32_t* tri_map /* or NULL */) {
+    const size_t plane = (size_t)nb * 512;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const size_t cell = (size_t)(cells[i * 4] - 1) * 512 + (size_t)(cells[i * 4 + 3] - 1) * 64 + (size_t)(cells[i * 4 + 2] - 1) * 8 + (size_t)(cells[i * 4 + 1] - 1);
+        for (int k = 0; k < 27; ++k)
+            if (q[i * 27 + k] > 0.0) {
+                q_map[plane * k + cell] = q16[i * 27 + k];
+                if (tri_map && tri) tri_map[plane * k + cell] = tri[i * 27 + k];
+            }
+    }
 }
 
 }  // extern "C"

@@ -609,6 +609,27 @@ int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* d
     return LUDWIG_OK;
 }
 
+// io_vtk.jl:52-58,100-111 restated: whole-array semantics, then the listed blocks.
+int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const int32_t* blocks, int32_t n_blocks,
+                         float* rho_arr, float* vel_mat, uint8_t* obst_arr) {
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size() || !blocks || n_blocks < 0 || !rho_arr || !vel_mat || !obst_arr)
+        return fail(ctx, LUDWIG_EINVAL, "bad gather args");
+    Level& L = *ctx->levels[level];
+    const std::vector<float>& vel = (t_step % 2 == 0) ? L.vel_temp : L.vel;   // :56
+    auto clean = [](float v) { return std::isfinite(v) ? v : 0.0f; };         // :110-111
+    for (int i = 0; i < n_blocks; ++i) {
+        const int b = blocks[i] - 1;
+        if (b < 0 || b >= L.nb) return fail(ctx, LUDWIG_EINVAL, "gather: block index out of range");
+        for (int c = 0; c < 512; ++c) {
+            const size_t o = (size_t)i * 512 + c, s = (size_t)b * 512 + c;
+            rho_arr[o] = clean(L.rho[s]);
+            for (int k = 0; k < 3; ++k) vel_mat[o * 3 + k] = clean(vel[s + 512 * (size_t)L.nb * k]);
+            obst_arr[o] = L.obstacle[s] ? 1 : 0;
+        }
+    }
+    return LUDWIG_OK;
+}
+
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n, const float* cx, const float* cy, const float* cz, const float* nx,
                        const float* ny, const float* nz, const float* area, ludwig_mesh** out) {
     if (!ctx || n <= 0 || !out) return fail(ctx, LUDWIG_EINVAL, "bad mesh");
