@@ -665,6 +665,8 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < 3; ++i) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+    for (cudaStream_t st : {ctx->pre_stream, ctx->halo_stream}) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : {ctx->ev_pre_fork, ctx->ev_pre, ctx->ev_halo, ctx->ev_halo_fork}) if (e) cudaEventDestroy(e);
     delete ctx;
     return LUDWIG_OK;
 }
