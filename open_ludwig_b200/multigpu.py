@@ -1,8 +1,9 @@
 """One-process-per-GPU plumbing around the C ABI's multi-GPU entry points (include/ludwig_b200.h, "multi-GPU").
 
-torch.distributed is used for plumbing only: the all-gather of the CUDA-IPC handles, the stream-ordered cross-rank
-barrier the library calls after every level step, and the final reductions of partial statistics / forces.  The data
-path itself has no collective: K1 pulls remote neighbour blocks through NVLink peer mappings inside the kernel.
+torch.distributed is used for plumbing only: the all-gather of the CUDA-IPC handles and the final reductions of partial
+statistics / forces.  The data path itself has no collective: K1 pulls remote neighbour blocks through NVLink peer
+mappings inside the kernel, and the cross-rank barrier after every level step is the library's own peer-flag kernel
+(an NCCL all-reduce can be registered instead for A/B runs).
 """
 from __future__ import annotations
 
