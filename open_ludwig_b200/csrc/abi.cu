@@ -228,7 +228,30 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         for (int d = 0; d < 27; ++d) if (nbrf[(size_t)b * 27 + d] >= REMOTE_BASE) return true;
         return false;
     };
-    L.n_plain_int = (int)(std::stable_partition(lp.begin(), lp.end(), [&](int32_t b) { return !has_remote(b); }) - lp.begin());
+    // Order of the plain list in a multi-GPU run.  Packed-mirror mode needs "interior first" (n_plain_int).  With direct NVLink
+    // pulls the default stays the Morton order (the configuration measured on 8 GPUs); LUDWIG_REMOTE_ORDER = first | last |
+    // interleave moves / spreads the blocks that pull from a peer (unmeasured experiments: where do their longer load
+    // latencies hide best?).
+    const char* ro = getenv("LUDWIG_REMOTE_ORDER");
+    const std::string order = ctx->use_mirror ? "last" : (ro ? ro : "morton");
+    L.n_plain_int = 0;
+    if (ctx->world > 1 && order != "morton") {
+        auto mid = std::stable_partition(lp.begin(), lp.end(), [&](int32_t b) { return !has_remote(b); });
+        const size_t ni = (size_t)(mid - lp.begin()), nbd = lp.size() - ni;
+        L.n_plain_int = (int)ni;
+        if (order == "first") std::rotate(lp.begin(), mid, lp.end());
+        else if (order == "interleave" && nbd > 0 && ni > 0) {
+            std::vector<int32_t> in(lp.begin(), mid), bd(mid, lp.end()), out;
+            out.reserve(lp.size());
+            size_t a = 0, c = 0;
+            for (size_t j = 0; j < lp.size(); ++j) {   // boundary block whenever its share of the list falls behind
+                if (c < nbd && (a >= ni || c * lp.size() < (j + 1) * nbd)) out.push_back(bd[c++]);
+                else out.push_back(in[a++]);
+            }
+            lp.swap(out);
+        }
+        if (order != "last") L.n_plain_int = 0;   // only the mirror mode splits the launch
+    }
     L.n_ghost = ng; L.n_gcell = (int)gcell.size();
     L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_feat = (int)le.size(); L.n_full = (int)lf.size();
     CU(dalloc(ctx, &L.d_nbr_fast, nbrf.size()));
