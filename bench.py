@@ -264,9 +264,9 @@ def run_ours(args, rank, local_rank, world):
                                    "level, inlet/outlet x + periodic y/z, regularized-BGK + WALE (c_wale 0.5, nu_bg 5e-4, inlet turbulence 0.01)",
                        "blocks_per_gpu": len(loc), "cells_per_gpu": cells_per_rank, "fp_mode": "strict" if args.strict else "fast",
                        "l2": f"working set {ctx.device_bytes() / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "multi_gpu": ("Morton-range block partition; remote halo layers imported over NVLink peer mappings (CUDA IPC) by a "
-                                     "copy kernel overlapped with the interior blocks' K1; one stream-ordered peer-flag barrier kernel "
-                                     "per step (no NCCL on the data path)") if world > 1 else "single GPU"},
+                       "multi_gpu": ("Morton-range block partition; K1 pulls the remote halo layers over NVLink peer mappings (CUDA IPC) "
+                                     "inside the stream-collide kernel; one stream-ordered peer-flag barrier kernel per step "
+                                     "(no NCCL on the data path)") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": TRAFFIC_BYTES_PER_LU * k_cells / max(k_launches, 1) if k_launches else None,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per LU (profiles/r1c_dram_traffic_k1_256cube.csv) x LU per launch",
