@@ -137,6 +137,15 @@ end
 
 sync(ctx::Context) = check(ctx, ccall((:ludwig_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h), "ludwig_sync")
 
+# io_vtk.jl:52-58,100-111 for one level: fills the slices of rho_arr / vel_mat / obst_arr that belong to the level's valid blocks
+# (b_idx list of io_vtk.jl:27-45, in the order they appear in valid_blocks) without downloading whole arrays.
+function output_gather!(ctx::Context, level::Integer, t_step::Integer, b_idx::Vector{Int32},
+                        rho_arr::AbstractVector{Float32}, vel_mat::AbstractMatrix{Float32}, obst_arr::AbstractVector{UInt8})
+    GC.@preserve b_idx rho_arr vel_mat obst_arr check(ctx, ccall((:ludwig_output_gather, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{Int32}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+        ctx.h, level, t_step, pointer(b_idx), length(b_idx), pointer(rho_arr), pointer(vel_mat), pointer(obst_arr)), "ludwig_output_gather")
+end
+
 # ---- more than one GPU: one process per GPU (INTEGRATION.md "More than one GPU") -----------------------------------
 # call right after Context(local_rank), before the first add_level!
 set_partition!(ctx::Context, rank::Integer, world::Integer) =
