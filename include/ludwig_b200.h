@@ -210,6 +210,10 @@ int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* 
 /* Relative cost of every block (reference order) by the kernel class it will run in; ludwig_level_create cuts the
  * Morton curve into `world` ranges of equal cost (host code, callable without a GPU). */
 int ludwig_block_costs(const ludwig_level_desc* desc, float* cost /* [n_blocks] */);
+/* Recursive coordinate bisection of one level into `world` compact boxes of equal cost (host code, callable without a GPU):
+ * owner[b] for every block in reference order.  ludwig_level_create uses it instead of the Morton ranges when the
+ * environment has LUDWIG_PARTITION=rcb (experiment: 2-3x less halo surface on the 339 M-cell bunny). */
+int ludwig_partition_rcb(const ludwig_level_desc* desc, int32_t world, int32_t* owner /* [n_blocks] */);
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
 /* Optional, multi-level cases: a spatially aligned plan.  ludwig_partition_plan (host code) takes the descriptors of ALL
  * levels and returns world+1 cut keys on the Morton axis of the finest level such that every interval carries the same

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_partition_starts", "ludwig_block_costs", "ludwig_ctx_set_partition", "ludwig_partition_plan",
     "ludwig_ctx_set_partition_keys", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
-    "ludwig_attach_inprocess", "ludwig_profile_levels", "ludwig_output_gather",
+    "ludwig_attach_inprocess", "ludwig_profile_levels", "ludwig_output_gather", "ludwig_partition_rcb",
 )
 
 BARRIER_CB = C.CFUNCTYPE(None, C.c_void_p)
@@ -120,6 +120,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_attach_inprocess": (C.c_int, [vp, C.POINTER(vp), i32]),
         "ludwig_profile_levels": (C.c_int, [vp, C.POINTER(f64), i32]),
         "ludwig_output_gather": (C.c_int, [vp, i32, i64, vp, i32, vp, vp, vp]),
+        "ludwig_partition_rcb": (C.c_int, [C.POINTER(LevelDesc), i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol

@@ -666,6 +666,7 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
     // 2 and 8 B200 (profiles/README.md, "halo strategies"): the extra kernels sit on the critical path of every level
     // step while the in-kernel pulls hide behind the other CTAs of an HBM-bound kernel.
     ctx->use_mirror = getenv("LUDWIG_HALO_MIRROR") != nullptr;
+    if (const char* pm = getenv("LUDWIG_PARTITION")) ctx->rcb = std::string(pm) == "rcb";
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -776,9 +777,20 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
             return fail(ctx, LUDWIG_EINVAL, "block coordinate outside block_pointer extents");
         key[i] = morton3((uint32_t)(bx - 1), (uint32_t)(by - 1), (uint32_t)(bz - 1));
     }
+    // LUDWIG_PARTITION=rcb (experiment): recursive coordinate bisection of THIS level's blocks into `world` compact boxes of
+    // equal cost (ludwig_partition_rcb).  The internal order becomes (owner, Morton key), so every rank still owns one
+    // contiguous range and walks its blocks along the Morton curve; nothing else in the library depends on how the ranges
+    // were chosen.  On the 339 M-cell bunny the Morton ranges have 2-3x the halo surface of RCB boxes.
+    std::vector<int32_t> rcb_owner;
+    if (ctx->world > 1 && ctx->rcb) {
+        rcb_owner.resize(nbg);
+        if (ludwig_partition_rcb(d, ctx->world, rcb_owner.data()) != LUDWIG_OK) return fail(ctx, LUDWIG_EINVAL, "rcb partition failed (fewer blocks than ranks?)");
+    }
     L.int2ref.resize(nbg);
     std::iota(L.int2ref.begin(), L.int2ref.end(), 0);
-    std::sort(L.int2ref.begin(), L.int2ref.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    if (rcb_owner.empty()) std::sort(L.int2ref.begin(), L.int2ref.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    else std::sort(L.int2ref.begin(), L.int2ref.end(), [&](int32_t a, int32_t b) {
+            return rcb_owner[a] != rcb_owner[b] ? rcb_owner[a] < rcb_owner[b] : key[a] < key[b]; });
     L.ref2int.resize(nbg);
     for (int i = 0; i < nbg; ++i) L.ref2int[L.int2ref[i]] = i;
 
@@ -786,7 +798,10 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     // follows the kernel class it will run in (measured on Wing_5_deg / bunny: feature blocks ~2x a plain block).
     L.part_starts.assign(ctx->world + 1, 0);
     if (ctx->world == 1) { L.part_starts[1] = nbg; }
-    else if (ctx->has_plan) {
+    else if (!rcb_owner.empty()) {
+        for (int i = 0; i < nbg; ++i) L.part_starts[rcb_owner[i] + 1] += 1;
+        for (int r = 0; r < ctx->world; ++r) L.part_starts[r + 1] += L.part_starts[r];
+    } else if (ctx->has_plan) {
         // spatially aligned cut (ludwig_partition_plan): a block belongs to the rank whose key interval holds its Morton
         // key scaled to the finest level, so parents, children and neighbours of one region live on one GPU
         if (d->level_id > ctx->plan_levels) return fail(ctx, LUDWIG_EINVAL, "level beyond the partition plan");
@@ -1383,6 +1398,49 @@ int ludwig_partition_plan(const ludwig_level_desc* const* descs, int32_t n_level
         while (i < items.size() && acc + items[i].second <= target) { acc += items[i].second; ++i; }
         keys[r] = i < items.size() ? items[i].first : ~0ull;
         if (keys[r] < keys[r - 1]) keys[r] = keys[r - 1];
+    }
+    return LUDWIG_OK;
+}
+
+// Recursive coordinate bisection of one level (host code, no GPU): splits the blocks into `world` boxes of equal cost
+// (ludwig_block_costs), always across the longest axis of the current box, at the cost-weighted median; ties along the axis
+// are ordered by Morton key, so the result is deterministic and identical on every rank.  owner[b] in reference order.
+int ludwig_partition_rcb(const ludwig_level_desc* d, int32_t world, int32_t* owner) {
+    if (!d || !owner || world < 1 || world > MAX_RANKS || d->n_blocks < world) return LUDWIG_EINVAL;
+    const int nb = d->n_blocks;
+    std::vector<float> cost(nb);
+    int rc = ludwig_block_costs(d, cost.data());
+    if (rc) return rc;
+    std::vector<uint64_t> key(nb);
+    for (int b = 0; b < nb; ++b) key[b] = morton3((uint32_t)(d->map_x[b] - 1), (uint32_t)(d->map_y[b] - 1), (uint32_t)(d->map_z[b] - 1));
+    const int32_t* coord[3] = {d->map_x, d->map_y, d->map_z};
+    std::vector<int32_t> idx(nb);
+    std::iota(idx.begin(), idx.end(), 0);
+    struct Node { int lo, hi, first, n; };   // blocks idx[lo, hi) go to ranks [first, first + n)
+    std::vector<Node> stack{{0, nb, 0, world}};
+    while (!stack.empty()) {
+        const Node nd = stack.back();
+        stack.pop_back();
+        if (nd.n == 1) { for (int i = nd.lo; i < nd.hi; ++i) owner[idx[i]] = nd.first; continue; }
+        int axis = 0, best = -1;
+        for (int a = 0; a < 3; ++a) {
+            int mn = INT32_MAX, mx = INT32_MIN;
+            for (int i = nd.lo; i < nd.hi; ++i) { mn = std::min(mn, coord[a][idx[i]]); mx = std::max(mx, coord[a][idx[i]]); }
+            if (mx - mn > best) { best = mx - mn; axis = a; }
+        }
+        const int32_t* ca = coord[axis];
+        std::sort(idx.begin() + nd.lo, idx.begin() + nd.hi, [&](int32_t x, int32_t y) { return ca[x] != ca[y] ? ca[x] < ca[y] : key[x] < key[y]; });
+        const int n_left = nd.n / 2, n_right = nd.n - n_left;
+        double total = 0;
+        for (int i = nd.lo; i < nd.hi; ++i) total += cost[idx[i]];
+        const double target = total * n_left / nd.n;
+        double acc = 0;
+        int cut = nd.lo;
+        while (cut < nd.hi && acc + 0.5 * cost[idx[cut]] < target) acc += cost[idx[cut++]];   // nearest prefix to the target
+        cut = std::max(cut, nd.lo + n_left);            // every rank gets at least one block
+        cut = std::min(cut, nd.hi - n_right);
+        stack.push_back({nd.lo, cut, nd.first, n_left});
+        stack.push_back({cut, nd.hi, nd.first + n_left, n_right});
     }
     return LUDWIG_OK;
 }

@@ -185,6 +185,7 @@ struct ludwig_ctx {
     cudaStream_t halo_stream = nullptr;      // halo import (multi-GPU), concurrent with the K1 launch over interior blocks
     cudaEvent_t ev_halo = nullptr, ev_halo_fork = nullptr;
     bool use_mirror = false;
+    bool rcb = false;                        // LUDWIG_PARTITION=rcb: per-level recursive coordinate bisection instead of Morton ranges
     bool fork_full = false;                  // LUDWIG_FORK_FULL: domain-face K1 launch concurrent with the plain launch on large levels
     int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
     std::vector<ludwig::Level*> levels;

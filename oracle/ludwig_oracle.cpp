@@ -888,6 +888,7 @@ int64_t ludwig_launch_count(const ludwig_ctx*) { return 0; }
 int ludwig_profile_enable(ludwig_ctx*, int32_t) { return LUDWIG_OK; }
 int ludwig_profile_classes(ludwig_ctx*, double out[8]) { for (int i = 0; i < 8; ++i) out[i] = 0; return LUDWIG_OK; }
 int ludwig_profile_levels(ludwig_ctx*, double* out, int32_t capacity) { for (int i = 0; i < capacity; ++i) out[i] = 0; return LUDWIG_OK; }
+int ludwig_partition_rcb(const ludwig_level_desc*, int32_t, int32_t*) { return LUDWIG_EINVAL; }   // multi-GPU only: not part of the oracle
 int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const*, int32_t) { return fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank"); }
 int ludwig_profile_read(ludwig_ctx*, double* ms, int64_t* n, int64_t* c) { if (ms) *ms = 0; if (n) *n = 0; if (c) *c = 0; return LUDWIG_OK; }
 

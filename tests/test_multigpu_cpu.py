@@ -14,6 +14,7 @@ import torch.multiprocessing as mp
 
 from open_ludwig_b200 import cabi, partition
 from open_ludwig_b200.host import synthetic as syn
+from open_ludwig_b200.host.cases import have_case
 
 PORT = 29631
 
@@ -119,3 +120,47 @@ def _worker(rank, world, tmp):
 
 def test_two_rank_gloo_plumbing(oracle_lib):
     mp.spawn(_worker, args=(2, {"oracle": oracle_lib}), nprocs=2, join=True)
+
+
+def _remote_pairs(lv, own, world):
+    """(block, direction) pairs whose neighbour belongs to another rank, per rank — the halo surface of a partition"""
+    nt = np.asarray(lv.neighbor_table)
+    faces = np.zeros(world, np.int64)
+    for d in range(27):
+        has = nt[d] > 0
+        a, b = own[has], own[nt[d][has] - 1]
+        np.add.at(faces, a[a != b], 1)
+    return faces
+
+
+@pytest.mark.skipif(not have_case("ball1m"), reason="case folder not available")
+def test_rcb_partition_is_balanced_compact_and_deterministic(cuda_lib):
+    """ludwig_partition_rcb (host code, no GPU): equal cost per rank, every rank non-empty, same answer twice, and a smaller
+    halo surface than the Morton-range cut on a real refined level (shipped ball1m, finest level: a shell around the sphere)."""
+    import ctypes as C
+    from open_ludwig_b200 import cabi
+    from open_ludwig_b200.host import domain as D
+    from open_ludwig_b200.host.cases import CASE_OVERRIDES, case_dir
+    lib = cabi.load_library(cuda_lib)
+    case, ov = CASE_OVERRIDES["sphere_re10m"]
+    dom = D.load_case(case_dir(case), ov, build_tri_map=False)
+    for world in (2, 3, 8):
+        for lv in dom.levels[1:]:
+            d, keep = cabi.Context.make_desc(lv)
+            own = np.full(lv.n_blocks, -1, np.int32); own2 = own.copy()
+            assert lib.ludwig_partition_rcb(C.byref(d), world, own.ctypes.data_as(C.c_void_p)) == 0
+            assert lib.ludwig_partition_rcb(C.byref(d), world, own2.ctypes.data_as(C.c_void_p)) == 0
+            assert np.array_equal(own, own2) and own.min() == 0 and own.max() == world - 1
+            cost = partition.block_costs(lv).astype(np.float64)
+            per = np.bincount(own, weights=cost, minlength=world)
+            assert per.min() > 0 and per.max() - per.min() <= 0.02 * per.mean() + 2 * cost.max(), (world, lv.level_id, per)
+    lv = dom.levels[-1]
+    d, keep = cabi.Context.make_desc(lv)
+    own = np.empty(lv.n_blocks, np.int32)
+    assert lib.ludwig_partition_rcb(C.byref(d), 8, own.ctypes.data_as(C.c_void_p)) == 0
+    morton = partition.owner_of_ref(lv.active_block_coords, 8, level=lv)
+    assert _remote_pairs(lv, own, 8).max() < _remote_pairs(lv, morton, 8).max()
+    own_bad = np.empty(3, np.int32)
+    small = syn.make_box_level(1, 1, 2)
+    d2, keep2 = cabi.Context.make_desc(small)
+    assert lib.ludwig_partition_rcb(C.byref(d2), 4, own_bad.ctypes.data_as(C.c_void_p)) != 0      # fewer blocks than ranks

@@ -53,8 +53,10 @@ def run_two_level(partitioned, steps=10, plan=False):
     levels = T.build_case()
     cells = tuple(8 * d for d in T.DIMS)
     p = default_params(cells, strict=0, wall_model_active=1, use_temporal=1, inlet_turbulence=0.02)
+    if plan == "rcb": os.environ["LUDWIG_PARTITION"] = "rcb"     # read at context creation
     ctx = mg.init_context(None, lr) if partitioned else cabi.Context(device=lr)
-    if partitioned and plan:
+    os.environ.pop("LUDWIG_PARTITION", None)
+    if partitioned and plan is True:
         ctx.set_partition_plan(levels)
     for lv in levels:
         ctx.add_level(lv)
@@ -86,7 +88,7 @@ for barrier in ("native", "nccl", "native-mirror"):   # peer-flag barrier kernel
         if rank == 0: print(f"box barrier={barrier} {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
 if rank == 0: print("box stats", sref["n_fluid"] == sgot["n_fluid"], abs(sref["rho_mean"] - sgot["rho_mean"]) < 1e-12, sref["rho_min"] == sgot["rho_min"], flush=True)
 ref, aref = run_two_level(False)
-for plan in (False, True):       # per-level cost-weighted cut, and the spatially aligned plan over all levels
+for plan in (False, True, "rcb"):   # per-level cost-weighted Morton cut, the spatially aligned plan, per-level RCB boxes
     got, agot = run_two_level(True, plan=plan)
     for k in ref:
         same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
