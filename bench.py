@@ -4,6 +4,10 @@
   python bench.py --gpus N --steps K --warmup W            (ours: libludwig_b200.so through its C ABI)
   python bench.py --impl reference --gpus N --steps K --warmup W   (restated reference CPU path, host cores)
 
+Besides the contract line's weak-scaling `value` (512^3 per GPU) the line carries `strong`: BASELINE config 5 (the Stanford
+bunny at surface_resolution 1300, 6 levels, 339 M cells, 9.4 G cell updates per coarse step) stepped on the same N GPUs —
+ms per coarse step, true MLUPS, Cd / Cl after the (shortened) ramp and rank 0's per-level, per-kernel-class device times.
+
 A "step" is one coarse time step of the whole hot path (K1 on every block of the level; the synthetic box has
 no Bouzidi cells or refinement) over a 512^3 single-level box with open x faces and periodic y/z — the
 configuration BASELINE.json's metric is quoted on.  Multi-GPU (N>1): one process per GPU, weak scaling: the box grows
@@ -28,9 +32,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BYTES_PER_LU = 216  # 27 x 4 B read + 27 x 4 B write
-# dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<PLAIN> per lattice update, from the ncu capture
-# profiles/r1c_dram_traffic_k1_256cube.csv: (2 090 983 680 + 1 903 583 488) B / (30 720 blocks x 512 cells)
-TRAFFIC_BYTES_PER_LU = (2090983680 + 1903583488) / (30720 * 512)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per lattice update, from ncu captures under profiles/
+TRAFFIC_BYTES_PER_LU = {"fast": (2090983680 + 1903583488) / (30720 * 512), "strict": None}
+TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum per LU (profiles/r1c_dram_traffic_k1_256cube.csv) x LU per launch",
+                  "strict": None}
+DEFAULT_FP_MODE = "fast"
+DEFAULT_STRONG_PARTITION = "plan"
+# 1-GPU time per coarse step of the strong-scaling case measured by this file's own strong record (profiles/), for the
+# efficiency shown at N > 1: (case, fp_mode) -> ms
+T1_MS_COMMITTED = {("bunny_fine", "fast"): 496.8}
 
 
 def measured_peaks():
@@ -105,19 +115,36 @@ def make_params(cabi, n_cells_axis, strict):
                        domain_nz=n_cells_axis, strict_fp=strict)
 
 
+WORKLOAD = ("synthetic uniform {n}^3 D3Q27 box per GPU ({nx}x{n}x{n} in total), single refinement level, inlet/outlet x + periodic y/z, "
+            "regularized-BGK + WALE (c_wale 0.5, nu_bg 5e-4, inlet turbulence 0.01), hashed-noise initial state")
+
+
+def omp_threads(n=None):
+    """Sets (n given) and returns the OpenMP thread count the oracle library will really use.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers; libgomp reads that when it is loaded, so the count is set at run time instead."""
+    import ctypes
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+    except OSError:
+        return 1
+    if n:
+        gomp.omp_set_num_threads(int(n))
+    return int(gomp.omp_get_max_threads())
+
+
 def cpu_leg(nb: int, steps: int, warmup: int):
     """Times the restated reference CPU path (oracle/, C++/OpenMP, -ffp-contract=off) on an nb^3-block box of
-    the same recipe.  Returns (mlups, cores, sample description, ms_per_step)."""
+    the same recipe with every host thread.  Returns (mlups, threads, sample description, ms_per_step)."""
     from open_ludwig_b200 import cabi
     from open_ludwig_b200.host import synthetic as syn
     lib = os.path.join(ROOT, "oracle", "_build", "libludwig_oracle.so")
     if not os.path.exists(lib):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-    cores = os.cpu_count() or 1
     lv = syn.make_box_level(nb, nb, nb)
     f, rho, vel = syn.noise_state(lv)
     p = make_params(cabi, nb * 8, 1)
-    with cabi.Context(lib) as c:
+    with cabi.Context(lib) as c:                 # loads the oracle (and libgomp) ...
+        threads = omp_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())   # ... then size its team
         c.add_level(lv)
         for w, a in ((cabi.F, f), (cabi.F_TEMP, f), (cabi.VEL, vel), (cabi.VEL_TEMP, vel), (cabi.RHO, rho)):
             c.upload(0, w, a)
@@ -126,20 +153,23 @@ def cpu_leg(nb: int, steps: int, warmup: int):
         c.step_batch(1 + warmup, steps, 0.03, p)
         dt = time.perf_counter() - t0
     mlups = lv.n_cells * steps / dt / 1e6
-    return mlups, cores, f"{nb * 8}^3 box ({lv.n_cells / 1e6:.2f} M cells), same recipe, {steps} steps, OpenMP {cores} threads", dt / steps * 1e3
+    return mlups, threads, (f"{nb * 8}^3 box ({lv.n_cells / 1e6:.2f} M cells, {lv.n_cells * 27 * 8 / 1e9:.1f} GB of populations: out of cache), same recipe, "
+                            f"{steps} steps, OpenMP {threads} threads"), dt / steps * 1e3
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     nb = args.cpu_nb
-    mlups, cores, sample, ms = cpu_leg(nb, args.steps, args.warmup)
+    steps = min(args.steps, args.cpu_max_steps)      # each step is a bounded sample: the whole run must end within minutes
+    mlups, threads, sample, ms = cpu_leg(nb, steps, min(args.warmup, 2))
     line = {
         "impl": "reference", "metric": "MLUPS (D3Q27 FP32)", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic uniform D3Q27 box, single level, inlet/outlet x + periodic y/z (bounded sample {nb * 8}^3 of the 512^3 workload)"},
-        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD.format(n=args.nb * 8, nx=args.nb * 8 * args.gpus),
+                   "sample": f"bounded sample of that workload: {nb * 8}^3 cells per step on the host cores"},
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference CPU path (C++/OpenMP oracle, -ffp-contract=off); Julia/KernelAbstractions is not installed in this image",
     }
@@ -163,10 +193,12 @@ def run_ours(args, rank, local_rank, world):
     # Morton-range partition gives every rank one 64^3 cube (x is the most significant Morton digit here).
     nb = args.nb
     ncell_axis = nb * 8
+    strict = int(args.fp_mode == "strict")
     lv = syn.make_box_level(nb * world, nb, nb)
     p = cabi.Params(c_wale=0.5, nu_sgs_bg=0.0005, inlet_turbulence=0.01, q_min_threshold=0.001, wall_model_active=0, use_temporal=0,
-                    sponge_blend=1, symmetric=0, domain_nx=ncell_axis * world, domain_ny=ncell_axis, domain_nz=ncell_axis, strict_fp=args.strict)
-    ctx = cabi.Context(device=local_rank)
+                    sponge_blend=1, symmetric=0, domain_nx=ncell_axis * world, domain_ny=ncell_axis, domain_nz=ncell_axis, strict_fp=strict)
+    opts = dict(kv.split("=", 1) for kv in args.option)
+    ctx = cabi.Context(device=local_rank, options=opts)
     if world > 1:
         ctx.set_partition(rank, world)
     ctx.add_level(lv)
@@ -202,8 +234,7 @@ def run_ours(args, rank, local_rank, world):
     ctx.step_batch(t, args.warmup, 0.03, p); t += args.warmup
     ctx.sync()
 
-    # ---- timed region 1: device-resident throughput (value) + per-kernel timing of the dominant kernel
-    ctx.profile_enable(True)
+    # ---- timed region 1: device-resident throughput (value).  No profiling events inside.
     n0 = ctx.launch_count()
     barrier()
     ev0.record(stream)
@@ -212,15 +243,23 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - n0
+
+    # ---- separate pass: per-launch device time of the dominant kernel (CUDA events on the library's stream around every
+    # launch of the plain-interior K1 kernel)
+    ksteps = min(args.steps, 20)
+    ctx.profile_enable(True)
+    ctx.step_batch(t, ksteps, 0.03, p); t += ksteps
     k_ms, k_launches, k_cells = ctx.profile_read()
+    classes = ctx.profile_classes()
     ctx.profile_enable(False)
 
     # ---- timed region 2: end to end through the C ABI with host buffers: every step passes the host-side
     # params/u_inlet (kernel arguments) and reads the step's flow statistics back to the host.
+    esteps = min(args.steps, 50)
     barrier()
     t0 = time.perf_counter()
     stats = None
-    for _ in range(args.steps):
+    for _ in range(esteps):
         ctx.step_batch(t, 1, 0.03, p); t += 1
         stats = ctx.flow_stats(0)          # device reduction + D2H of the per-CTA partials + host reduction (syncs)
         if world > 1:
@@ -229,18 +268,17 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    # ---- timed region 3: the same steps in the STRICT build (reference operation order, no FMA: bit-exact against the
-    # CPU oracle) — reported beside the fast-mode headline, not instead of it
-    strict_ms = None
-    if world == 1 and not args.strict:
-        ps = cabi.Params.from_buffer_copy(bytes(p)); ps.strict_fp = 1
-        ctx.step_batch(t, 2, 0.03, ps); t += 2
+    # ---- timed region 3: the same steps in the OTHER FP mode, reported beside the headline, not instead of it
+    other_ms, osteps = None, min(args.steps, 50)
+    if world == 1 and not args.fast_init:
+        po = cabi.Params.from_buffer_copy(bytes(p)); po.strict_fp = 1 - strict
+        ctx.step_batch(t, 2, 0.03, po); t += 2
         barrier()
         ev0.record(stream)
-        ctx.step_batch(t, args.steps, 0.03, ps); t += args.steps
+        ctx.step_batch(t, osteps, 0.03, po); t += osteps
         ev1.record(stream)
         barrier()
-        strict_ms = ev0.elapsed_time(ev1)
+        other_ms = ev0.elapsed_time(ev1)
 
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     ncell = torch.tensor([cells_per_rank], dtype=torch.float64, device="cuda")
@@ -250,34 +288,62 @@ def run_ours(args, rank, local_rank, world):
     ms_max, e2e_ms_max = float(times[0]), float(times[1])
     total_cells = float(ncell[0])
     mlups = total_cells * args.steps / (ms_max * 1e-3) / 1e6
-    e2e_mlups = total_cells * args.steps / (e2e_ms_max * 1e-3) / 1e6
+    e2e_mlups = total_cells * esteps / (e2e_ms_max * 1e-3) / 1e6
+    dev_gb = ctx.device_bytes() / 1e9
+    if world > 1:
+        dist.barrier()
+    ctx.close()
+    del ctx
+    torch.cuda.empty_cache()
+
+    # ---- strong scaling on BASELINE config 5 (the bunny at surface_resolution 1300, 6 levels, 339 M cells) with the same N GPUs
+    strong = None
+    if args.strong_case != "none":
+        try:
+            strong = mg.run_case_strong(args.strong_case, args.strong_steps, local_rank, strict=bool(strict),
+                                        options={**opts, **({"partition": args.strong_partition} if world > 1 and args.strong_partition != "plan" else {})},
+                                        plan=(world > 1 and args.strong_partition == "plan"), ramp_steps=args.strong_ramp, profile_steps=2,
+                                        log=lambda m: print(m, file=sys.stderr, flush=True))
+            t1 = T1_MS_COMMITTED.get((args.strong_case, "strict" if strict else "fast"))
+            if strong["n_gpus"] == 1:
+                strong["note"] = "T_1 of this run; the driver's SCALE runs give T_N on the same code"
+            elif t1:
+                strong["efficiency_vs_committed_T1"] = t1 / (strong["n_gpus"] * strong["ms_per_coarse_step"])
+                strong["T1_ms_committed"] = t1
+        except Exception as e:   # the headline line must survive a failure of the second workload (missing case files, memory)
+            strong = {"case": args.strong_case, "error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_avg_ms = k_ms / max(k_launches, 1)
         achieved = (k_cells / max(k_launches, 1)) * BYTES_PER_LU / (k_avg_ms * 1e-3) / 1e9 if k_launches else None
         stats_parts = min(4096, max(1, min(148 * 8, (cells_per_rank + 255) // 256)))
+        kname = "k1_strict_kernel<plain>" if strict else "k1_fast_kernel<PLAIN>"
         line = {
             "metric": "MLUPS (D3Q27 FP32)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic uniform {ncell_axis}^3 D3Q27 box per GPU ({ncell_axis * world}x{ncell_axis}x{ncell_axis} in total), single refinement "
-                                   "level, inlet/outlet x + periodic y/z, regularized-BGK + WALE (c_wale 0.5, nu_bg 5e-4, inlet turbulence 0.01)",
-                       "blocks_per_gpu": len(loc), "cells_per_gpu": cells_per_rank, "fp_mode": "strict" if args.strict else "fast",
-                       "l2": f"working set {ctx.device_bytes() / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
+            "config": {"workload": WORKLOAD.format(n=ncell_axis, nx=ncell_axis * world),
+                       "blocks_per_gpu": len(loc), "cells_per_gpu": cells_per_rank, "fp_mode": args.fp_mode,
+                       "parity": ("strict: the reference's FP32 operation order, bit-identical to the CPU oracle (tests/test_parity_1000_steps_gpu.py, "
+                                  "tests/test_large_sizes_gpu.py)") if strict else "fast: FMA contraction + regrouped sums, documented tolerance (DESIGN.md section 3)",
+                       "l2": f"working set {dev_gb:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "multi_gpu": ("Morton-range block partition; K1 pulls the remote halo layers over NVLink peer mappings (CUDA IPC) "
                                      "inside the stream-collide kernel; one stream-ordered peer-flag barrier kernel per step "
                                      "(no NCCL on the data path)") if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": TRAFFIC_BYTES_PER_LU * k_cells / max(k_launches, 1) if k_launches else None,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per LU (profiles/r1c_dram_traffic_k1_256cube.csv) x LU per launch",
-                         "peak_source": peak_src, "kernel": "k1_fast_kernel<PLAIN> (rank 0)", "kernel_ms": k_avg_ms,
+                         "traffic": TRAFFIC_BYTES_PER_LU[args.fp_mode] * k_cells / max(k_launches, 1) if k_launches and TRAFFIC_BYTES_PER_LU.get(args.fp_mode) else None,
+                         "traffic_source": TRAFFIC_SOURCE.get(args.fp_mode),
+                         "peak_source": peak_src, "kernel": f"{kname} (rank 0)", "kernel_ms": k_avg_ms,
                          "bytes_per_lu": BYTES_PER_LU, "lu_per_launch": k_cells / max(k_launches, 1),
+                         "whole_step_frac": total_cells / world * BYTES_PER_LU / (ms_max / args.steps * 1e-3) / 1e9 / peak,
+                         "class_ms_per_step": {k: v / ksteps for k, v in classes.items() if v},
                          "frac_of_8TBs_nominal": (achieved / 8000.0) if achieved else None},
-            "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": int(64), "d2h_bytes_per_step": int(stats_parts * 48),
+            "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": int(64), "d2h_bytes_per_step": int(stats_parts * 48), "steps": esteps,
                     "what": "ludwig_step_batch(1 step, host params) + ludwig_flow_stats (device reduction, D2H, host sync) every step"},
-            "strict_mode": ({"value": total_cells * args.steps / (strict_ms * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": strict_ms / args.steps,
-                             "what": "same workload with strict_fp = 1: the reference's FP32 operation order without FMA contraction, "
-                                     "bit-exact against the CPU oracle (tests/test_large_sizes_gpu.py)"} if strict_ms else None),
+            ("fast_mode" if strict else "strict_mode"): ({"value": total_cells * osteps / (other_ms * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": other_ms / osteps,
+                             "what": "same workload in the other FP mode (strict_fp = %d)" % (1 - strict)} if other_ms else None),
+            "strong": strong,
             "gpu_launches": int(launches),
             **({"not_a_bench_value": "--fast-init: rest-state initial condition, profiling run"} if args.fast_init else {}),
             "clocks": clocks,
@@ -290,22 +356,27 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-    ctx.close()
-    if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nb", type=int, default=64, help="blocks per axis (64 -> 512^3 cells)")
-    ap.add_argument("--strict", type=int, default=0, help="1 = parity build (reference operation order, no FMA)")
-    ap.add_argument("--cpu-nb", type=int, default=16, help="blocks per axis of the bounded CPU sample (16 -> 128^3)")
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--fp-mode", default=DEFAULT_FP_MODE, choices=["strict", "fast"],
+                    help="strict = the reference's FP32 operation order (bit-identical to the oracle); fast = FMA + regrouped sums")
+    ap.add_argument("--option", action="append", default=[], help="library option key=value (ludwig_ctx_set_option); repeatable")
+    ap.add_argument("--cpu-nb", type=int, default=32, help="blocks per axis of the bounded CPU sample (32 -> 256^3)")
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--cpu-max-steps", type=int, default=24, help="cap on the steps of the reference arm (each ~0.4 s)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong-case", default="bunny_fine", help="case of the strong-scaling record (BASELINE config 5); 'none' skips it")
+    ap.add_argument("--strong-steps", type=int, default=24)
+    ap.add_argument("--strong-ramp", type=int, default=16, help="ramp length for the strong record, so that Cd is O(1) after a few coarse steps")
+    ap.add_argument("--strong-partition", default=DEFAULT_STRONG_PARTITION, choices=["plan", "morton", "rcb", "rcb_yz"])
     ap.add_argument("--fast-init", action="store_true", help="device-side rest-state initialisation instead of the hashed noise "
                     "state of config 2 (for ncu captures; the line is marked and is not a bench value)")
     args = ap.parse_args()

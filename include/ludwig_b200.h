@@ -104,6 +104,20 @@ enum {
 int ludwig_ctx_create(ludwig_ctx** out, int device);
 /* main.jl:247-248 (grids = nothing; force_cleanup()) */
 int ludwig_ctx_destroy(ludwig_ctx* ctx);
+/* Behaviour switches without a reference counterpart (the reference has one device and one kernel per step).  The library
+ * reads NO environment variable; everything that changes what runs is set here, key / value as strings:
+ *   prepass = thread | block          interface pre-pass variant (identical bits)
+ *   serial_prepass = 0 | 1            pre-pass on the main stream instead of beside the plain K1 launch
+ *   single_stream = 0 | 1             no concurrent launches at all
+ *   fork_full = 0 | 1                 domain-face K1 launch beside the plain launch on large levels
+ *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default 40000)
+ *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
+ *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)
+ *   halo_mirror = 0 | 1               packed halo exchange into local mirrors instead of in-kernel NVLink pulls (before the first level)
+ *   remote_order = morton | first | last | interleave   place of the blocks that pull from a peer in the plain launch
+ *   barrier_timeout_s = seconds       time-out of the native cross-GPU barrier (default 20)
+ *   verbose = 0 | 1                   per-level table sizes on stderr */
+int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value);
 const char* ludwig_last_error(const ludwig_ctx* ctx);
 /* "cuda-sm100a" for the product library, "cpu-oracle" for the test oracle. */
 const char* ludwig_backend_name(void);
@@ -202,18 +216,21 @@ int64_t ludwig_device_bytes(const ludwig_ctx* ctx);
  * remote parents / cells the same way.  The only collective the data path needs is a cross-rank barrier after every
  * level step.  By default the library runs it itself: a one-warp kernel on the context's stream stores this rank's epoch
  * into every peer's flag slots over NVLink and spins on its own slots (stream-ordered, no host round trip, no NCCL; a
- * ~20 s time-out is reported by ludwig_sync).  ludwig_set_barrier_callback replaces it with a caller-supplied barrier
+ * time-out is sticky and fatal, see ludwig_set_barrier_callback).  ludwig_set_barrier_callback replaces it with a caller-supplied barrier
  * (e.g. a stream-ordered NCCL all-reduce).  ludwig_flow_stats and
  * ludwig_compute_aerodynamics return the calling rank's PARTIAL result (triangles dealt round-robin); all 18
- * aerodynamic outputs are linear in the partial sums, so the caller adds them over the ranks.  Fast mode only. */
+ * aerodynamic outputs are linear in the partial sums, so the caller adds them over the ranks.  Both FP modes. */
 int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts /* [world+1] or NULL */);  /* equal-count rule */
 /* Relative cost of every block (reference order) by the kernel class it will run in; ludwig_level_create cuts the
  * Morton curve into `world` ranges of equal cost (host code, callable without a GPU). */
 int ludwig_block_costs(const ludwig_level_desc* desc, float* cost /* [n_blocks] */);
 /* Recursive coordinate bisection of one level into `world` compact boxes of equal cost (host code, callable without a GPU):
  * owner[b] for every block in reference order.  ludwig_level_create uses it instead of the Morton ranges when the
- * environment has LUDWIG_PARTITION=rcb (experiment: 2-3x less halo surface on the 339 M-cell bunny). */
+ * option partition = rcb is set (2-3x less halo surface on the 339 M-cell bunny). */
 int ludwig_partition_rcb(const ludwig_level_desc* desc, int32_t world, int32_t* owner /* [n_blocks] */);
+/* The same with a mask of the axes a cut may cross (bit 0 x, 1 y, 2 z).  6 = never cut across x: an x-face halo layer is 64
+ * separate 32-byte sectors per direction in the block layout, so pulling it over NVLink moves 8 bytes per useful byte. */
+int ludwig_partition_rcb_axes(const ludwig_level_desc* desc, int32_t world, int32_t axes, int32_t* owner /* [n_blocks] */);
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
 /* Optional, multi-level cases: a spatially aligned plan.  ludwig_partition_plan (host code) takes the descriptors of ALL
  * levels and returns world+1 cut keys on the Morton axis of the finest level such that every interval carries the same
@@ -221,7 +238,9 @@ int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world);
  * places in space, so a fine block, its parent cells and its neighbours live on one GPU except at the cut surfaces. */
 int ludwig_partition_plan(const ludwig_level_desc* const* descs, int32_t n_levels, int32_t world, uint64_t* keys /* [world+1] */);
 int ludwig_ctx_set_partition_keys(ludwig_ctx* ctx, const uint64_t* keys /* [world+1] */, int32_t n_levels);
-int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user);
+/* fn returns 0 on success; a non-zero return marks the context failed (every later stepping / result call returns
+ * LUDWIG_ESTATE).  A time-out of the native barrier (option barrier_timeout_s) has the same effect. */
+int ludwig_set_barrier_callback(ludwig_ctx* ctx, int (*fn)(void*), void* user);
 /* Reference (1-based) indices of the blocks this rank owns on `level`, in the library's internal order. */
 int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices /* or NULL */);
 /* Upload / download of ONLY this rank's blocks of a state field: Float32[8,8,8,n_local,ncomp] in the order
@@ -233,6 +252,41 @@ int ludwig_ipc_attach(ludwig_ctx* ctx, const void* all_handles, int64_t bytes_pe
 /* The same attach for contexts that live in ONE process (a single host thread driving several GPUs, or several virtual
  * ranks on one GPU for profiling): peers[r] = the context of rank r, peers[rank] == ctx.  No IPC handles involved. */
 int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const* peers, int32_t n_peers);
+
+/* -- multi-GPU: ONE process, one host thread ("Multi-GPU is hidden behind ludwig_ctx_create(n_gpus,
+ * device_ids); level creation takes the global tables and the library partitions") ------------------------------------
+ *
+ * A ludwig_multi owns one context per rank (devices[r] = CUDA ordinal of rank r; ordinals may repeat: several virtual ranks
+ * on one GPU, which is how the partitioned path is tested on a one-GPU box), partitions every level like the per-process
+ * path, attaches the ranks in-process and steps them in lock-step from the calling thread.  Cross-rank barriers are
+ * stream-ordered event waits.  The kept single-process Julia driver (main.jl:54-249) makes the same sequence of calls as
+ * for one GPU: create, level_create x L, init_equilibrium, step_batch, flow_stats / compute_aerodynamics, destroy.
+ * Results are bit-identical to the single-context run in both FP modes. */
+typedef struct ludwig_multi ludwig_multi;
+int ludwig_multi_create(ludwig_multi** out, int32_t n_ranks, const int32_t* devices /* [n_ranks] or NULL = 0..n-1 */);
+int ludwig_multi_destroy(ludwig_multi* m);
+const char* ludwig_multi_last_error(const ludwig_multi* m);
+int32_t ludwig_multi_num_ranks(const ludwig_multi* m);
+/* The context of one rank, for the per-rank calls (ludwig_level_local_blocks, ludwig_level_upload_local, profiling ...). */
+ludwig_ctx* ludwig_multi_ctx(ludwig_multi* m, int32_t rank);
+int ludwig_multi_set_option(ludwig_multi* m, const char* key, const char* value);                 /* every rank */
+int ludwig_multi_set_partition_plan(ludwig_multi* m, const ludwig_level_desc* const* descs, int32_t n_levels);  /* optional, before the levels */
+int ludwig_multi_level_create(ludwig_multi* m, const ludwig_level_desc* desc, int32_t* out_index);               /* main.jl:98 */
+int ludwig_multi_level_upload(ludwig_multi* m, int32_t level, int32_t which, const void* src);     /* whole level, reference layout */
+int ludwig_multi_level_download(ludwig_multi* m, int32_t level, int32_t which, void* dst);         /* io_vtk.jl:55-57 */
+int ludwig_multi_init_equilibrium(ludwig_multi* m);                                                /* main.jl:109-135 */
+int ludwig_multi_step_batch(ludwig_multi* m, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params);  /* solver_control.jl:145-165 */
+int ludwig_multi_sync(ludwig_multi* m);
+int ludwig_multi_flow_stats(ludwig_multi* m, int32_t level, double out[6]);                        /* main.jl:186, reduced over the ranks */
+/* main.jl:101,145: mesh + ForceData on every rank; *out_handle identifies them in the two calls below. */
+int ludwig_multi_forces_create(ludwig_multi* m, int32_t n_triangles, const float* cx, const float* cy, const float* cz,
+                               const float* nx, const float* ny, const float* nz, const float* area,
+                               double rho_ref, double u_ref, double area_ref, double chord_ref,
+                               const double moment_center[3], int32_t symmetric, int32_t* out_handle);
+int ludwig_multi_compute_aerodynamics(ludwig_multi* m, int32_t handle, int32_t level, const double mesh_offset[3],
+                                      double velocity_scale, double rho_phys, int32_t search_radius, double out[18]);   /* main.jl:197,223 */
+int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p, float* sx, float* sy, float* sz);
+int64_t ludwig_multi_device_bytes(const ludwig_multi* m);
 
 /* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */
 

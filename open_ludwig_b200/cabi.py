@@ -35,9 +35,15 @@ EXPORTED_SYMBOLS = (
     "ludwig_ctx_set_partition_keys", "ludwig_set_barrier_callback", "ludwig_level_local_blocks",
     "ludwig_ipc_export", "ludwig_ipc_attach", "ludwig_level_upload_local", "ludwig_level_download_local",
     "ludwig_attach_inprocess", "ludwig_profile_levels", "ludwig_output_gather", "ludwig_partition_rcb",
+    "ludwig_partition_rcb_axes", "ludwig_ctx_set_option",
+    "ludwig_multi_create", "ludwig_multi_destroy", "ludwig_multi_last_error", "ludwig_multi_num_ranks", "ludwig_multi_ctx",
+    "ludwig_multi_set_option", "ludwig_multi_set_partition_plan", "ludwig_multi_level_create", "ludwig_multi_level_upload",
+    "ludwig_multi_level_download", "ludwig_multi_init_equilibrium", "ludwig_multi_step_batch", "ludwig_multi_sync",
+    "ludwig_multi_flow_stats", "ludwig_multi_forces_create", "ludwig_multi_compute_aerodynamics",
+    "ludwig_multi_forces_download_maps", "ludwig_multi_device_bytes",
 )
 
-BARRIER_CB = C.CFUNCTYPE(None, C.c_void_p)
+BARRIER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)   # returns 0 on success (include/ludwig_b200.h)
 
 
 class LudwigError(RuntimeError):
@@ -121,6 +127,26 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_profile_levels": (C.c_int, [vp, C.POINTER(f64), i32]),
         "ludwig_output_gather": (C.c_int, [vp, i32, i64, vp, i32, vp, vp, vp]),
         "ludwig_partition_rcb": (C.c_int, [C.POINTER(LevelDesc), i32, vp]),
+        "ludwig_partition_rcb_axes": (C.c_int, [C.POINTER(LevelDesc), i32, i32, vp]),
+        "ludwig_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
+        "ludwig_multi_create": (C.c_int, [C.POINTER(vp), i32, vp]),
+        "ludwig_multi_destroy": (C.c_int, [vp]),
+        "ludwig_multi_last_error": (C.c_char_p, [vp]),
+        "ludwig_multi_num_ranks": (i32, [vp]),
+        "ludwig_multi_ctx": (vp, [vp, i32]),
+        "ludwig_multi_set_option": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
+        "ludwig_multi_set_partition_plan": (C.c_int, [vp, vp, i32]),
+        "ludwig_multi_level_create": (C.c_int, [vp, C.POINTER(LevelDesc), C.POINTER(i32)]),
+        "ludwig_multi_level_upload": (C.c_int, [vp, i32, i32, vp]),
+        "ludwig_multi_level_download": (C.c_int, [vp, i32, i32, vp]),
+        "ludwig_multi_init_equilibrium": (C.c_int, [vp]),
+        "ludwig_multi_step_batch": (C.c_int, [vp, i64, i32, f32, C.POINTER(Params)]),
+        "ludwig_multi_sync": (C.c_int, [vp]),
+        "ludwig_multi_flow_stats": (C.c_int, [vp, i32, C.POINTER(f64)]),
+        "ludwig_multi_forces_create": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, C.POINTER(f64), i32, C.POINTER(i32)]),
+        "ludwig_multi_compute_aerodynamics": (C.c_int, [vp, i32, i32, C.POINTER(f64), f64, f64, i32, C.POINTER(f64)]),
+        "ludwig_multi_forces_download_maps": (C.c_int, [vp, i32, vp, vp, vp, vp]),
+        "ludwig_multi_device_bytes": (C.c_int64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -180,12 +206,15 @@ def _as(a, dtype) -> np.ndarray:
 class Context:
     """One solver context = the reference's ``grids`` vector + lattice arrays on one device."""
 
-    def __init__(self, lib_path: Optional[str] = None, device: int = 0):
+    def __init__(self, lib_path: Optional[str] = None, device: int = 0, options: Optional[dict] = None):
         self.lib = load_library(lib_path)
         self._h = C.c_void_p()
         rc = self.lib.ludwig_ctx_create(C.byref(self._h), device)
         if rc != 0:
             raise LudwigError(f"ludwig_ctx_create failed ({rc}): is a CUDA device visible?")
+        self._cb_error: Optional[BaseException] = None
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
         self.n_blocks: list[int] = []
         self.rank, self.world = 0, 1
         self._meshes: list[C.c_void_p] = []
@@ -195,7 +224,16 @@ class Context:
     def _check(self, rc: int, what: str):
         if rc != 0:
             msg = self.lib.ludwig_last_error(self._h)
-            raise LudwigError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+            err = LudwigError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+            if self._cb_error is not None:      # an exception raised inside the barrier callback (ctypes cannot propagate it)
+                raise err from self._cb_error
+            raise err
+
+    def set_option(self, key: str, value):
+        """ludwig_ctx_set_option: every behaviour switch of the library (it reads no environment variable)."""
+        if isinstance(value, bool):
+            value = int(value)
+        self._check(self.lib.ludwig_ctx_set_option(self._h, str(key).encode(), str(value).encode()), f"ludwig_ctx_set_option({key})")
 
     @property
     def backend(self) -> str:
@@ -275,8 +313,17 @@ class Context:
         self.rank, self.world = rank, world
 
     def set_barrier(self, fn):
-        """fn(): cross-rank barrier called by the library after every level step (keep a reference to the thunk)."""
-        self._barrier_thunk = BARRIER_CB(lambda _user: fn())
+        """fn(): cross-rank barrier called by the library after every level step (keep a reference to the thunk).
+        An exception inside fn makes the callback return non-zero: the library marks the context failed and the next
+        call raises LudwigError chained to that exception (ctypes itself would only print and swallow it)."""
+        def thunk(_user):
+            try:
+                fn()
+                return 0
+            except BaseException as e:          # noqa: BLE001 - must not escape into C
+                self._cb_error = e
+                return -1
+        self._barrier_thunk = BARRIER_CB(thunk)
         self._check(self.lib.ludwig_set_barrier_callback(self._h, self._barrier_thunk, None), "ludwig_set_barrier_callback")
 
     def clear_barrier(self):
@@ -445,3 +492,117 @@ class Context:
         out = (C.c_double * 6)()
         self._check(self.lib.ludwig_flow_stats(self._h, level, out), "ludwig_flow_stats")
         return dict(zip(self.STATS_KEYS, list(out)))
+
+
+class MultiContext:
+    """ludwig_multi: N ranks (N GPUs, or N virtual ranks on one GPU) driven by this one thread.  Same call sequence as
+    ``Context`` for what the kept Julia driver does (main.jl:54-249); ``create_forces`` takes the mesh arrays directly."""
+
+    def __init__(self, n_ranks: int, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None, options: Optional[dict] = None):
+        self.lib = load_library(lib_path)
+        self._h = C.c_void_p()
+        dev = None if devices is None else _as(np.asarray(devices), np.int32)
+        rc = self.lib.ludwig_multi_create(C.byref(self._h), n_ranks, _ptr(dev))
+        if rc != 0:
+            raise LudwigError(f"ludwig_multi_create failed ({rc})")
+        self.world = n_ranks
+        self.n_blocks: list[int] = []
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.ludwig_multi_last_error(self._h)
+            raise LudwigError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self.lib.ludwig_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value):
+        if isinstance(value, bool):
+            value = int(value)
+        self._check(self.lib.ludwig_multi_set_option(self._h, str(key).encode(), str(value).encode()), f"ludwig_multi_set_option({key})")
+
+    def rank_ctx(self, rank: int) -> "Context":
+        """A non-owning Context view of one rank (per-rank calls: local_blocks, upload_local, profile_*)."""
+        c = Context.__new__(Context)
+        c.lib, c._h = self.lib, C.c_void_p(self.lib.ludwig_multi_ctx(self._h, rank))
+        c.n_blocks, c.rank, c.world, c._meshes, c._forces, c._cb_error = self.n_blocks, rank, self.world, [], [], None
+        c.close = lambda: None            # the ludwig_multi owns it
+        return c
+
+    def set_partition_plan(self, levels):
+        descs, keeps = zip(*[Context.make_desc(lv) for lv in levels])
+        arr = (C.POINTER(LevelDesc) * len(descs))(*[C.pointer(d) for d in descs])
+        self._check(self.lib.ludwig_multi_set_partition_plan(self._h, arr, len(descs)), "ludwig_multi_set_partition_plan")
+        del keeps
+
+    def add_level(self, lv: BlockLevel) -> int:
+        d, keep = Context.make_desc(lv)
+        idx = C.c_int32(-1)
+        self._check(self.lib.ludwig_multi_level_create(self._h, C.byref(d), C.byref(idx)), "ludwig_multi_level_create")
+        del keep
+        self.n_blocks.append(lv.n_blocks)
+        return idx.value
+
+    def upload(self, level: int, which: int, arr: np.ndarray):
+        a = _as(arr, np.uint8 if which == OBSTACLE else np.float32)
+        assert a.size == self.n_blocks[level] * 512 * _NCOMP[which]
+        self._check(self.lib.ludwig_multi_level_upload(self._h, level, which, _ptr(a)), "ludwig_multi_level_upload")
+
+    def download(self, level: int, which: int) -> np.ndarray:
+        nb, nc = self.n_blocks[level], _NCOMP[which]
+        out = np.empty((nb, 8, 8, 8) if nc == 1 else (nc, nb, 8, 8, 8), dtype=np.uint8 if which == OBSTACLE else np.float32)
+        self._check(self.lib.ludwig_multi_level_download(self._h, level, which, _ptr(out)), "ludwig_multi_level_download")
+        return out
+
+    def init_equilibrium(self):
+        self._check(self.lib.ludwig_multi_init_equilibrium(self._h), "ludwig_multi_init_equilibrium")
+
+    def step_batch(self, t_start: int, batch: int, u_curr: float, params: Params):
+        self._check(self.lib.ludwig_multi_step_batch(self._h, t_start, batch, C.c_float(u_curr), C.byref(params)), "ludwig_multi_step_batch")
+
+    def sync(self):
+        self._check(self.lib.ludwig_multi_sync(self._h), "ludwig_multi_sync")
+
+    def flow_stats(self, level: int = 0) -> dict:
+        out = (C.c_double * 6)()
+        self._check(self.lib.ludwig_multi_flow_stats(self._h, level, out), "ludwig_multi_flow_stats")
+        return dict(zip(Context.STATS_KEYS, list(out)))
+
+    def create_forces(self, centers, normals, areas, rho_ref, u_ref, area_ref, chord_ref, moment_center, symmetric) -> int:
+        arrs = [_as(centers[:, i], np.float32) for i in range(3)] + [_as(normals[:, i], np.float32) for i in range(3)] + [_as(areas, np.float32)]
+        mc = (C.c_double * 3)(*[float(v) for v in moment_center])
+        h = C.c_int32(-1)
+        self._check(self.lib.ludwig_multi_forces_create(self._h, len(areas), *[_ptr(a) for a in arrs], rho_ref, u_ref, area_ref, chord_ref,
+                                                        mc, int(symmetric), C.byref(h)), "ludwig_multi_forces_create")
+        return h.value
+
+    def compute_aerodynamics(self, handle: int, level: int, mesh_offset, velocity_scale: float, rho_phys: float, search_radius: int = 5) -> dict:
+        off = (C.c_double * 3)(*[float(v) for v in mesh_offset])
+        out = (C.c_double * 18)()
+        self._check(self.lib.ludwig_multi_compute_aerodynamics(self._h, handle, level, off, velocity_scale, rho_phys, search_radius, out),
+                    "ludwig_multi_compute_aerodynamics")
+        return dict(zip(Context.AERO_KEYS, list(out)))
+
+    def download_force_maps(self, handle: int, n_triangles: int):
+        maps = [np.empty(n_triangles, np.float32) for _ in range(4)]
+        self._check(self.lib.ludwig_multi_forces_download_maps(self._h, handle, *[_ptr(m) for m in maps]), "ludwig_multi_forces_download_maps")
+        return maps
+
+    def device_bytes(self) -> int:
+        return int(self.lib.ludwig_multi_device_bytes(self._h))

@@ -232,8 +232,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     // pulls the default stays the Morton order (the configuration measured on 8 GPUs); LUDWIG_REMOTE_ORDER = first | last |
     // interleave moves / spreads the blocks that pull from a peer (unmeasured experiments: where do their longer load
     // latencies hide best?).
-    const char* ro = getenv("LUDWIG_REMOTE_ORDER");
-    const std::string order = ctx->use_mirror ? "last" : (ro ? ro : "morton");
+    const std::string order = ctx->use_mirror ? "last" : ctx->remote_order;
     L.n_plain_int = 0;
     if (ctx->world > 1 && order != "morton") {
         auto mid = std::stable_partition(lp.begin(), lp.end(), [&](int32_t b) { return !has_remote(b); });
@@ -280,7 +279,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     CU(cudaStreamSynchronize(ctx->stream));
     L.fast_dom[0] = p.domain_nx; L.fast_dom[1] = p.domain_ny; L.fast_dom[2] = p.domain_nz;
     L.fast_ready = true;
-    if (getenv("LUDWIG_VERBOSE"))
+    if (ctx->verbose)
         fprintf(stderr, "[ludwig rank %d] level %d: %d local blocks (plain %d, plain+ghost %d, feature %d, full %d), %d remote, %d ghost blocks, %d ghost groups\n",
                 ctx->rank, L.level_id, nb, L.n_plain, L.n_plain_g, L.n_feat, L.n_full, L.n_remote, ng, L.n_gcell);
     return LUDWIG_OK;
@@ -312,13 +311,27 @@ int prof_end(ludwig_ctx* ctx, bool active, int64_t cells, cudaStream_t st = null
 
 // Cross-rank barrier after a level step: the registered callback if any, else the native peer-flag kernel.
 // Profiling class 6 = device time spent in barriers (mostly waiting for the slowest rank of that level step).
+// A failed barrier is STICKY and fatal for the context: the peer-flag kernel reports a time-out through a flag in
+// mapped pinned host memory (read here without any synchronisation), a callback through its return value; from then
+// on every stepping / result call returns LUDWIG_ESTATE instead of running kernels on unsynchronised peer memory.
+int barrier_state(ludwig_ctx* ctx) {
+    if (ctx->bar_failed || (ctx->h_bar_err && *(volatile int*)ctx->h_bar_err != 0)) {
+        ctx->bar_failed = true;
+        return fail(ctx, LUDWIG_ESTATE, "cross-GPU barrier failed (time-out: a peer stopped or the ranks issued different call sequences; or the "
+                                        "barrier callback reported an error) - the context's state is no longer consistent");
+    }
+    return LUDWIG_OK;
+}
 int rank_barrier(ludwig_ctx* ctx) {
-    if (ctx->world <= 1) return LUDWIG_OK;
+    if (ctx->world <= 1 || ctx->group_managed) return LUDWIG_OK;   // a ludwig_multi places its own (event) barriers
     int rc;
+    if ((rc = barrier_state(ctx))) return rc;
     if ((rc = prof_begin(ctx, 6, true))) return rc;
-    if (ctx->barrier_cb) ctx->barrier_cb(ctx->barrier_user);
-    else if (ctx->peers_attached && ctx->d_bar)
-        launch_peer_barrier(ctx->peer_bar, ctx->d_bar, ctx->rank, ctx->world, ++ctx->bar_epoch, ctx->d_bar_err, ctx->stream);
+    if (ctx->barrier_cb) {
+        if (ctx->barrier_cb(ctx->barrier_user) != 0) { ctx->bar_failed = true; return barrier_state(ctx); }
+    } else if (ctx->peers_attached && ctx->d_bar)
+        launch_peer_barrier(ctx->peer_bar, ctx->d_bar, ctx->rank, ctx->world, ++ctx->bar_epoch, ctx->d_bar_err, ctx->d_bar_err_dev,
+                            (long long)(ctx->barrier_timeout_s * 1e9), ctx->stream);
     return prof_end(ctx, true, 0);
 }
 
@@ -364,19 +377,22 @@ int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
     return LUDWIG_OK;
 }
 
-// perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2.
-int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p) {
+// perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2, in three phases so that the cross-rank barriers between them can be
+// placed by the caller (one context: rank_barrier; several contexts driven by one thread: an event barrier over the group).
+enum : int { PH_K1 = 1, PH_GATHER = 2, PH_FINISH = 4, PH_ALL = 7 };
+int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p, int phase) {
     const int in = (t_sub % 2 == 0) ? 0 : 1, out = 1 - in;   // solver_control.jl:35-41
     ctx->prof_level = L.level_id - 1;
+    int rho_out = L.rho_cur;
+    if (L.d_rho[1]) rho_out = 1 - L.rho_cur;   // keep the pre-step density for the children
+  if (phase & PH_K1) {
     // class 7: the whole level step on the main stream (its kernels, side-stream joins and barriers)
-    size_t p7 = (size_t)-1;
+    ctx->p7 = (size_t)-1;
     if (ctx->profiling) {
         int rc7 = prof_begin(ctx, 7, true);
         if (rc7) return rc7;
-        p7 = ctx->ev_used; ctx->ev_used += 2;
+        ctx->p7 = ctx->ev_used; ctx->ev_used += 2;
     }
-    int rho_out = L.rho_cur;
-    if (L.d_rho[1]) rho_out = 1 - L.rho_cur;   // keep the pre-step density for the children
     K1Args a{};
     a.f_in = L.d_f[in]; a.f_out = L.d_f[out];
     a.vel_in = L.d_vel[in]; a.vel_out = L.d_vel[out];
@@ -399,30 +415,23 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
     a.use_temporal = p.use_temporal; a.sponge_blend = p.sponge_blend;
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
-    if (ctx->world > 1 && (!ctx->peers_attached || p.strict_fp))
-        return fail(ctx, LUDWIG_ESTATE, !ctx->peers_attached ? "multi-GPU context: call ludwig_ipc_attach before stepping"
-                                                            : "multi-GPU stepping supports fast mode only (strict_fp = 0)");
-    if (p.strict_fp) {
-        // parity build: reference operation order, no FMA.  Plain interior blocks run the packed two-cells-per-thread
-        // kernel (same bits), everything else the generic one-thread-per-cell kernel with in-kernel interpolation.
-        static const bool generic_only = getenv("LUDWIG_STRICT_GENERIC") != nullptr;
-        int rc = generic_only ? LUDWIG_OK : ensure_fast_tables(ctx, L, p);
-        if (rc) return rc;
-        if (generic_only) {
-            a.list = nullptr; a.n_list = L.nb;
-            launch_k1_generic_strict(a, ctx->stream);
-            ctx->launches += 1;
-        } else {
-            a.list = L.d_list_plain; a.n_list = L.n_plain;
-            if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
-            launch_k1_strict_packed(a, ctx->stream);
-            if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
-            if (L.n_plain > 0) ctx->launches += 1;
-            a.list = L.d_list_nonplain; a.n_list = L.nb - L.n_plain;
-            launch_k1_generic_strict(a, ctx->stream);
-            if (a.n_list > 0) ctx->launches += 1;
-        }
+    if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
+    a.negzero = -0.0f;
+    const bool strict = p.strict_fp != 0;
+    if (strict && ctx->opt_strict_generic) {
+        // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
+        // inside it, in-kernel interface interpolation; single rank only
+        if (ctx->world > 1) return fail(ctx, LUDWIG_ESTATE, "option strict_generic is single-GPU only");
+        a.list = nullptr; a.n_list = L.nb;
+        launch_k1_generic_strict(a, ctx->stream);
+        ctx->launches += 1;
     } else {
+        // Both FP modes share one schedule: ghost blocks + interface pre-pass, four K1 launch classes, remote neighbours through
+        // peer offsets.  strict_fp selects the kernels compiled in the reference's operation order (k1_strict.cu).
+        void (*const k_plain)(const K1Args&, cudaStream_t) = strict ? launch_k1s_plain : launch_k1_plain;
+        void (*const k_plain_g)(const K1Args&, cudaStream_t) = strict ? launch_k1s_plain_ghost : launch_k1_plain_ghost;
+        void (*const k_feat)(const K1Args&, cudaStream_t) = strict ? launch_k1s_feat : launch_k1_feat;
+        void (*const k_full)(const K1Args&, cudaStream_t) = strict ? launch_k1s_full : launch_k1_full;
         int rc = ensure_fast_tables(ctx, L, p);
         if (rc) return rc;
         a.nbr = L.d_nbr_fast;
@@ -443,17 +452,17 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             // The plain K1 launch never touches a ghost block: with side streams the pre-pass runs on its own stream
             // CONCURRENTLY with it, and only the launches that may pull from ghost blocks wait for it.  (The ghost buffer
             // was last read by the previous step's K1 launches, all ordered before ev_pre_fork on the main stream.)
-            overlap_pre = ctx->pre_stream != nullptr && L.n_plain > 0;
+            overlap_pre = ctx->use_side_streams && !ctx->serial_prepass && L.n_plain > 0;
             if (overlap_pre) {
                 CU(cudaEventRecord(ctx->ev_pre_fork, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->pre_stream, ctx->ev_pre_fork, 0));
                 if ((rc = prof_begin(ctx, 4, true, ctx->pre_stream))) return rc;
-                launch_ghost_interp(g, ctx->pre_stream);
+                if (strict) launch_ghost_interp_strict(g, ctx->pre_stream); else launch_ghost_interp(g, ctx->opt_block_prepass, ctx->pre_stream);
                 if ((rc = prof_end(ctx, true, 0, ctx->pre_stream))) return rc;
                 CU(cudaEventRecord(ctx->ev_pre, ctx->pre_stream));
             } else {
                 if ((rc = prof_begin(ctx, 4, true))) return rc;
-                launch_ghost_interp(g, ctx->stream);
+                if (strict) launch_ghost_interp_strict(g, ctx->stream); else launch_ghost_interp(g, ctx->opt_block_prepass, ctx->stream);
                 if ((rc = prof_end(ctx, true, 0))) return rc;
             }
             ctx->launches += 1;
@@ -464,7 +473,7 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         bool wait_halo = false;
         if (mirror) {
             a.roff_f = L.d_moff_f[in]; a.roff_v = L.d_moff_v[in];
-            if (ctx->halo_stream && L.n_plain_int > 0) {
+            if (ctx->use_side_streams && L.n_plain_int > 0) {
                 CU(cudaEventRecord(ctx->ev_halo_fork, ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_halo_fork, 0));
                 if ((rc = prof_begin(ctx, 8, true, ctx->halo_stream))) return rc;
@@ -481,16 +490,16 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
         }
         // The (up to four) K1 launches of a level step read f_in / vel_in and write disjoint blocks of f_out: on small
         // levels, where each of them is a few waves of latency-bound CTAs, they run concurrently on side streams.
-        const bool fork = ctx->side[0] != nullptr && L.nb <= ctx->fork_max_blocks;
+        const bool fork = ctx->use_side_streams && L.nb <= ctx->fork_max_blocks;
         // LUDWIG_FORK_FULL=1 (experiment for large levels, unmeasured): the domain-face blocks (128 registers, latency-bound,
         // 8 GLUPS on the bench box's inlet / outlet faces) run on a side stream UNDER the HBM-bound plain launch
-        const bool fork_full = !fork && ctx->fork_full && ctx->side[0] != nullptr && L.n_full > 0 && L.n_plain > 0;
+        const bool fork_full = !fork && ctx->fork_full && ctx->use_side_streams && L.n_full > 0 && L.n_plain > 0;
         int used = 0;
         if (fork || fork_full) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream, bool ghosts) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
-            if ((!fork && !(fork_full && fn == launch_k1_full)) || main_stream) {
+            if ((!fork && !(fork_full && fn == k_full)) || main_stream) {
                 if (overlap_pre && ghosts) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
                 fn(a, ctx->stream);
             } else {
@@ -505,64 +514,121 @@ int step_level(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, f
             ctx->launches += 1;
             return LUDWIG_OK;
         };
-        if (fork_full && (rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, false, true))) return rc;
+        if (fork_full && (rc = launch_on(k_full, L.d_list_full, L.n_full, false, true))) return rc;
         if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
         if (wait_halo) {
-            if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain_int, true, false))) return rc;
+            if ((rc = launch_on(k_plain, L.d_list_plain, L.n_plain_int, true, false))) return rc;
             CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-            if ((rc = launch_on(launch_k1_plain, L.d_list_plain + L.n_plain_int, L.n_plain - L.n_plain_int, true, false))) return rc;
-        } else if ((rc = launch_on(launch_k1_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
+            if ((rc = launch_on(k_plain, L.d_list_plain + L.n_plain_int, L.n_plain - L.n_plain_int, true, false))) return rc;
+        } else if ((rc = launch_on(k_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
         if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)L.n_plain * BS3))) return rc;
         // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
         const bool pc = ctx->profiling && !fork && !fork_full;
         if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
-        if ((rc = launch_on(launch_k1_plain_ghost, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0, true))) return rc;
+        if ((rc = launch_on(k_plain_g, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_plain_g > 0, 0))) return rc;
         if ((rc = prof_begin(ctx, 2, pc && L.n_feat > 0))) return rc;
-        if ((rc = launch_on(launch_k1_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
+        if ((rc = launch_on(k_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
         if ((rc = prof_begin(ctx, 3, pc && L.n_full > 0))) return rc;
-        if (!fork_full && (rc = launch_on(launch_k1_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
+        if (!fork_full && (rc = launch_on(k_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         if (overlap_pre) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));   // nothing on the main stream consumed it yet
     }
+  }   // PH_K1
     const bool mg = ctx->world > 1;
-    if (L.bouzidi) {
-        // K2 reads f_out of x_ff cells that may belong to another GPU: K1 must be complete everywhere before the
-        // gather, and every gather before any scatter (the same two-phase argument as on one GPU, across ranks).
-        if (mg) rank_barrier(ctx);
+    // K2 reads f_out of x_ff cells that may belong to another GPU: K1 must be complete everywhere before the gather, and
+    // every gather before any scatter (the same two-phase argument as on one GPU, across ranks): the caller puts a
+    // cross-rank barrier between the phases.
+    if ((phase & PH_GATHER) && L.bouzidi) {
+        int rcp;
         int rcb = ensure_bouzidi_links(ctx, L, p.q_min_threshold);
         if (rcb) return rcb;
-        int rcp;
         if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
         launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 1, ctx->stream);
         if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
-        if (mg) rank_barrier(ctx);
-        if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
-        launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 2, ctx->stream);
-        if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
-        if (L.n_links > 0) ctx->launches += 2;
     }
-    if (mg && ctx->use_mirror && L.n_pack > 0) {   // the layers the peers pull at the start of the next step of this level
-        int rcq;
-        if ((rcq = prof_begin(ctx, 9, true))) return rcq;
-        launch_halo_pack(L, out, ctx->stream);
-        if ((rcq = prof_end(ctx, true, 0))) return rcq;
-        ctx->launches += 1;
+    if (phase & PH_FINISH) {
+        if (L.bouzidi) {
+            int rcp;
+            if ((rcp = prof_begin(ctx, 5, L.n_links > 0))) return rcp;
+            launch_bouzidi(L, L.d_f[out], L.d_roff_f[out], p.strict_fp != 0, 2, ctx->stream);
+            if ((rcp = prof_end(ctx, L.n_links > 0, 0))) return rcp;
+            if (L.n_links > 0) ctx->launches += 2;
+        }
+        if (mg && ctx->use_mirror && L.n_pack > 0) {   // the layers the peers pull at the start of the next step of this level
+            int rcq;
+            if ((rcq = prof_begin(ctx, 9, true))) return rcq;
+            launch_halo_pack(L, out, ctx->stream);
+            if ((rcq = prof_end(ctx, true, 0))) return rcq;
+            ctx->launches += 1;
+        }
+        L.rho_cur = rho_out;
+        L.last_t_sub = t_sub;
     }
-    if (mg) rank_barrier(ctx);   // every rank finished this level step
-    if (p7 != (size_t)-1) CU(cudaEventRecord(ctx->ev_pool[p7 + 1], ctx->stream));
-    L.rho_cur = rho_out;
-    L.last_t_sub = t_sub;
     CU(cudaGetLastError());
+    return LUDWIG_OK;
+}
+
+// A group = the contexts one host thread steps in lock-step: a single context (one GPU, or one process per GPU with the
+// peer-flag / callback barrier), or the N contexts of a ludwig_multi (one process, N GPUs or N virtual ranks on one GPU),
+// whose barrier is a set of stream-ordered event waits: rank r's stream waits for an event recorded on every other rank's
+// stream.  Nothing blocks the host and no kernel spins, so any number of virtual ranks can share one device.
+struct Group {
+    std::vector<ludwig_ctx*> c;
+    std::vector<cudaEvent_t>* ev = nullptr;   // one event per rank (ludwig_multi); null for a single context
+};
+int group_barrier(Group& g) {
+    if (g.c.size() == 1) return rank_barrier(g.c[0]);
+    const size_t n = g.c.size();
+    for (size_t r = 0; r < n; ++r) {
+        ludwig_ctx* ctx = g.c[r];
+        CU(cudaSetDevice(ctx->device));
+        int rc = prof_begin(ctx, 6, true); if (rc) return rc;
+        CU(cudaEventRecord((*g.ev)[r], ctx->stream));
+    }
+    for (size_t r = 0; r < n; ++r) {
+        ludwig_ctx* ctx = g.c[r];
+        CU(cudaSetDevice(ctx->device));
+        for (size_t q = 0; q < n; ++q) if (q != r) CU(cudaStreamWaitEvent(ctx->stream, (*g.ev)[q], 0));
+        int rc = prof_end(ctx, true, 0); if (rc) return rc;
+    }
+    return LUDWIG_OK;
+}
+
+// One level step of every context of the group, phase by phase, with the cross-rank barriers in between.
+int group_step_level(Group& g, size_t lvl, const std::vector<ParentView>* pvs, int64_t t_sub, float tw, float u, const ludwig_params& p) {
+    const bool mg = g.c[0]->world > 1;
+    const bool bz = g.c[0]->levels[lvl]->bouzidi;
+    auto run = [&](int phase) -> int {
+        for (size_t r = 0; r < g.c.size(); ++r) {
+            ludwig_ctx* ctx = g.c[r];
+            if (g.c.size() > 1) CU(cudaSetDevice(ctx->device));
+            int rc = step_level_phase(ctx, *ctx->levels[lvl], pvs ? &(*pvs)[r] : nullptr, t_sub, tw, u, p, phase);
+            if (rc) { if (ctx != g.c[0]) g.c[0]->err = ctx->err; return rc; }
+        }
+        return LUDWIG_OK;
+    };
+    int rc;
+    if (!mg || !bz) { if ((rc = run(PH_ALL))) return rc; }
+    else {
+        if ((rc = run(PH_K1))) return rc;
+        if ((rc = group_barrier(g))) return rc;
+        if ((rc = run(PH_GATHER))) return rc;
+        if ((rc = group_barrier(g))) return rc;
+        if ((rc = run(PH_FINISH))) return rc;
+    }
+    if (mg && (rc = group_barrier(g))) return rc;   // every rank finished this level step
+    for (ludwig_ctx* ctx : g.c)
+        if (ctx->p7 != (size_t)-1) { CU(cudaEventRecord(ctx->ev_pool[ctx->p7 + 1], ctx->stream)); ctx->p7 = (size_t)-1; }
     return LUDWIG_OK;
 }
 
 // Multi-GPU: build every lazily built host table (fast-mode lists, ghost blocks, compacted Bouzidi links) BEFORE the first
 // cross-rank barrier of a call, so that no rank sits in a barrier kernel while a peer is still doing seconds of host work.
 int prepare_tables(ludwig_ctx* ctx, const ludwig_params& p) {
-    if (ctx->world <= 1 || p.strict_fp) return LUDWIG_OK;
+    if (ctx->world <= 1) return LUDWIG_OK;
     for (Level* L : ctx->levels) {
         int rc = ensure_fast_tables(ctx, *L, p);
         if (rc) return rc;
@@ -572,16 +638,39 @@ int prepare_tables(ludwig_ctx* ctx, const ludwig_params& p) {
 }
 
 // recursive_step! / recursive_step_temporal! (solver_control.jl:21-143)
-int recursive_step(ludwig_ctx* ctx, size_t lvl, int64_t t_sub, const ParentView* pv, float tw, float u, const ludwig_params& p) {
-    if (lvl >= ctx->levels.size()) return LUDWIG_OK;
-    Level& L = *ctx->levels[lvl];
-    int rc = step_level(ctx, L, pv, t_sub, tw, u, p);
+int recursive_step(Group& g, size_t lvl, int64_t t_sub, const std::vector<ParentView>* pvs, float tw, float u, const ludwig_params& p) {
+    if (lvl >= g.c[0]->levels.size()) return LUDWIG_OK;
+    int rc = group_step_level(g, lvl, pvs, t_sub, tw, u, p);
     if (rc) return rc;
-    if (lvl + 1 < ctx->levels.size()) {
-        ParentView me = make_parent_view(L, t_sub, /*explicit_old=*/false);
-        if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub, &me, 0.0f, u, p))) return rc;
-        if ((rc = recursive_step(ctx, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p))) return rc;
+    if (lvl + 1 < g.c[0]->levels.size()) {
+        std::vector<ParentView> me;
+        for (ludwig_ctx* ctx : g.c) me.push_back(make_parent_view(*ctx->levels[lvl], t_sub, /*explicit_old=*/false));
+        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub, &me, 0.0f, u, p))) return rc;
+        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p))) return rc;
     }
+    return LUDWIG_OK;
+}
+
+// execute_timestep_batch! (solver_control.jl:145-165) for a group
+int group_step_batch(Group& g, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params& p) {
+    for (ludwig_ctx* ctx : g.c) {
+        if (g.c.size() > 1) CU(cudaSetDevice(ctx->device));
+        if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: attach the peers first");
+        int rcp = prepare_tables(ctx, p);
+        if (rcp) return rcp;
+        // export the halo layers of the CURRENT state (it may have been uploaded or initialised since the last batch): level l's
+        // first sub-step is t_start * 2^l and reads the buffer of that parity
+        if (ctx->world > 1 && ctx->use_mirror)
+            for (size_t l = 0; l < ctx->levels.size(); ++l) {
+                const int64_t t0 = t_start << l;
+                launch_halo_pack(*ctx->levels[l], (t0 % 2 == 0) ? 0 : 1, ctx->stream);
+            }
+    }
+    // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
+    int rc;
+    if (g.c[0]->world > 1 && (rc = group_barrier(g))) return rc;
+    for (int t_offset = 0; t_offset < batch_size; ++t_offset)
+        if ((rc = recursive_step(g, 0, t_start + t_offset, nullptr, 0.0f, u_curr, p))) return rc;
     return LUDWIG_OK;
 }
 
@@ -642,7 +731,7 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LUDWIG_ECUDA; }
-    if (!getenv("LUDWIG_SINGLE_STREAM")) {
+    {
         bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < 3 && ok; ++i)
             ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -657,16 +746,8 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
              cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_halo_fork, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
-        ctx->fork_full = getenv("LUDWIG_FORK_FULL") != nullptr;
-        if (getenv("LUDWIG_SERIAL_PREPASS")) { cudaStreamDestroy(ctx->pre_stream); ctx->pre_stream = nullptr; }
-        if (const char* e = getenv("LUDWIG_FORK_MAX_BLOCKS")) ctx->fork_max_blocks = atoi(e);
     }
-    // Multi-GPU halo strategy.  Default: K1 pulls remote layers straight over NVLink inside the stream-collide kernel.
-    // LUDWIG_HALO_MIRROR=1: packed exchange into local mirrors (pack / unpack kernels, k_misc.cu) — measured SLOWER on
-    // 2 and 8 B200 (profiles/README.md, "halo strategies"): the extra kernels sit on the critical path of every level
-    // step while the in-kernel pulls hide behind the other CTAs of an HBM-bound kernel.
-    ctx->use_mirror = getenv("LUDWIG_HALO_MIRROR") != nullptr;
-    if (const char* pm = getenv("LUDWIG_PARTITION")) ctx->rcb = std::string(pm) == "rcb";
+    // Every behaviour switch is an explicit option (ludwig_ctx_set_option); the library reads no environment variable.
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -683,6 +764,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (Level* L : ctx->levels) free_level(L);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
+    if (ctx->h_bar_err) cudaFreeHost(ctx->h_bar_err);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -692,6 +774,37 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     for (cudaStream_t st : {ctx->pre_stream, ctx->halo_stream}) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t e : {ctx->ev_pre_fork, ctx->ev_pre, ctx->ev_halo, ctx->ev_halo_fork}) if (e) cudaEventDestroy(e);
     delete ctx;
+    return LUDWIG_OK;
+}
+
+// Behaviour switches that have no counterpart in the reference (it has one device and one kernel per step).  Every one
+// defaults to the configuration measured fastest; the alternatives are kept for A/B runs and cross-checks.
+int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
+    if (!ctx || !key || !value) return fail(ctx, LUDWIG_EINVAL, "set_option: null argument");
+    const std::string k(key), v(value);
+    const bool on = v == "1" || v == "true" || v == "on";
+    const bool before_levels = ctx->levels.empty();
+    auto need_early = [&]() { return fail(ctx, LUDWIG_ESTATE, "option '" + k + "' must be set before the first ludwig_level_create"); };
+    if (k == "prepass") {                       // "thread" (default) | "block": block-cooperative interface pre-pass
+        if (v != "thread" && v != "block") return fail(ctx, LUDWIG_EINVAL, "prepass: thread | block");
+        ctx->opt_block_prepass = v == "block";
+    } else if (k == "serial_prepass") ctx->serial_prepass = on;          // pre-pass on the main stream instead of beside the plain K1 launch
+    else if (k == "single_stream") ctx->use_side_streams = !on;          // no concurrent launches at all
+    else if (k == "fork_full") ctx->fork_full = on;                      // domain-face K1 launch beside the plain launch on large levels
+    else if (k == "fork_max_blocks") ctx->fork_max_blocks = atoi(value); // levels up to this size run their K1 classes concurrently
+    else if (k == "strict_generic") ctx->opt_strict_generic = on;        // strict mode through the one-thread-per-cell cross-check kernel
+    else if (k == "verbose") ctx->verbose = on;
+    else if (k == "barrier_timeout_s") { ctx->barrier_timeout_s = atof(value); if (!(ctx->barrier_timeout_s > 0)) return fail(ctx, LUDWIG_EINVAL, "barrier_timeout_s > 0"); }
+    else if (k == "halo_mirror") { if (!before_levels) return need_early(); ctx->use_mirror = on; }   // packed halo exchange into local mirrors
+    else if (k == "partition") {                // "morton" (default: cost-weighted Morton ranges / aligned plan) | "rcb" | "rcb_yz"
+        if (!before_levels) return need_early();
+        if (v == "morton") ctx->partition_mode = 0; else if (v == "rcb") ctx->partition_mode = 1; else if (v == "rcb_yz") ctx->partition_mode = 2;
+        else return fail(ctx, LUDWIG_EINVAL, "partition: morton | rcb | rcb_yz");
+    } else if (k == "remote_order") {           // where the blocks that pull from a peer sit in the plain launch
+        if (v != "morton" && v != "first" && v != "last" && v != "interleave") return fail(ctx, LUDWIG_EINVAL, "remote_order: morton | first | last | interleave");
+        for (Level* L : ctx->levels) if (L->fast_ready) return fail(ctx, LUDWIG_ESTATE, "remote_order must be set before the first step");
+        ctx->remote_order = v;
+    } else return fail(ctx, LUDWIG_EINVAL, "unknown option '" + k + "'");
     return LUDWIG_OK;
 }
 
@@ -743,12 +856,7 @@ int ludwig_profile_levels(ludwig_ctx* ctx, double* out, int32_t capacity) {
 int ludwig_sync(ludwig_ctx* ctx) {
     if (!ctx) return LUDWIG_EINVAL;
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_bar_err) {
-        int e = 0;
-        CU(memcpy_sync(ctx->stream, &e, ctx->d_bar_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (e) return fail(ctx, LUDWIG_ESTATE, "cross-GPU barrier timed out (a peer stopped, or the ranks issued different call sequences)");
-    }
-    return LUDWIG_OK;
+    return barrier_state(ctx);
 }
 
 int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* out_index) {
@@ -782,9 +890,9 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
     // contiguous range and walks its blocks along the Morton curve; nothing else in the library depends on how the ranges
     // were chosen.  On the 339 M-cell bunny the Morton ranges have 2-3x the halo surface of RCB boxes.
     std::vector<int32_t> rcb_owner;
-    if (ctx->world > 1 && ctx->rcb) {
+    if (ctx->world > 1 && ctx->partition_mode != 0) {
         rcb_owner.resize(nbg);
-        if (ludwig_partition_rcb(d, ctx->world, rcb_owner.data()) != LUDWIG_OK) return fail(ctx, LUDWIG_EINVAL, "rcb partition failed (fewer blocks than ranks?)");
+        if (ludwig_partition_rcb_axes(d, ctx->world, ctx->partition_mode == 2 ? 6 : 7, rcb_owner.data()) != LUDWIG_OK) return fail(ctx, LUDWIG_EINVAL, "rcb partition failed (fewer blocks than ranks?)");
     }
     L.int2ref.resize(nbg);
     std::iota(L.int2ref.begin(), L.int2ref.end(), 0);
@@ -1196,40 +1304,28 @@ int ludwig_init_equilibrium(ludwig_ctx* ctx) {
 // solver_control.jl:145-165
 int ludwig_step_batch(ludwig_ctx* ctx, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params) {
     if (!ctx || !params || ctx->levels.empty() || batch_size < 0) return fail(ctx, LUDWIG_EINVAL, "bad step args");
+    if (ctx->group_managed) return fail(ctx, LUDWIG_ESTATE, "this context belongs to a ludwig_multi: step it with ludwig_multi_step_batch");
     CU(cudaSetDevice(ctx->device));
-    if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach first");
-    int rcp = prepare_tables(ctx, *params);
-    if (rcp) return rcp;
-    // export the halo layers of the CURRENT state (it may have been uploaded or initialised since the last batch): level l's
-    // first sub-step is t_start * 2^l and reads the buffer of that parity
-    if (ctx->world > 1 && ctx->use_mirror)
-        for (size_t l = 0; l < ctx->levels.size(); ++l) {
-            const int64_t t0 = t_start << l;
-            launch_halo_pack(*ctx->levels[l], (t0 % 2 == 0) ? 0 : 1, ctx->stream);
-        }
-    // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
-    rank_barrier(ctx);
-    for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
-        int rc = recursive_step(ctx, 0, t_start + t_offset, nullptr, 0.0f, u_curr, *params);
-        if (rc) return rc;
-    }
-    return LUDWIG_OK;
+    Group g; g.c.push_back(ctx);
+    return group_step_batch(g, t_start, batch_size, u_curr, *params);
 }
 
 int ludwig_level_step(ludwig_ctx* ctx, int32_t level, int64_t t_sub, int64_t parent_t_sub, float temporal_weight, float u_curr,
                       const ludwig_params* params) {
     if (!level_ok(ctx, level) || !params) return fail(ctx, LUDWIG_EINVAL, "bad level");
+    if (ctx->group_managed) return fail(ctx, LUDWIG_ESTATE, "this context belongs to a ludwig_multi");
     CU(cudaSetDevice(ctx->device));
     Level& L = *ctx->levels[level];
     int rcp = prepare_tables(ctx, *params);
     if (rcp) return rcp;
     if (ctx->world > 1 && ctx->use_mirror) launch_halo_pack(L, (t_sub % 2 == 0) ? 0 : 1, ctx->stream);
-    rank_barrier(ctx);
-    if (level == 0) return step_level(ctx, L, nullptr, t_sub, temporal_weight, u_curr, *params);
+    if ((rcp = rank_barrier(ctx))) return rcp;
+    Group g; g.c.push_back(ctx);
+    if (level == 0) return group_step_level(g, 0, nullptr, t_sub, temporal_weight, u_curr, *params);
     Level& P = *ctx->levels[level - 1];
     if (params->use_temporal && !P.temporal) return fail(ctx, LUDWIG_ESTATE, "parent has no temporal storage");
-    ParentView pv = make_parent_view(P, parent_t_sub, /*explicit_old=*/true);
-    return step_level(ctx, L, &pv, t_sub, temporal_weight, u_curr, *params);
+    std::vector<ParentView> pv{make_parent_view(P, parent_t_sub, /*explicit_old=*/true)};
+    return group_step_level(g, (size_t)level, &pv, t_sub, temporal_weight, u_curr, *params);
 }
 
 // blocks.jl:199-205.  Only the fine-grained API needs real copies; ludwig_step_batch never calls this.
@@ -1258,7 +1354,7 @@ int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* F, int32_t level
     const float pscale = (float)(rho_phys * velocity_scale * velocity_scale);   // forces/surface.jl:402-403
     const float offx = (float)mesh_offset[0], offy = (float)mesh_offset[1], offz = (float)mesh_offset[2];
     // K3 reads level.rho and level.vel (NOT vel_temp) whatever the parity — forces/surface.jl:412
-    rank_barrier(ctx);   // K3 reads cells owned by other GPUs
+    { int rcb = rank_barrier(ctx); if (rcb) return rcb; }   // K3 reads cells owned by other GPUs
     // multi-GPU: triangles are dealt round-robin to the ranks; each rank returns PARTIAL sums (every output of this
     // call is linear in them), the caller adds the 18 numbers over the ranks.
     PeerBytes obs;
@@ -1268,6 +1364,7 @@ int ludwig_compute_aerodynamics(ludwig_ctx* ctx, ludwig_forces* F, int32_t level
     launch_integrate_forces(M, *F, offx, offy, offz, ctx->rank, ctx->world, ctx->stream);
     CU(cudaMemcpyAsync(F->h_acc, F->d_acc, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { int rcb = barrier_state(ctx); if (rcb) return rcb; }
     // FP64 sums of the FP32 per-triangle contributions (the reference's FP32 atomics lose ~1e-4 here)
     double Fx_p = F->h_acc[0], Fy_p = F->h_acc[1], Fz_p = F->h_acc[2];
     double Fx_v = F->h_acc[3], Fy_v = F->h_acc[4], Fz_v = F->h_acc[5];
@@ -1308,12 +1405,17 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
     launch_flow_stats(L, L.d_rho[L.rho_cur], L.d_vel[0], ctx->d_stats, nparts, ctx->stream);
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, (size_t)nparts * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { int rcb = barrier_state(ctx); if (rcb) return rcb; }
     double n = 0, rs = 0, ke = 0, rmin = INFINITY, rmax = -INFINITY, vmax = 0;
+    bool nan_rho = false, nan_v = false;   // NaN partials (see flow_stats_kernel): std::min / std::max would drop them
     for (int i = 0; i < nparts; ++i) {
         const double* q = ctx->h_stats + (size_t)i * 6;
         n += q[0]; rs += q[1]; ke += q[5];
+        nan_rho |= q[2] != q[2]; nan_v |= q[4] != q[4];
         rmin = std::min(rmin, q[2]); rmax = std::max(rmax, q[3]); vmax = std::max(vmax, q[4]);
     }
+    if (nan_rho) rmin = rmax = NAN;
+    if (nan_v) vmax = NAN;
     if (n > 0) { out[0] = n; out[1] = rs / n; out[2] = rmin; out[3] = rmax; out[4] = vmax; out[5] = 0.5 * ke; }
     else { out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 1; out[4] = 0; out[5] = 0; }
     return LUDWIG_OK;
@@ -1405,8 +1507,13 @@ int ludwig_partition_plan(const ludwig_level_desc* const* descs, int32_t n_level
 // Recursive coordinate bisection of one level (host code, no GPU): splits the blocks into `world` boxes of equal cost
 // (ludwig_block_costs), always across the longest axis of the current box, at the cost-weighted median; ties along the axis
 // are ordered by Morton key, so the result is deterministic and identical on every rank.  owner[b] in reference order.
-int ludwig_partition_rcb(const ludwig_level_desc* d, int32_t world, int32_t* owner) {
-    if (!d || !owner || world < 1 || world > MAX_RANKS || d->n_blocks < world) return LUDWIG_EINVAL;
+int ludwig_partition_rcb(const ludwig_level_desc* d, int32_t world, int32_t* owner) { return ludwig_partition_rcb_axes(d, world, 7, owner); }
+
+// axes: bit a set = cuts across axis a allowed (7 = x, y and z; 6 = y and z only).  A cut across x puts x-faces on the cut
+// surface: in the block layout an x-face layer is 64 separate 32-byte sectors per direction for 4 useful bytes each, so
+// every byte K1 pulls through it over NVLink costs 8; y-faces (8 full sectors) and z-faces (256 contiguous bytes) cost 1.
+int ludwig_partition_rcb_axes(const ludwig_level_desc* d, int32_t world, int32_t axes, int32_t* owner) {
+    if (!d || !owner || world < 1 || world > MAX_RANKS || d->n_blocks < world || (axes & 7) == 0) return LUDWIG_EINVAL;
     const int nb = d->n_blocks;
     std::vector<float> cost(nb);
     int rc = ludwig_block_costs(d, cost.data());
@@ -1424,6 +1531,7 @@ int ludwig_partition_rcb(const ludwig_level_desc* d, int32_t world, int32_t* own
         if (nd.n == 1) { for (int i = nd.lo; i < nd.hi; ++i) owner[idx[i]] = nd.first; continue; }
         int axis = 0, best = -1;
         for (int a = 0; a < 3; ++a) {
+            if (!((axes >> a) & 1)) continue;
             int mn = INT32_MAX, mx = INT32_MIN;
             for (int i = nd.lo; i < nd.hi; ++i) { mn = std::min(mn, coord[a][idx[i]]); mx = std::max(mx, coord[a][idx[i]]); }
             if (mx - mn > best) { best = mx - mn; axis = a; }
@@ -1469,11 +1577,14 @@ int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
         CU(cudaMalloc((void**)&ctx->d_bar, 2 * 1024 * 1024));        // own allocation granule: IPC exports whole allocations
         CU(cudaMemset(ctx->d_bar, 0, 2 * 1024 * 1024));
         ctx->d_bar_err = (int*)(ctx->d_bar + 64);
+        CU(cudaHostAlloc((void**)&ctx->h_bar_err, sizeof(int), cudaHostAllocMapped));
+        *ctx->h_bar_err = 0;
+        CU(cudaHostGetDevicePointer((void**)&ctx->d_bar_err_dev, ctx->h_bar_err, 0));
     }
     return LUDWIG_OK;
 }
 
-int ludwig_set_barrier_callback(ludwig_ctx* ctx, void (*fn)(void*), void* user) {
+int ludwig_set_barrier_callback(ludwig_ctx* ctx, int (*fn)(void*), void* user) {
     if (!ctx) return LUDWIG_EINVAL;
     ctx->barrier_cb = fn; ctx->barrier_user = user;
     return LUDWIG_OK;
@@ -1573,6 +1684,238 @@ int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const* peers, int32_t n
         }
     }
     return finish_attach(ctx);
+}
+
+
+// ---- several GPUs (or several virtual ranks on one GPU) driven by ONE host thread -------------------------------------------------
+//
+// "Multi-GPU is hidden behind ludwig_ctx_create(n_gpus, device_ids); level creation takes the global
+// tables and the library partitions."  A ludwig_multi owns one context per rank, partitions every level as the per-process
+// path does, attaches the ranks in-process (plain device pointers, peer access enabled between devices) and steps them in
+// lock-step from the calling thread: every phase of a level step is enqueued on every rank's stream, and the cross-rank
+// barriers are stream-ordered event waits (group_barrier) — no spinning kernel, no host blocking, no NCCL.  The kept
+// single-process Julia driver (main.jl:54-249) can therefore use N GPUs with the same sequence of calls it makes for one.
+// Results are bit-identical to the single-context run in both FP modes.
+struct ludwig_multi {
+    std::vector<ludwig_ctx*> ctx;
+    std::vector<cudaEvent_t> ev;
+    bool attached = false;
+    struct FH { std::vector<ludwig_mesh*> mesh; std::vector<ludwig_forces*> forces; };
+    std::vector<FH> fh;
+    std::string err;
+};
+
+namespace {
+int mfail(ludwig_multi* m, int code, const std::string& msg) { if (m) m->err = msg; return code; }
+int mpass(ludwig_multi* m, ludwig_ctx* c, int rc) { if (rc && m) m->err = c ? c->err : "error"; return rc; }
+int multi_attach(ludwig_multi* m) {
+    if (m->attached) return LUDWIG_OK;
+    if (m->ctx.size() > 1)
+        for (ludwig_ctx* c : m->ctx) {
+            int rc = ludwig_attach_inprocess(c, m->ctx.data(), (int32_t)m->ctx.size());
+            if (rc) return mpass(m, c, rc);
+        }
+    m->attached = true;
+    return LUDWIG_OK;
+}
+}  // namespace
+
+int ludwig_multi_create(ludwig_multi** out, int32_t n_ranks, const int32_t* devices) {
+    if (!out || n_ranks < 1 || n_ranks > MAX_RANKS) return LUDWIG_EINVAL;
+    *out = nullptr;
+    auto* m = new ludwig_multi();
+    for (int r = 0; r < n_ranks; ++r) {
+        ludwig_ctx* c = nullptr;
+        int rc = ludwig_ctx_create(&c, devices ? devices[r] : r);
+        if (rc == LUDWIG_OK && n_ranks > 1) rc = ludwig_ctx_set_partition(c, r, n_ranks);
+        if (rc != LUDWIG_OK) { if (c) ludwig_ctx_destroy(c); ludwig_multi_destroy(m); return rc; }
+        c->group_managed = n_ranks > 1;
+        m->ctx.push_back(c);
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { ludwig_multi_destroy(m); return LUDWIG_ECUDA; }
+        m->ev.push_back(e);
+    }
+    *out = m;
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_destroy(ludwig_multi* m) {
+    if (!m) return LUDWIG_OK;
+    for (ludwig_ctx* c : m->ctx) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }   // nobody frees memory a peer still reads
+    for (auto& f : m->fh) {
+        for (ludwig_forces* x : f.forces) ludwig_forces_destroy(x);
+        for (ludwig_mesh* x : f.mesh) ludwig_mesh_destroy(x);
+    }
+    for (size_t r = 0; r < m->ctx.size(); ++r) {
+        cudaSetDevice(m->ctx[r]->device);
+        if (r < m->ev.size() && m->ev[r]) cudaEventDestroy(m->ev[r]);
+        ludwig_ctx_destroy(m->ctx[r]);
+    }
+    delete m;
+    return LUDWIG_OK;
+}
+
+const char* ludwig_multi_last_error(const ludwig_multi* m) { return m ? m->err.c_str() : "null handle"; }
+int32_t ludwig_multi_num_ranks(const ludwig_multi* m) { return m ? (int32_t)m->ctx.size() : LUDWIG_EINVAL; }
+ludwig_ctx* ludwig_multi_ctx(ludwig_multi* m, int32_t rank) { return (m && rank >= 0 && rank < (int)m->ctx.size()) ? m->ctx[rank] : nullptr; }
+
+int ludwig_multi_set_option(ludwig_multi* m, const char* key, const char* value) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_ctx_set_option(c, key, value); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_set_partition_plan(ludwig_multi* m, const ludwig_level_desc* const* descs, int32_t n_levels) {
+    if (!m || !descs) return LUDWIG_EINVAL;
+    if (m->ctx.size() == 1) return LUDWIG_OK;
+    std::vector<uint64_t> keys(m->ctx.size() + 1);
+    int rc = ludwig_partition_plan(descs, n_levels, (int32_t)m->ctx.size(), keys.data());
+    if (rc) return mfail(m, rc, "ludwig_partition_plan failed");
+    for (ludwig_ctx* c : m->ctx) if ((rc = ludwig_ctx_set_partition_keys(c, keys.data(), n_levels))) return mpass(m, c, rc);
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_level_create(ludwig_multi* m, const ludwig_level_desc* desc, int32_t* out_index) {
+    if (!m || !desc) return LUDWIG_EINVAL;
+    if (m->attached) return mfail(m, LUDWIG_ESTATE, "levels cannot be added after the first step");
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_level_create(c, desc, out_index); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_init_equilibrium(ludwig_multi* m) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_init_equilibrium(c); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_sync(ludwig_multi* m) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_sync(c); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_step_batch(ludwig_multi* m, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params) {
+    if (!m || !params || m->ctx.empty() || m->ctx[0]->levels.empty() || batch_size < 0) return mfail(m, LUDWIG_EINVAL, "bad step args");
+    int rc = multi_attach(m);
+    if (rc) return rc;
+    Group g; g.c = m->ctx; g.ev = &m->ev;
+    rc = group_step_batch(g, t_start, batch_size, u_curr, *params);
+    if (rc) for (ludwig_ctx* c : m->ctx) if (!c->err.empty()) { m->err = c->err; break; }
+    return rc;
+}
+
+// Whole-level upload / download in the reference layout: every rank picks / contributes its own blocks.
+int ludwig_multi_level_upload(ludwig_multi* m, int32_t level, int32_t which, const void* src) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_level_upload(c, level, which, src); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+int ludwig_multi_level_download(ludwig_multi* m, int32_t level, int32_t which, void* dst) {
+    if (!m || !dst) return LUDWIG_EINVAL;
+    if (m->ctx.size() == 1) return mpass(m, m->ctx[0], ludwig_level_download(m->ctx[0], level, which, dst));
+    if (!level_ok(m->ctx[0], level)) return mfail(m, LUDWIG_EINVAL, "bad level");
+    const size_t nbg = (size_t)m->ctx[0]->levels[level]->nb_global;
+    const int ncomp = which == LUDWIG_OBSTACLE ? 1 : (which == LUDWIG_RHO || which == LUDWIG_RHO_OLD) ? 1 : (which == LUDWIG_VEL || which == LUDWIG_VEL_TEMP || which == LUDWIG_VEL_OLD) ? 3 : Q;
+    if (which == LUDWIG_OBSTACLE) {   // bytes: every rank returns zeros outside its blocks -> OR them together
+        std::vector<uint8_t> tmp(nbg * BS3);
+        std::memset(dst, 0, nbg * BS3);
+        for (ludwig_ctx* c : m->ctx) {
+            int rc = ludwig_level_download(c, level, which, tmp.data());
+            if (rc) return mpass(m, c, rc);
+            uint8_t* d = (uint8_t*)dst;
+            for (size_t i = 0; i < tmp.size(); ++i) d[i] |= tmp[i];
+        }
+        return LUDWIG_OK;
+    }
+    std::vector<float> tmp;
+    for (ludwig_ctx* c : m->ctx) {
+        Level& L = *c->levels[level];
+        tmp.resize((size_t)L.nb * BS3 * ncomp);
+        int rc = ludwig_level_download_local(c, level, which, tmp.data());
+        if (rc) return mpass(m, c, rc);
+        for (int k = 0; k < ncomp; ++k)
+            for (int b = 0; b < L.nb; ++b)
+                std::memcpy((float*)dst + ((size_t)k * nbg + (size_t)L.int2ref[L.part_start + b]) * BS3, tmp.data() + ((size_t)k * L.nb + b) * BS3, BS3 * sizeof(float));
+    }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_flow_stats(ludwig_multi* m, int32_t level, double out[6]) {
+    if (!m || !out) return LUDWIG_EINVAL;
+    double n = 0, rs = 0, ke = 0, rmin = INFINITY, rmax = -INFINITY, vmax = 0;
+    bool nan_seen = false, nan_v = false;
+    for (ludwig_ctx* c : m->ctx) {
+        double q[6];
+        int rc = ludwig_flow_stats(c, level, q);
+        if (rc) return mpass(m, c, rc);
+        if (q[0] <= 0) continue;
+        n += q[0]; rs += q[1] * q[0]; ke += q[5];
+        if (q[2] != q[2]) nan_seen = true;
+        if (q[4] != q[4]) nan_v = true;
+        rmin = std::min(rmin, q[2]); rmax = std::max(rmax, q[3]); vmax = std::max(vmax, q[4]);
+    }
+    if (n > 0) { out[0] = n; out[1] = rs / n; out[2] = rmin; out[3] = rmax; out[4] = vmax; out[5] = ke; }
+    else { out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 1; out[4] = 0; out[5] = 0; }
+    if (nan_seen) out[2] = out[3] = NAN;
+    if (nan_v) out[4] = NAN;
+    return LUDWIG_OK;
+}
+
+// Mesh + ForceData on every rank (main.jl:101,145); returns a handle index for ludwig_multi_compute_aerodynamics.
+int ludwig_multi_forces_create(ludwig_multi* m, int32_t n_triangles, const float* cx, const float* cy, const float* cz, const float* nx,
+                               const float* ny, const float* nz, const float* area, double rho_ref, double u_ref, double area_ref,
+                               double chord_ref, const double moment_center[3], int32_t symmetric, int32_t* out_handle) {
+    if (!m || !out_handle) return LUDWIG_EINVAL;
+    ludwig_multi::FH f;
+    for (ludwig_ctx* c : m->ctx) {
+        ludwig_mesh* mesh = nullptr; ludwig_forces* forces = nullptr;
+        int rc = ludwig_mesh_create(c, n_triangles, cx, cy, cz, nx, ny, nz, area, &mesh);
+        if (rc == LUDWIG_OK) { f.mesh.push_back(mesh); rc = ludwig_forces_create(c, mesh, rho_ref, u_ref, area_ref, chord_ref, moment_center, symmetric, &forces); }
+        if (rc == LUDWIG_OK) f.forces.push_back(forces);
+        if (rc) { for (auto* x : f.forces) ludwig_forces_destroy(x); for (auto* x : f.mesh) ludwig_mesh_destroy(x); return mpass(m, c, rc); }
+    }
+    m->fh.push_back(f);
+    *out_handle = (int32_t)m->fh.size() - 1;
+    return LUDWIG_OK;
+}
+
+// compute_aerodynamics! over all ranks: every rank integrates the triangles dealt to it; all 18 outputs are linear in the partial sums.
+int ludwig_multi_compute_aerodynamics(ludwig_multi* m, int32_t handle, int32_t level, const double mesh_offset[3], double velocity_scale,
+                                      double rho_phys, int32_t search_radius, double out[18]) {
+    if (!m || !out || handle < 0 || handle >= (int)m->fh.size()) return mfail(m, LUDWIG_EINVAL, "bad forces handle");
+    int rc = multi_attach(m);
+    if (rc) return rc;
+    Group g; g.c = m->ctx; g.ev = &m->ev;
+    if (m->ctx.size() > 1 && (rc = group_barrier(g))) return rc;   // K3 reads cells owned by other ranks
+    for (int i = 0; i < 18; ++i) out[i] = 0.0;
+    for (size_t r = 0; r < m->ctx.size(); ++r) {
+        double q[18];
+        rc = ludwig_compute_aerodynamics(m->ctx[r], m->fh[handle].forces[r], level, mesh_offset, velocity_scale, rho_phys, search_radius, q);
+        if (rc) return mpass(m, m->ctx[r], rc);
+        for (int i = 0; i < 18; ++i) out[i] += q[i];
+    }
+    return LUDWIG_OK;
+}
+
+// forces/io.jl:28-31: the per-triangle maps; triangle i was computed by rank i % n_ranks.
+int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p, float* sx, float* sy, float* sz) {
+    if (!m || handle < 0 || handle >= (int)m->fh.size()) return mfail(m, LUDWIG_EINVAL, "bad forces handle");
+    const int n = m->fh[handle].mesh[0]->n, W = (int)m->ctx.size();
+    std::vector<float> t[4];
+    float* dst[4] = {p, sx, sy, sz};
+    for (auto& v : t) v.resize(n);
+    for (int r = 0; r < W; ++r) {
+        int rc = ludwig_forces_download_maps(m->ctx[r], m->fh[handle].forces[r], t[0].data(), t[1].data(), t[2].data(), t[3].data());
+        if (rc) return mpass(m, m->ctx[r], rc);
+        for (int j = 0; j < 4; ++j) if (dst[j]) for (int i = r; i < n; i += W) dst[j][i] = t[j][i];
+    }
+    return LUDWIG_OK;
+}
+
+int64_t ludwig_multi_device_bytes(const ludwig_multi* m) {
+    int64_t b = 0;
+    if (m) for (ludwig_ctx* c : m->ctx) b += c->bytes;
+    return b;
 }
 
 }  // extern "C"

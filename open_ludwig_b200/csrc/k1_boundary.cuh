@@ -25,6 +25,13 @@ __device__ __forceinline__ float calc_eq(float rho, float ux, float uy, float uz
     return rho * w_k * (1.0f + 3.0f * cu + 4.5f * cu * cu - 1.5f * usq);
 }
 
+// Julia's Float32 power and logarithm, which the wall model calls (physics_kernels.jl:209,213): Base evaluates both in
+// Float64 and rounds once — x^y = Float32(exp2(log2(Float64(x)) * y)) (base/math.jl, pow_body for Float16 / Float32) and
+// log(::Float32) through the Float64 tables of base/special/log.jl.  Restated the same way here and in the CPU oracle, the
+// strict build matches the oracle bit for bit with the wall model on (libdevice powf / logf are 2-4 ulp functions).
+__device__ __forceinline__ float pow32(float x, float y) { return (float)exp2(log2((double)x) * (double)y); }
+__device__ __forceinline__ float log32(float x) { return (float)log((double)x); }
+
 struct Corner { float v[5]; bool ok; };
 
 __device__ __forceinline__ Corner get_blended(const K1Args& a, int pgx, int pgy, int pgz, int k, float w_k) {

@@ -8,7 +8,7 @@
 //
 // The floating-point expressions below are written in the reference's operation order.  This header
 // is compiled twice: k1_generic_strict.cu with -fmad=false (no FMA contraction: bit-comparable with
-// the CPU oracle apart from powf/logf) and k1_generic_fast.cu with contraction on.  In fast mode this
+// the CPU oracle) and k1_generic_fast.cu with contraction on.  In fast mode this
 // kernel only runs the blocks that are not BF_INTERIOR; those go to k1_interior.cu.
 //
 // One CTA = half a block (256 threads = 4 z-planes); a warp = 4 x-rows of one z-plane, so the in-block
@@ -114,11 +114,11 @@ __global__ void __launch_bounds__(256, 2) K1_KERNEL_NAME(const K1Args a) {
             float u_mag = sqrtf(ux * ux + uy * uy + uz * uz);
             float nu_visc = (a.tau - 0.5f) / 3.0f;
             if (u_mag > 1.0e-6f && nu_visc > 1.0e-10f) {
-                float u_tau = u_mag * powf(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * powf(2.0f * 8.3f, -1.0f / 7.0f);
+                float u_tau = u_mag * pow32(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * pow32(2.0f * 8.3f, -1.0f / 7.0f);
                 u_tau = fmaxf(u_tau, 1.0e-6f);
                 float y_p = u_tau * dist_wall / nu_visc;
                 if (y_p > 11.81f) {
-                    float u_plus_law = (1.0f / KAPPA) * logf(y_p) + 5.2f;
+                    float u_plus_law = (1.0f / KAPPA) * log32(y_p) + 5.2f;
                     if (u_plus_law > 0.1f) {
                         u_tau = u_tau * ((u_mag / u_tau) / u_plus_law);
                         u_tau = fmaxf(u_tau, 1.0e-6f);

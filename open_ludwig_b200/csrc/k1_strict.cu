@@ -1,0 +1,383 @@
+// k1_strict.cu — K1 in STRICT mode: the reference's exact FP32 operation order (physics_kernels.jl:62-354) on the
+// B200-native kernel structure of k1_fast.cu (one CTA per 8^3 block, a warp per z-plane, two x-adjacent cells per
+// thread, packed FP32x2 arithmetic, ghost blocks + pre-pass for refinement interfaces, remote neighbour blocks through
+// peer offsets).  Every class of block runs here: plain, plain + ghost neighbours, feature (obstacle / sponge / wall
+// model) and domain-face blocks.  Results are BIT-IDENTICAL to the CPU oracle (tests/test_k1_*_gpu.py,
+// tests/test_large_sizes_gpu.py); wall model included (Float32 power / logarithm evaluated in Float64 as Julia does, k1_boundary.cuh).
+//
+// How the packed arithmetic keeps the reference's roundings (this file is compiled with -fmad=false):
+//   * FADD2 rounds each half exactly like FADD;  a - b  is  FFMA2(b, -1, a): the product by -1 is exact, one rounding.
+//   * a * b  is  FFMA2(a, b, nz)  with nz = -0.0f passed as a KERNEL ARGUMENT: round(a b + (-0)) = round(a b), and because
+//     ptxas cannot see the value of nz it cannot contract the product into the next addition.  (ptxas 12.9 contracts
+//     mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, and folds a CONSTANT -0 addend away.)
+//   * terms the reference multiplies by a zero lattice component are skipped: x + (+-0) = x, and a sum that stays +-0 only
+//     feeds 1 + 3 cu etc., where the sign of zero cannot matter.  Division and square root are the IEEE ones.
+//   * the 27 pulled populations stay in registers between the moment sums, the Pi loop (which needs f_k - feq_k in k
+//     order) and the collision loop — the price of the reference's operation order (the fast build streams them).
+#include <climits>
+
+#include "ludwig_internal.h"
+
+namespace ludwig {
+namespace k1s {
+
+#include "k1_boundary.cuh"
+#include "k1_ghost.cuh"
+
+typedef float2 v2;
+__device__ __forceinline__ v2 V(float s) { return make_float2(s, s); }
+__device__ __forceinline__ v2 vadd(v2 a, v2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ v2 vsub(v2 a, v2 b) { return __ffma2_rn(b, V(-1.0f), a); }   // a - b, one rounding
+__device__ __forceinline__ v2 vneg(v2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ v2 vmaxs(v2 a, float s) { return make_float2(fmaxf(a.x, s), fmaxf(a.y, s)); }
+__device__ __forceinline__ v2 vsqrt(v2 a) { return make_float2(__fsqrt_rn(a.x), __fsqrt_rn(a.y)); }
+__device__ __forceinline__ v2 vdiv(v2 a, v2 b) { return make_float2(__fdiv_rn(a.x, b.x), __fdiv_rn(a.y, b.y)); }
+__device__ __forceinline__ void st2(float* p, v2 v) { __stcs(reinterpret_cast<float2*>(p), v); }
+__device__ __forceinline__ v2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+// packed product with the rounding of a * b (see the file header); NZ = (-0, -0) from the kernel arguments
+#define VMUL(a, b) __ffma2_rn((a), (b), NZ)
+
+__host__ __device__ constexpr int d2of(int k) { return (lat_cx(k) != 0) + (lat_cy(k) != 0) + (lat_cz(k) != 0); }
+
+// c . u in the reference's order ((cx*ux + cy*uy) + cz*uz), zero components skipped
+template <int K>
+__device__ __forceinline__ v2 cdot(v2 ux, v2 uy, v2 uz) {
+    constexpr int cx = lat_cx(K), cy = lat_cy(K), cz = lat_cz(K);
+    v2 r = V(0.f);
+    bool have = false;
+    if (cx != 0) { r = cx > 0 ? ux : vneg(ux); have = true; }
+    if (cy != 0) { r = have ? (cy > 0 ? vadd(r, uy) : vsub(r, uy)) : (cy > 0 ? uy : vneg(uy)); have = true; }
+    if (cz != 0) { r = have ? (cz > 0 ? vadd(r, uz) : vsub(r, uz)) : (cz > 0 ? uz : vneg(uz)); }
+    return r;
+}
+
+template <int K>
+__device__ __forceinline__ void moment_step(v2 val, v2& rho, v2& jx, v2& jy, v2& jz) {   // :144-148
+    constexpr int cx = lat_cx(K), cy = lat_cy(K), cz = lat_cz(K);
+    rho = K == 0 ? val : vadd(rho, val);
+    if (cx == 1) jx = vadd(jx, val); else if (cx == -1) jx = vsub(jx, val);
+    if (cy == 1) jy = vadd(jy, val); else if (cy == -1) jy = vsub(jy, val);
+    if (cz == 1) jz = vadd(jz, val); else if (cz == -1) jz = vsub(jz, val);
+}
+
+template <int K, int KEND>
+struct Unroll {
+    template <typename F> __device__ __forceinline__ static void run(F&& f) { f.template operator()<K>(); Unroll<K + 1, KEND>::run(f); }
+};
+template <int KEND>
+struct Unroll<KEND, KEND> {
+    template <typename F> __device__ __forceinline__ static void run(F&&) {}
+};
+
+// Wall-model force of one cell in the reference's operation order (physics_kernels.jl:206-236); scalar, near-wall cells only.
+__device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, float uy, float uz, float tau) {
+    float3 F = make_float3(0.f, 0.f, 0.f);
+    if (dist_wall > 0.0f && dist_wall < 10.0f) {
+        float u_mag = sqrtf(ux * ux + uy * uy + uz * uz);
+        float nu_visc = (tau - 0.5f) / 3.0f;
+        if (u_mag > 1.0e-6f && nu_visc > 1.0e-10f) {
+            float u_tau = u_mag * pow32(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * pow32(2.0f * 8.3f, -1.0f / 7.0f);
+            u_tau = fmaxf(u_tau, 1.0e-6f);
+            float y_p = u_tau * dist_wall / nu_visc;
+            if (y_p > 11.81f) {
+                float u_plus_law = (1.0f / KAPPA) * log32(y_p) + 5.2f;
+                if (u_plus_law > 0.1f) {
+                    u_tau = u_tau * ((u_mag / u_tau) / u_plus_law);
+                    u_tau = fmaxf(u_tau, 1.0e-6f);
+                }
+            }
+            float tau_wall = rho * u_tau * u_tau;
+            float tau_res = rho * nu_visc * (u_mag / dist_wall);
+            if (tau_wall > tau_res) {
+                float force_mag = (tau_wall - tau_res) / dist_wall;
+                F.x = -force_mag * ux / u_mag;
+                F.y = -force_mag * uy / u_mag;
+                F.z = -force_mag * uz / u_mag;
+            }
+        }
+    }
+    return F;
+}
+
+constexpr long long MISSING = LLONG_MIN;
+
+// FULL : obstacle / sponge / wall-model handling (per-block flag bits gate each feature uniformly)
+// VELFB: some axis neighbour may lack a velocity field (ghost block or domain face) -> the cell's own value (physics_utils.jl:69)
+// MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh
+template <bool FULL, bool VELFB, bool MISS>
+__global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
+    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
+    const int b = a.list[blockIdx.x];
+    const int t = threadIdx.x;
+    if (t < 27) {
+        const int nbi = a.nbr[(size_t)b * 27 + t];
+        s_fo[t] = nbi < 0 ? MISSING
+                  : nbi < a.nb ? (long long)nbi * (Q * BS3)
+                  : nbi < REMOTE_BASE ? a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3)
+                                      : a.roff_f[nbi - REMOTE_BASE];
+        s_vo[t] = nbi < 0 ? MISSING : nbi < a.nb ? (long long)nbi * (3 * BS3) : nbi < REMOTE_BASE ? MISSING : a.roff_v[nbi - REMOTE_BASE];
+    }
+    __syncthreads();
+    const v2 NZ = V(a.negzero);
+
+    const int p = t & 3, y = (t >> 2) & 7, z = t >> 5;
+    const int x0 = 2 * p, c0 = 2 * t;
+    uint32_t bflags = BF_INTERIOR;
+    int gx = 0, gy = 0, gz = 0;   // 1-based global coords of cell A (MISS only)
+    if (FULL) {
+        const int4 bc = *reinterpret_cast<const int4*>(a.bcoord + (size_t)b * 4);
+        bflags = (uint32_t)bc.w;
+        if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
+    }
+    const float* __restrict__ fin_own = a.f_in + (size_t)b * (Q * BS3) + c0;
+
+    int yoff[3], ydir[3], zoff[3], zdir[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int ys = y - (j - 1), zs = z - (j - 1);
+        yoff[j] = (ys & 7) * 8; ydir[j] = (ys < 0 ? 0 : (ys > 7 ? 2 : 1)) * 3;
+        zoff[j] = (zs & 7) * 64; zdir[j] = (zs < 0 ? 0 : (zs > 7 ? 2 : 1)) * 9;
+    }
+    const int dM = p > 0 ? 1 : 0, xM = p > 0 ? x0 - 1 : 7;
+    const int dP = p < 3 ? 1 : 2, xP = p < 3 ? x0 + 2 : 0;
+
+    // ---- pull-stream (:62-149); combo (jy,jz) yields the three consecutive directions k0-1, k0, k0+1
+    v2 f[27];
+#pragma unroll
+    for (int jzc = 0; jzc < 3; ++jzc) {
+#pragma unroll
+        for (int jyc = 0; jyc < 3; ++jyc) {
+            const int loc = zoff[jzc] + yoff[jyc], dir = zdir[jzc] + ydir[jyc];
+            const int k0 = 1 + 3 * jyc + 9 * jzc, kp = k0 + 1, km = k0 - 1;
+            const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
+            if (!MISS || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
+                const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
+                const float* __restrict__ PM = a.f_in + oM + (loc + xM);
+                const float* __restrict__ PP = a.f_in + oP + (loc + xP);
+                f[km] = make_float2(P0[km * BS3 + 1], PP[km * BS3]);   // cx=-1: sources x0+1, x0+2
+                f[k0] = ld2(P0 + k0 * BS3);
+                f[kp] = make_float2(PM[kp * BS3], P0[kp * BS3]);       // cx=+1: sources x0-1, x0
+            } else {
+                // some source block is missing: domain face (rare path)
+                if (o0 != MISSING) {
+                    const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
+                    f[k0] = ld2(P0 + k0 * BS3); f[kp].y = P0[kp * BS3]; f[km].x = P0[km * BS3 + 1];
+                } else {
+                    f[k0].x = pull_missing(a, fin_own, k0, gx, gy, gz); f[k0].y = pull_missing(a, fin_own + 1, k0, gx + 1, gy, gz);
+                    f[kp].y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
+                    f[km].x = pull_missing(a, fin_own, km, gx, gy, gz);
+                }
+                f[kp].x = oM != MISSING ? a.f_in[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
+                f[km].y = oP != MISSING ? a.f_in[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+            }
+        }
+    }
+
+    bool obsA = false, obsB = false;
+    if (FULL && (bflags & BF_OBSTACLE)) {
+        const uchar2 o = *reinterpret_cast<const uchar2*>(a.obstacle + (size_t)b * BS3 + c0);
+        obsA = o.x != 0; obsB = o.y != 0;
+    }
+    float* __restrict__ fout = a.f_out + (size_t)b * (Q * BS3) + c0;
+    float* __restrict__ vout = a.vel_out + (size_t)b * (3 * BS3) + c0;
+    float* __restrict__ rout = a.rho_out + (size_t)b * BS3 + c0;
+
+    // Full-way bounce-back (:154-166): f_out[26-k] = pulled f_k, vel = 0, rho = 1.  No arithmetic.
+    const bool anyobs = FULL && (obsA || obsB);
+    if (anyobs) {
+        if (obsA && obsB) {
+#pragma unroll
+            for (int k = 0; k < 27; ++k) st2(fout + (26 - k) * BS3, f[k]);
+            st2(vout, V(0.f)); st2(vout + BS3, V(0.f)); st2(vout + 2 * BS3, V(0.f)); st2(rout, V(1.0f));
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            if (obsA) fout[(26 - k) * BS3] = f[k].x; else fout[(26 - k) * BS3 + 1] = f[k].y;
+        }
+    }
+
+    // ---- moments in k order (:144-148)
+    v2 rho = V(0.f), jx = V(0.f), jy = V(0.f), jz = V(0.f);
+    Unroll<0, 27>::run([&]<int K>() { moment_step<K>(f[K], rho, jx, jy, jz); });
+
+    // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
+    v2 uE[3], uW[3], uN[3], uS[3], uT[3], uB[3];
+    {
+        const int row = z * 64 + y * 8;
+        const float* __restrict__ vo = a.vel_in + s_vo[13] + c0;
+        const long long oM = s_vo[12 + dM], oP = s_vo[13 + (dP - 1)];
+        const long long oN = s_vo[y < 7 ? 13 : 16], oS = s_vo[y > 0 ? 13 : 10], oT = s_vo[z < 7 ? 13 : 22], oB = s_vo[z > 0 ? 13 : 4];
+        const int lN = z * 64 + ((y + 1) & 7) * 8 + x0, lS = z * 64 + ((y - 1) & 7) * 8 + x0;
+        const int lT = ((z + 1) & 7) * 64 + y * 8 + x0, lB = ((z - 1) & 7) * 64 + y * 8 + x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const v2 own = ld2(vo + c * BS3);
+            uW[c] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + c * BS3] : own.x, own.x);
+            uE[c] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + c * BS3] : own.y);
+            uN[c] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + c * BS3) : own;
+            uS[c] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + c * BS3) : own;
+            uT[c] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + c * BS3) : own;
+            uB[c] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + c * BS3) : own;
+        }
+    }
+
+    rho = vmaxs(rho, 0.01f);                                          // :172
+    const v2 inv_rho = vdiv(V(1.0f), rho);
+    v2 ux = VMUL(jx, inv_rho), uy = VMUL(jy, inv_rho), uz = VMUL(jz, inv_rho);
+
+    // ---- sponge (:181-199).  Lanes with sp = 0 keep their bits: x * (1 - 0) + y * 0 = x.
+    if (FULL && (bflags & BF_SPONGE)) {
+        const v2 sp = ld2(a.sponge + (size_t)b * BS3 + c0);
+        const v2 om = vsub(V(1.0f), sp);
+        rho = vadd(VMUL(rho, om), VMUL(V(1.0f), sp));
+        ux = vadd(VMUL(ux, om), VMUL(V(a.u_inlet), sp));
+        uy = VMUL(uy, om);
+        uz = VMUL(uz, om);
+        if (a.sponge_blend == 1) {
+            Unroll<0, 27>::run([&]<int K>() {
+                const float feq_t = calc_eq(1.0f, a.u_inlet, 0.0f, 0.0f, lat_w(K), (float)lat_cx(K), (float)lat_cy(K), (float)lat_cz(K));
+                f[K] = vadd(VMUL(f[K], om), VMUL(V(feq_t), sp));
+            });
+        }
+    }
+
+    // ---- wall-model force (:202-236)
+    v2 Fx = V(0.f), Fy = V(0.f), Fz = V(0.f);
+    bool has_force = false;
+    if (FULL && a.wm == 1 && (bflags & BF_WALLDIST)) {
+        const v2 dw = ld2(a.wall_dist + (size_t)b * BS3 + c0);
+        if (dw.x > 0.0f && dw.x < 10.0f && !obsA) { float3 F = wall_force(dw.x, rho.x, ux.x, uy.x, uz.x, a.tau); Fx.x = F.x; Fy.x = F.y; Fz.x = F.z; }
+        if (dw.y > 0.0f && dw.y < 10.0f && !obsB) { float3 F = wall_force(dw.y, rho.y, ux.y, uy.y, uz.y, a.tau); Fx.y = F.x; Fy.y = F.y; Fz.y = F.z; }
+        has_force = true;
+    }
+    // u_eq = u + 0.5 F inv_rho with the PRE-sponge 1/rho (:238); without a force it is u (+0 changes no value)
+    v2 uxe = ux, uye = uy, uze = uz;
+    if (FULL && has_force) {
+        uxe = vadd(ux, VMUL(VMUL(V(0.5f), Fx), inv_rho));
+        uye = vadd(uy, VMUL(VMUL(V(0.5f), Fy), inv_rho));
+        uze = vadd(uz, VMUL(VMUL(V(0.5f), Fz), inv_rho));
+    }
+    const v2 usq = vadd(vadd(VMUL(uxe, uxe), VMUL(uye, uye)), VMUL(uze, uze));
+
+    // vel_out / rho_out (:155-158, :243-246)
+    if (anyobs) {
+        if (obsA) { vout[0] = 0.f; vout[BS3] = 0.f; vout[2 * BS3] = 0.f; rout[0] = 1.f; vout[1] = ux.y; vout[BS3 + 1] = uy.y; vout[2 * BS3 + 1] = uz.y; rout[1] = rho.y; }
+        else { vout[1] = 0.f; vout[BS3 + 1] = 0.f; vout[2 * BS3 + 1] = 0.f; rout[1] = 1.f; vout[0] = ux.x; vout[BS3] = uy.x; vout[2 * BS3] = uz.x; rout[0] = rho.x; }
+    } else {
+        st2(vout, ux); st2(vout + BS3, uy); st2(vout + 2 * BS3, uz); st2(rout, rho);
+    }
+
+    // ---- WALE (:251-300) in the reference's expression order
+    v2 omega;
+    {
+        const v2 h = V(0.5f);
+        const v2 g11 = VMUL(h, vsub(uE[0], uW[0])), g12 = VMUL(h, vsub(uN[0], uS[0])), g13 = VMUL(h, vsub(uT[0], uB[0]));
+        const v2 g21 = VMUL(h, vsub(uE[1], uW[1])), g22 = VMUL(h, vsub(uN[1], uS[1])), g23 = VMUL(h, vsub(uT[1], uB[1]));
+        const v2 g31 = VMUL(h, vsub(uE[2], uW[2])), g32 = VMUL(h, vsub(uN[2], uS[2])), g33 = VMUL(h, vsub(uT[2], uB[2]));
+#define DOT3(a1, b1, a2, b2, a3, b3) vadd(vadd(VMUL(a1, b1), VMUL(a2, b2)), VMUL(a3, b3))
+        const v2 gsq11 = DOT3(g11, g11, g12, g21, g13, g31), gsq12 = DOT3(g11, g12, g12, g22, g13, g32), gsq13 = DOT3(g11, g13, g12, g23, g13, g33);
+        const v2 gsq21 = DOT3(g21, g11, g22, g21, g23, g31), gsq22 = DOT3(g21, g12, g22, g22, g23, g32), gsq23 = DOT3(g21, g13, g22, g23, g23, g33);
+        const v2 gsq31 = DOT3(g31, g11, g32, g21, g33, g31), gsq32 = DOT3(g31, g12, g32, g22, g33, g32), gsq33 = DOT3(g31, g13, g32, g23, g33, g33);
+        const v2 tr_gsq = vadd(vadd(gsq11, gsq22), gsq33);
+        const v2 tr_term = vdiv(tr_gsq, V(3.0f));
+        const v2 Sd11 = vsub(gsq11, tr_term), Sd22 = vsub(gsq22, tr_term), Sd33 = vsub(gsq33, tr_term);
+        const v2 Sd12 = VMUL(h, vadd(gsq12, gsq21)), Sd13 = VMUL(h, vadd(gsq13, gsq31)), Sd23 = VMUL(h, vadd(gsq23, gsq32));
+        const v2 S12 = VMUL(h, vadd(g12, g21)), S13 = VMUL(h, vadd(g13, g31)), S23 = VMUL(h, vadd(g23, g32));
+        const v2 OP1 = vadd(DOT3(Sd11, Sd11, Sd22, Sd22, Sd33, Sd33), VMUL(V(2.0f), DOT3(Sd12, Sd12, Sd13, Sd13, Sd23, Sd23)));
+        const v2 OP2 = vadd(DOT3(g11, g11, g22, g22, g33, g33), VMUL(V(2.0f), DOT3(S12, S12, S13, S13, S23, S23)));
+#undef DOT3
+        const v2 OP1_32 = VMUL(OP1, vsqrt(OP1));
+        const v2 OP2_52 = VMUL(VMUL(OP2, OP2), vsqrt(vmaxs(OP2, 1.0e-12f)));
+        const v2 denom = vadd(OP2_52, VMUL(OP1, vsqrt(vsqrt(vmaxs(OP1, 1.0e-12f)))));
+        const float cw2 = __fmul_rn(a.c_wale, a.c_wale);
+        float ne0 = 0.0f, ne1 = 0.0f;
+        if (OP1.x > 1.0e-12f && denom.x > 1.0e-12f) ne0 = __fdiv_rn(__fmul_rn(cw2, OP1_32.x), denom.x);
+        if (OP1.y > 1.0e-12f && denom.y > 1.0e-12f) ne1 = __fdiv_rn(__fmul_rn(cw2, OP1_32.y), denom.y);
+        const v2 nu_eddy = vmaxs(make_float2(ne0, ne1), a.nu_bg);
+        const v2 tau_turb = vadd(V(a.tau), VMUL(nu_eddy, V(3.0f)));
+        omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
+    }
+
+    // ---- Pi loop (:308-322): f[k] is replaced by feq_k
+    const v2 usq15 = VMUL(V(1.5f), usq);
+    const v2 rw0 = VMUL(rho, V(lat_w(13))), rw1 = VMUL(rho, V(lat_w(12))), rw2 = VMUL(rho, V(lat_w(9))), rw3 = VMUL(rho, V(lat_w(0)));
+    v2 Pxx = V(0.f), Pyy = V(0.f), Pzz = V(0.f), Pxy = V(0.f), Pyz = V(0.f), Pzx = V(0.f);
+    Unroll<0, 27>::run([&]<int K>() {
+        constexpr int cx = lat_cx(K), cy = lat_cy(K), cz = lat_cz(K);
+        const v2 rw = d2of(K) == 0 ? rw0 : d2of(K) == 1 ? rw1 : d2of(K) == 2 ? rw2 : rw3;
+        v2 poly;
+        if (K == 13) poly = vsub(V(1.0f), usq15);                                  // cu = 0: ((1 + 0) + 0) - 1.5 usq
+        else {
+            const v2 cu = cdot<K>(uxe, uye, uze);
+            poly = vsub(vadd(vadd(V(1.0f), VMUL(V(3.0f), cu)), VMUL(VMUL(V(4.5f), cu), cu)), usq15);
+        }
+        const v2 feq = VMUL(rw, poly);
+        const v2 fneq = vsub(f[K], feq);
+        f[K] = feq;
+        if (cx != 0) Pxx = vadd(Pxx, fneq);
+        if (cy != 0) Pyy = vadd(Pyy, fneq);
+        if (cz != 0) Pzz = vadd(Pzz, fneq);
+        if (cx * cy == 1) Pxy = vadd(Pxy, fneq); else if (cx * cy == -1) Pxy = vsub(Pxy, fneq);
+        if (cy * cz == 1) Pyz = vadd(Pyz, fneq); else if (cy * cz == -1) Pyz = vsub(Pyz, fneq);
+        if (cz * cx == 1) Pzx = vadd(Pzx, fneq); else if (cz * cx == -1) Pzx = vsub(Pzx, fneq);
+    });
+
+    // ---- collision loop (:324-354):  f_out = (feq + (1 - omega) f_neq_reg) + (1 - omega/2) force_term
+    const float cs2 = 1.0f / 3.0f;
+    const float qa = 1.0f - cs2, qb = 0.0f - cs2;                     // Q = c*c - CS2 for |c| = 1 and c = 0
+    const v2 PQ[3][2] = {{VMUL(Pxx, V(qa)), VMUL(Pxx, V(qb))}, {VMUL(Pyy, V(qa)), VMUL(Pyy, V(qb))}, {VMUL(Pzz, V(qa)), VMUL(Pzz, V(qb))}};
+    const v2 om1 = vsub(V(1.0f), omega);
+    v2 hw = V(0.f);
+    if (FULL && has_force) hw = vsub(V(1.0f), VMUL(V(0.5f), omega));
+    Unroll<0, 27>::run([&]<int K>() {
+        constexpr int cx = lat_cx(K), cy = lat_cy(K), cz = lat_cz(K);
+        // Pi_xx Q_xx + Pi_yy Q_yy + Pi_zz Q_zz
+        const v2 diag = vadd(vadd(PQ[0][cx != 0 ? 0 : 1], PQ[1][cy != 0 ? 0 : 1]), PQ[2][cz != 0 ? 0 : 1]);
+        // Pi_xy cx cy + Pi_yz cy cz + Pi_zx cz cx
+        v2 off = V(0.f);
+        bool have = false;
+        if (cx * cy != 0) { off = cx * cy > 0 ? Pxy : vneg(Pxy); have = true; }
+        if (cy * cz != 0) { off = have ? (cy * cz > 0 ? vadd(off, Pyz) : vsub(off, Pyz)) : (cy * cz > 0 ? Pyz : vneg(Pyz)); have = true; }
+        if (cz * cx != 0) { off = have ? (cz * cx > 0 ? vadd(off, Pzx) : vsub(off, Pzx)) : (cz * cx > 0 ? Pzx : vneg(Pzx)); have = true; }
+        const v2 inner = have ? vadd(diag, VMUL(V(2.0f), off)) : diag;     // + 2 * 0 changes nothing
+        const v2 fnr = VMUL(V(lat_w(K) * 4.5f), inner);
+        v2 out = vadd(f[K], VMUL(om1, fnr));
+        if (FULL && has_force) {
+            // force_term = (w 3) * (((cx - ux + 3 cu cx) Fx + (cy - uy + 3 cu cy) Fy) + (cz - uz + 3 cu cz) Fz), cu from u_eq, u from u
+            const v2 cu = K == 13 ? V(0.f) : cdot<K>(uxe, uye, uze);
+            const v2 cu3 = VMUL(V(3.0f), cu);
+            // (c_a - u_a) + (3 cu) c_a : a zero component contributes (0 - u_a) + (+-0) = -u_a
+            const v2 ax = cx != 0 ? vadd(vsub(V((float)cx), ux), cx > 0 ? cu3 : vneg(cu3)) : vsub(V(0.f), ux);
+            const v2 ay = cy != 0 ? vadd(vsub(V((float)cy), uy), cy > 0 ? cu3 : vneg(cu3)) : vsub(V(0.f), uy);
+            const v2 az = cz != 0 ? vadd(vsub(V((float)cz), uz), cz > 0 ? cu3 : vneg(cu3)) : vsub(V(0.f), uz);
+            const v2 dotF = vadd(vadd(VMUL(ax, Fx), VMUL(ay, Fy)), VMUL(az, Fz));
+            const v2 force_term = VMUL(V(lat_w(K) * 3.0f), dotF);
+            out = vadd(out, VMUL(hw, force_term));
+        }
+        if (!anyobs) st2(fout + K * BS3, out);
+        else if (obsA) fout[K * BS3 + 1] = out.y;
+        else fout[K * BS3] = out.x;
+    });
+}
+
+}  // namespace k1s
+
+void launch_k1s_plain(const K1Args& a, cudaStream_t s) {
+    if (a.n_list > 0) k1s::k1_strict_kernel<false, false, false><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) {
+    if (a.n_list > 0) k1s::k1_strict_kernel<false, true, false><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_k1s_feat(const K1Args& a, cudaStream_t s) {
+    if (a.n_list > 0) k1s::k1_strict_kernel<true, true, false><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_k1s_full(const K1Args& a, cudaStream_t s) {
+    if (a.n_list > 0) k1s::k1_strict_kernel<true, true, true><<<a.n_list, 256, 0, s>>>(a);
+}
+void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s) {
+    if (g.n > 0) k1s::ghost_interp_kernel<<<(g.n + 127) / 128, 128, 0, s>>>(g);
+}
+
+}  // namespace ludwig

@@ -280,27 +280,30 @@ void launch_halo_unpack(const Level& L, int buf, cudaStream_t s) {
 // Cross-GPU barrier (multi-GPU, one process per GPU): every rank owns MAX_RANKS epoch slots in device memory that its
 // peers have mapped through CUDA IPC.  Lane r writes this rank's epoch into peer r's slot [my rank] (a store over
 // NVLink), then spins on the local slot [r] until peer r has done the same.  Stream-ordered, no host round trip, ~5 us.
-// Each rank runs on its OWN GPU, so the spinning kernels never wait for a kernel queued behind them; a ~20 s time-out
-// (a peer died or the ranks issued different numbers of barriers) sets an error flag instead of hanging the GPU.
+// Each rank runs on its OWN GPU, so the spinning kernels never wait for a kernel queued behind them; a time-out (option
+// barrier_timeout_s, default 20 s of %globaltimer: a peer died or the ranks issued different numbers of barriers) sets a STICKY
+// error flag in mapped host memory instead of hanging the GPU; the host turns it into LUDWIG_ESTATE from every later call.
 struct BarrierPeers { unsigned int* slot[MAX_RANKS]; };
-__global__ void peer_barrier_kernel(BarrierPeers peers, unsigned int* own, int rank, int world, unsigned int epoch, int* err) {
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__global__ void peer_barrier_kernel(BarrierPeers peers, unsigned int* own, int rank, int world, unsigned int epoch, volatile int* err, volatile int* err_host, long long timeout_ns) {
     const int r = threadIdx.x;
     if (r < world && r != rank) {
         __threadfence_system();
-        *((volatile unsigned int*)(peers.slot[r] + rank)) = epoch;
+        *((volatile unsigned int*)(peers.slot[r] + rank)) = epoch;   // always publish: the peers must not wait for a failed rank's epoch
         __threadfence_system();
-        const long long t0 = clock64();
+        if (*err != 0) return;                                       // sticky: a context whose barrier timed out never spins again
+        const unsigned long long t0 = global_ns();
         while ((int)(*((volatile unsigned int*)(own + r)) - epoch) < 0) {
-            if (clock64() - t0 > 40000000000LL) { *err = 1; break; }
+            if ((long long)(global_ns() - t0) > timeout_ns) { *err = 1; *err_host = 1; __threadfence_system(); break; }
             __nanosleep(100);
         }
         __threadfence_system();
     }
 }
-void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s) {
+void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, int* err_host, long long timeout_ns, cudaStream_t s) {
     BarrierPeers p;
     for (int r = 0; r < MAX_RANKS; ++r) p.slot[r] = peer_slots[r];
-    peer_barrier_kernel<<<1, 32, 0, s>>>(p, own, rank, world, epoch, err);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(p, own, rank, world, epoch, err, err_host, timeout_ns);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -436,11 +439,14 @@ void launch_integrate_forces(const ludwig_mesh& M, ludwig_forces& F, float offx,
 
 // ---------------------------------------------------------------------------------------------
 // R1  flow statistics over the non-obstacle cells of one level: n, sum(rho), min, max, max|u|, sum(rho*u^2).
-// partial layout per CTA: [n, rho_sum, rho_min, rho_max, v_max, ke]
+// partial layout per CTA: [n, rho_sum, rho_min, rho_max, v_max, ke].  Julia's minimum / maximum (diagnostics.jl:70-77) propagate
+// NaN and fminf / fmaxf drop it, so NaN densities / velocities are tracked separately and turn the CTA's min / max / v_max
+// partials into NaN: the rho_min column of the console table is the reference's only divergence indicator.
 __global__ void __launch_bounds__(256) flow_stats_kernel(const float* __restrict__ rho, const float* __restrict__ vel,
                                                          const uint8_t* __restrict__ obstacle, size_t ncell, double* __restrict__ partials) {
     double n = 0, rs = 0, ke = 0;
     float rmin = INFINITY, rmax = -INFINITY, vmax = 0.f;
+    int bad = 0;   // bit 0: NaN density, bit 1: NaN velocity
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (size_t)gridDim.x * blockDim.x) {
         if (obstacle[c]) continue;
         size_t b = c >> 9, loc = c & 511;
@@ -448,10 +454,14 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float* __restrict
         float r = rho[c], ux = vel[vi], uy = vel[vi + BS3], uz = vel[vi + 2 * BS3];
         float v2 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz));
         n += 1; rs += r; ke += (double)__fmul_rn(r, v2);
+        bad |= (r != r ? 1 : 0) | (v2 != v2 ? 2 : 0);
         rmin = fminf(rmin, r); rmax = fmaxf(rmax, r); vmax = fmaxf(vmax, __fsqrt_rn(v2));
     }
     __shared__ double s_d[8][3];
     __shared__ float s_f[8][3];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -459,6 +469,7 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float* __restrict
         rmin = fminf(rmin, __shfl_down_sync(0xffffffffu, rmin, o)); rmax = fmaxf(rmax, __shfl_down_sync(0xffffffffu, rmax, o));
         vmax = fmaxf(vmax, __shfl_down_sync(0xffffffffu, vmax, o));
     }
+    if (bad) atomicOr(&s_bad, bad);
     if (lane == 0) { s_d[warp][0] = n; s_d[warp][1] = rs; s_d[warp][2] = ke; s_f[warp][0] = rmin; s_f[warp][1] = rmax; s_f[warp][2] = vmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -466,8 +477,10 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float* __restrict
             n += s_d[w][0]; rs += s_d[w][1]; ke += s_d[w][2];
             rmin = fminf(rmin, s_f[w][0]); rmax = fmaxf(rmax, s_f[w][1]); vmax = fmaxf(vmax, s_f[w][2]);
         }
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
         double* o = partials + (size_t)blockIdx.x * 6;
-        o[0] = n; o[1] = rs; o[2] = rmin; o[3] = rmax; o[4] = vmax; o[5] = ke;
+        o[0] = n; o[1] = rs; o[2] = (s_bad & 1) ? qnan : (double)rmin; o[3] = (s_bad & 1) ? qnan : (double)rmax;
+        o[4] = (s_bad & 2) ? qnan : (double)vmax; o[5] = ke;
     }
 }
 void launch_flow_stats(const Level& L, const float* rho, const float* vel, double* d_partials, int nparts, cudaStream_t s) {

@@ -184,10 +184,18 @@ struct ludwig_ctx {
     cudaEvent_t ev_pre_fork = nullptr, ev_pre = nullptr;
     cudaStream_t halo_stream = nullptr;      // halo import (multi-GPU), concurrent with the K1 launch over interior blocks
     cudaEvent_t ev_halo = nullptr, ev_halo_fork = nullptr;
-    bool use_mirror = false;
-    bool rcb = false;                        // LUDWIG_PARTITION=rcb: per-level recursive coordinate bisection instead of Morton ranges
-    bool fork_full = false;                  // LUDWIG_FORK_FULL: domain-face K1 launch concurrent with the plain launch on large levels
-    int fork_max_blocks = 40000;             // levels above this are HBM-bound: concurrency gains nothing there
+    // options (ludwig_ctx_set_option)
+    bool use_mirror = false;                 // "halo_mirror": packed halo exchange into local mirrors instead of in-kernel NVLink pulls
+    int partition_mode = 0;                  // "partition": 0 Morton ranges / aligned plan, 1 per-level RCB, 2 RCB cutting y and z only
+    bool fork_full = false;                  // "fork_full": domain-face K1 launch concurrent with the plain launch on large levels
+    int fork_max_blocks = 40000;             // "fork_max_blocks": levels above this are HBM-bound, concurrency gains nothing there
+    bool use_side_streams = true;            // "single_stream" = 1 turns every concurrent launch off
+    bool serial_prepass = false;             // "serial_prepass"
+    bool opt_block_prepass = false;          // "prepass" = block
+    bool opt_strict_generic = false;         // "strict_generic"
+    bool verbose = false;                    // "verbose"
+    std::string remote_order = "morton";     // "remote_order"
+    double barrier_timeout_s = 20.0;         // "barrier_timeout_s"
     std::vector<ludwig::Level*> levels;
     std::string err;
     int64_t bytes = 0;
@@ -199,13 +207,18 @@ struct ludwig_ctx {
     std::vector<uint64_t> plan_keys;        // [world+1] cut keys at finest-level resolution
     int plan_levels = 0;
     bool peers_attached = false;
-    void (*barrier_cb)(void*) = nullptr;   // cross-rank barrier, stream-ordered or blocking (multi-GPU only)
+    bool group_managed = false;             // one of the contexts of a ludwig_multi: barriers are placed by the group driver
+    size_t p7 = (size_t)-1;                 // open "whole level step" profiling bracket
+    int (*barrier_cb)(void*) = nullptr;    // cross-rank barrier, stream-ordered or blocking (multi-GPU only); non-zero = failed
     void* barrier_user = nullptr;
     std::vector<void*> ipc_opened;
     // native peer-flag barrier (used when no callback is registered)
     unsigned int* d_bar = nullptr;            // [MAX_RANKS] epoch slots, written by the peers
     unsigned int* peer_bar[ludwig::MAX_RANKS] = {};   // the peers' slot arrays (IPC mappings)
-    int* d_bar_err = nullptr;
+    int* d_bar_err = nullptr;                 // the same flag in device memory (checked by the kernel before it spins)
+    int* h_bar_err = nullptr;                 // time-out flag in mapped pinned host memory (the barrier kernel writes, the host reads without sync)
+    int* d_bar_err_dev = nullptr;             // its device address
+    bool bar_failed = false;                  // sticky: once a barrier failed every stepping / result call returns LUDWIG_ESTATE
     unsigned int bar_epoch = 0;
     int64_t launches = 0;
     // K1 profiling (ludwig_profile_enable)
@@ -239,12 +252,12 @@ struct K1Args {
     const int32_t* pptr; int pdimx, pdimy, pdimz;
     float tau, tau_parent, c_wale, nu_bg, u_inlet, inlet_turb, tw;
     int is_l1, is_symmetric, nxg, nyg, nzg, wm, seed, use_temporal, sponge_blend;
+    float negzero;          // -0.0f, opaque to ptxas: the strict build's packed multiply is FFMA2(a, b, negzero) (k1_strict.cu)
 };
 
-// k1_generic_strict.cu (compiled with -fmad=false): the parity build, one thread per cell, reference operation order
+// k1_generic_strict.cu (compiled with -fmad=false): one thread per cell, every branch of the reference inside the kernel
+// (in-kernel interface interpolation).  Cross-check only (option "strict_generic"); not on the default path.
 void launch_k1_generic_strict(const K1Args& a, cudaStream_t s);
-// k1_strict_packed.cu (-fmad=false): the same bits for plain interior blocks, two cells per thread, packed FP32x2
-void launch_k1_strict_packed(const K1Args& a, cudaStream_t s);
 // Arguments of the interface-halo pre-pass (k1_fast.cu ghost_interp_kernel)
 struct GhostArgs {
     const int32_t* gcell;    // [n] ghost group id  g*64 + qz*16 + qy*4 + qx  (a group = the 2x2x2 fine cells of one parent cell)
@@ -267,7 +280,14 @@ void launch_k1_plain(const K1Args& a, cudaStream_t s);
 void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s);
 void launch_k1_feat(const K1Args& a, cudaStream_t s);   // features (obstacle/sponge/wall model), all 26 neighbours present
 void launch_k1_full(const K1Args& a, cudaStream_t s);   // features + missing neighbours (domain faces)
-void launch_ghost_interp(const GhostArgs& g, cudaStream_t s);
+void launch_ghost_interp(const GhostArgs& g, bool block_variant, cudaStream_t s);
+// k1_strict.cu (-fmad=false): the same four classes and the pre-pass in the reference's operation order (bit-exact
+// against the CPU oracle), packed FP32x2
+void launch_k1s_plain(const K1Args& a, cudaStream_t s);
+void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s);
+void launch_k1s_feat(const K1Args& a, cudaStream_t s);
+void launch_k1s_full(const K1Args& a, cudaStream_t s);
+void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s);
 
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
@@ -282,7 +302,7 @@ void launch_output_gather(const int32_t* sel, int n, const float* rho, const flo
                           uint8_t* o_obs, cudaStream_t s);
 void launch_halo_pack(const Level& L, int buf, cudaStream_t s);
 void launch_halo_unpack(const Level& L, int buf, cudaStream_t s);
-void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, cudaStream_t s);
+void launch_peer_barrier(unsigned int* const* peer_slots, unsigned int* own, int rank, int world, unsigned int epoch, int* err, int* err_host, long long timeout_ns, cudaStream_t s);
 void launch_map_stresses(const Level& L, const PeerPtrs& rho, const PeerPtrs& vel, const PeerBytes& obstacle, const ludwig_mesh& M,
                          ludwig_forces& F, float dx, float offx, float offy, float offz, float pscale, float sscale, int radius,
                          int tri_first, int tri_stride, cudaStream_t s);

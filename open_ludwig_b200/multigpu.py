@@ -27,9 +27,8 @@ def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = 
 
     barrier = "native" (default): the library's own peer-flag barrier kernel (flag stores over NVLink, stream-ordered,
     no host call per barrier).  barrier = "nccl": a stream-ordered NCCL all-reduce of one float registered through
-    ludwig_set_barrier_callback (the round-1 path, kept for A/B measurements; LUDWIG_BARRIER=nccl selects it)."""
-    import os
-    barrier = barrier or os.environ.get("LUDWIG_BARRIER", "native")
+    ludwig_set_barrier_callback (the round-1 path, kept for A/B measurements)."""
+    barrier = barrier or "native"
     world = dist.get_world_size()
     mine = ctx.ipc_export()
     t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
@@ -61,6 +60,13 @@ def reduce_stats(stats: dict, device: torch.device) -> dict:
     mx = torch.tensor([stats["rho_max"], stats["v_max"]], dtype=torch.float64, device=device)
     dist.all_reduce(s); dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     n = float(s[0])
+    # torch's MIN / MAX all-reduce drop NaN like fminf; the library reports a NaN density / velocity as NaN min / max, keep it
+    bad = torch.tensor([float(np.isnan(stats["rho_min"]) or np.isnan(stats["rho_max"])), float(np.isnan(stats["v_max"]))], dtype=torch.float64, device=device)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if float(bad[0]) > 0:
+        mn[0] = float("nan"); mx[0] = float("nan")
+    if float(bad[1]) > 0:
+        mx[1] = float("nan")
     return {"n_fluid": n, "rho_mean": float(s[1]) / max(n, 1.0), "rho_min": float(mn[0]), "rho_max": float(mx[0]),
             "v_max": float(mx[1]), "kinetic_energy": float(s[2])}
 
@@ -71,3 +77,129 @@ def reduce_aero(aero: dict, device: torch.device) -> dict:
     t = torch.tensor([aero[k] for k in keys], dtype=torch.float64, device=device)
     dist.all_reduce(t)
     return dict(zip(keys, t.tolist()))
+
+
+def load_domain_shared(name: str, log=None):
+    """The domain of a named case on every rank of the process group: rank 0 builds it with every host thread and the
+    other ranks map the arrays from a private /dev/shm directory (mkdtemp, 0700, name broadcast by rank 0: nobody else can
+    plant a pickle there).  Returns (domain, build seconds)."""
+    import shutil
+    import tempfile
+    import time
+    from .host import domain as D
+    from .host.cases import CASE_OVERRIDES, case_dir
+    mg = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if mg else (0, 1)
+    case, ov = CASE_OVERRIDES[name]
+    t0 = time.time()
+    if world > 1:
+        box = [tempfile.mkdtemp(prefix="ludwig_domain_", dir="/dev/shm") if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        cache = box[0]
+        if rank == 0:
+            dom = D.load_case(case_dir(case), ov, verbose=False, build_tri_map=False)
+            D.save_domain(dom, cache)
+        dist.barrier()
+        if rank != 0:
+            dom = D.load_domain(cache)
+        dist.barrier()
+        if rank == 0:
+            shutil.rmtree(cache, ignore_errors=True)     # the mappings stay valid after the unlink
+    else:
+        dom = D.load_case(case_dir(case), ov, verbose=False, build_tri_map=False)
+    build_s = time.time() - t0
+    if log is not None and rank == 0:
+        log(f"[strong] {name}: domain build {build_s:.1f}s, {dom.total_cells / 1e6:.1f} M cells, {dom.cell_updates_per_coarse_step / 1e6:.0f} M updates per coarse step")
+    return dom, build_s
+
+
+def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = False, options: dict | None = None, plan: bool = False,
+                    ramp_steps: int | None = None, profile_steps: int = 0, log=None, dom=None, all_ranks_levels: bool = False) -> dict:
+    """One strong-scaling measurement of a named case (open_ludwig_b200.host.cases) over the ranks of the current process
+    group (or a single GPU when torch.distributed is not initialised): every rank creates its partitioned context from the
+    shared domain (load_domain_shared), attaches the peers and steps `steps` coarse steps along the driver's cosine ramp
+    (main.jl:168-176, one batch per step).  Device time = max over ranks of CUDA events on the library's stream.
+    Returns the record (identical on every rank)."""
+    import time
+    from .solver import make_params, ramp_velocity
+
+    mg = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if mg else (0, 1)
+    dev = torch.device("cuda", local_rank)
+    build_s = 0.0
+    if dom is None:
+        dom, build_s = load_domain_shared(name, log)
+    t0 = time.time()
+    ctx = cabi.Context(device=local_rank, options=options)
+    try:
+        if world > 1:
+            ctx.set_partition(rank, world)
+            if plan:
+                ctx.set_partition_plan(dom.levels)
+        for lv in dom.levels:
+            ctx.add_level(lv)
+        if world > 1:
+            attach_peers(ctx, dev)
+        m = dom.mesh
+        mesh = ctx.create_mesh(m.centers, m.normals, m.areas)
+        p = dom.params
+        forces = ctx.create_forces(mesh, p.rho_physical, p.u_physical, p.reference_area, p.reference_chord, p.moment_center, dom.cfg.symmetric)
+        ctx.init_equilibrium()
+        params = make_params(dom, strict=strict)
+        ctx.sync()
+        upload_s = time.time() - t0
+        ramp = ramp_steps or dom.cfg.ramp_steps
+        stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+        t = 1
+        for _ in range(2):                                     # warm-up (builds the lazily built tables)
+            ctx.step_batch(t, 1, ramp_velocity(dom.cfg.u_target, t, ramp), params); t += 1
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ctx.launch_count()
+        if mg:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.step_batch(t, 1, ramp_velocity(dom.cfg.u_target, t, ramp), params); t += 1
+        e1.record(stream)
+        ctx.sync()
+        launches = ctx.launch_count() - n0
+        tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if mg:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm[0]) / steps
+        levels_ms = None
+        if profile_steps > 0:                                  # per-level / per-class device time (separate, untimed pass)
+            ctx.profile_enable(True)
+            for _ in range(profile_steps):
+                ctx.step_batch(t, 1, ramp_velocity(dom.cfg.u_target, t, ramp), params); t += 1
+            ctx.sync()
+            ctx.profile_read()
+            levels_ms = [{k: v / profile_steps for k, v in d.items()} for d in ctx.profile_levels()]
+            ctx.profile_enable(False)
+        if mg:
+            dist.barrier()
+        aero = ctx.compute_aerodynamics(forces, len(dom.levels) - 1, p.mesh_offset, p.velocity_scale, p.rho_physical, 5)
+        stats = ctx.flow_stats(0)
+        if mg:
+            aero = reduce_aero(aero, dev); stats = reduce_stats(stats, dev)
+        blocks = [len(ctx.local_blocks(i)) for i in range(len(dom.levels))]
+        all_levels = None
+        if all_ranks_levels and mg and levels_ms is not None:
+            box = [None] * world
+            dist.all_gather_object(box, {"blocks": blocks, "levels_ms": levels_ms})
+            all_levels = box
+        gb = ctx.device_bytes() / 1e9
+        if mg:
+            dist.barrier()
+    finally:
+        ctx.close()
+    upd = dom.cell_updates_per_coarse_step
+    return {"case": name, "n_gpus": world, "cells": dom.total_cells, "levels": len(dom.levels), "cell_updates_per_coarse_step": upd,
+            "coarse_steps": steps, "steps_run": t - 1, "ramp_steps": ramp, "ms_per_coarse_step": ms, "mlups_true": upd / (ms * 1e-3) / 1e6,
+            "mlups_reference_style": dom.total_cells / (ms * 1e-3) / 1e6, "fp_mode": "strict" if strict else "fast",
+            "Cd": aero["Cd"], "Cl": aero["Cl"], "rho_min": stats["rho_min"], "rho_max": stats["rho_max"], "v_max": stats["v_max"],
+            "partition": (options or {}).get("partition", "plan" if plan else "morton"), "options": options or {},
+            "blocks_rank0": blocks, "device_gb_rank0": gb, "launches_rank0": int(launches), "rank0_levels_ms": levels_ms, "all_ranks": all_levels,
+            "domain_build_s": build_s, "upload_s": upload_s}

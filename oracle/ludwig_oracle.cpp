@@ -71,6 +71,13 @@ struct Lattice {
 const Lattice LAT;
 
 // physics_utils.jl:17-22
+// Julia's x^y and log(x) for Float32 (the wall model, physics_kernels.jl:211,216): Base evaluates both in Float64 and rounds
+// once — base/math.jl `pow_body(x::T, y::T) where T<:Union{Float16,Float32} = T(exp2(log2(abs(widen(x))) * y))`, and
+// base/special/log.jl computes log(::Float32) with Float64 tables.  glibc's powf / logf are 0.8-ulp functions of their own and
+// would differ from that in ~30 % of the calls.
+inline float pow32(float x, float y) { return (float)std::exp2(std::log2((double)x) * (double)y); }
+inline float log32(float x) { return (float)std::log((double)x); }
+
 inline uint32_t gpu_hash(int32_t x) {
     uint32_t h = static_cast<uint32_t>(x);
     h = (h ^ (h >> 16)) * 0x85ebca6bu;
@@ -336,12 +343,12 @@ void stream_collide_cell(Level& L, const Parent& P, const StepArgs& A, float* f_
             float u_mag = std::sqrt(ux * ux + uy * uy + uz * uz);
             float nu_visc = (tau_molecular - 0.5f) / 3.0f;
             if (u_mag > 1.0e-6f && nu_visc > 1.0e-10f) {
-                float u_tau = u_mag * std::pow(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) *
-                              std::pow(2.0f * 8.3f, -1.0f / 7.0f);
+                float u_tau = u_mag * pow32(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) *
+                              pow32(2.0f * 8.3f, -1.0f / 7.0f);
                 u_tau = std::max(u_tau, 1.0e-6f);
                 float y_p = u_tau * dist_wall / nu_visc;
                 if (y_p > 11.81f) {
-                    float u_plus_law = (1.0f / KAPPA) * std::log(y_p) + 5.2f;
+                    float u_plus_law = (1.0f / KAPPA) * log32(y_p) + 5.2f;
                     if (u_plus_law > 0.1f) {
                         u_tau = u_tau * ((u_mag / u_tau) / u_plus_law);
                         u_tau = std::max(u_tau, 1.0e-6f);
@@ -832,18 +839,21 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
     size_t s = 512 * (size_t)L.nb;
     double n_fluid = 0, rho_sum = 0, ke = 0;
     float rho_min = INFINITY, rho_max = -INFINITY, v_max = 0.0f;
+    bool nan_rho = false, nan_v = false;   // Julia's minimum / maximum propagate NaN (diagnostics.jl:70-77): a blown-up run must not look healthy
     for (size_t c = 0; c < s; ++c) {
         if (L.obstacle[c]) continue;
         n_fluid += 1;
         float r = L.rho[c];
         float v2 = L.vel[c] * L.vel[c] + L.vel[c + s] * L.vel[c + s] + L.vel[c + 2 * s] * L.vel[c + 2 * s];
         rho_sum += r;
+        nan_rho |= r != r; nan_v |= v2 != v2;
         rho_min = std::min(rho_min, r); rho_max = std::max(rho_max, r);
         v_max = std::max(v_max, std::sqrt(v2));
         ke += (double)(r * v2);
     }
     if (n_fluid > 0) {
-        out[0] = n_fluid; out[1] = rho_sum / n_fluid; out[2] = rho_min; out[3] = rho_max; out[4] = v_max; out[5] = 0.5 * ke;
+        out[0] = n_fluid; out[1] = rho_sum / n_fluid; out[2] = nan_rho ? NAN : rho_min; out[3] = nan_rho ? NAN : rho_max;
+        out[4] = nan_v ? NAN : v_max; out[5] = 0.5 * ke;
     } else {
         out[0] = 0; out[1] = 1; out[2] = 1; out[3] = 1; out[4] = 0; out[5] = 0;
     }
@@ -871,7 +881,7 @@ int ludwig_ctx_set_partition_keys(ludwig_ctx*, const uint64_t*, int32_t) { retur
 int ludwig_ctx_set_partition(ludwig_ctx* ctx, int32_t rank, int32_t world) {
     return (rank == 0 && world == 1) ? LUDWIG_OK : fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank");
 }
-int ludwig_set_barrier_callback(ludwig_ctx*, void (*)(void*), void*) { return LUDWIG_OK; }
+int ludwig_set_barrier_callback(ludwig_ctx*, int (*)(void*), void*) { return LUDWIG_OK; }
 int ludwig_level_local_blocks(ludwig_ctx* ctx, int32_t level, int32_t* n_local, int32_t* ref_indices) {
     if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return LUDWIG_EINVAL;
     int nb = ctx->levels[level]->nb;
@@ -889,6 +899,30 @@ int ludwig_profile_enable(ludwig_ctx*, int32_t) { return LUDWIG_OK; }
 int ludwig_profile_classes(ludwig_ctx*, double out[8]) { for (int i = 0; i < 8; ++i) out[i] = 0; return LUDWIG_OK; }
 int ludwig_profile_levels(ludwig_ctx*, double* out, int32_t capacity) { for (int i = 0; i < capacity; ++i) out[i] = 0; return LUDWIG_OK; }
 int ludwig_partition_rcb(const ludwig_level_desc*, int32_t, int32_t*) { return LUDWIG_EINVAL; }   // multi-GPU only: not part of the oracle
+int ludwig_partition_rcb_axes(const ludwig_level_desc*, int32_t, int32_t, int32_t*) { return LUDWIG_EINVAL; }
+// The options select between implementations of the CUDA library; the oracle has one code path and accepts them all.
+int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) { return (ctx && key && value) ? LUDWIG_OK : LUDWIG_EINVAL; }
+// ludwig_multi (several ranks in one process) is multi-GPU plumbing: not part of the oracle.
+struct ludwig_multi;
+int ludwig_multi_create(ludwig_multi** out, int32_t, const int32_t*) { if (out) *out = nullptr; return LUDWIG_ESTATE; }
+int ludwig_multi_destroy(ludwig_multi*) { return LUDWIG_OK; }
+const char* ludwig_multi_last_error(const ludwig_multi*) { return "the CPU oracle is single-rank"; }
+int32_t ludwig_multi_num_ranks(const ludwig_multi*) { return LUDWIG_ESTATE; }
+ludwig_ctx* ludwig_multi_ctx(ludwig_multi*, int32_t) { return nullptr; }
+int ludwig_multi_set_option(ludwig_multi*, const char*, const char*) { return LUDWIG_ESTATE; }
+int ludwig_multi_set_partition_plan(ludwig_multi*, const ludwig_level_desc* const*, int32_t) { return LUDWIG_ESTATE; }
+int ludwig_multi_level_create(ludwig_multi*, const ludwig_level_desc*, int32_t*) { return LUDWIG_ESTATE; }
+int ludwig_multi_level_upload(ludwig_multi*, int32_t, int32_t, const void*) { return LUDWIG_ESTATE; }
+int ludwig_multi_level_download(ludwig_multi*, int32_t, int32_t, void*) { return LUDWIG_ESTATE; }
+int ludwig_multi_init_equilibrium(ludwig_multi*) { return LUDWIG_ESTATE; }
+int ludwig_multi_step_batch(ludwig_multi*, int64_t, int32_t, float, const ludwig_params*) { return LUDWIG_ESTATE; }
+int ludwig_multi_sync(ludwig_multi*) { return LUDWIG_ESTATE; }
+int ludwig_multi_flow_stats(ludwig_multi*, int32_t, double*) { return LUDWIG_ESTATE; }
+int ludwig_multi_forces_create(ludwig_multi*, int32_t, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                               double, double, double, double, const double*, int32_t, int32_t*) { return LUDWIG_ESTATE; }
+int ludwig_multi_compute_aerodynamics(ludwig_multi*, int32_t, int32_t, const double*, double, double, int32_t, double*) { return LUDWIG_ESTATE; }
+int ludwig_multi_forces_download_maps(ludwig_multi*, int32_t, float*, float*, float*, float*) { return LUDWIG_ESTATE; }
+int64_t ludwig_multi_device_bytes(const ludwig_multi*) { return 0; }
 int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const*, int32_t) { return fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank"); }
 int ludwig_profile_read(ludwig_ctx*, double* ms, int64_t* n, int64_t* c) { if (ms) *ms = 0; if (n) *n = 0; if (c) *c = 0; return LUDWIG_OK; }
 

@@ -145,3 +145,40 @@ def test_oracle_step_matches_numpy_restatement(oracle_lib):
     got_d = np.stack([dense(got["f_temp"][k]) for k in range(27)])
     assert np.array_equal(want.view(np.int32), got_d.view(np.int32))          # same FP32 operation order -> same bits
     assert np.array_equal(dense(got["rho"]).view(np.int32), r.view(np.int32))
+
+
+def _stats_with_nan(lib, where):
+    """flow statistics of a 2^3-block box at rest with one NaN planted in rho (where = 'rho') or vel (where = 'vel')"""
+    import numpy as np
+    from open_ludwig_b200 import cabi
+    from open_ludwig_b200.host import synthetic as syn
+    lv = syn.make_box_level(2, 2, 2)
+    f, rho, vel = syn.noise_state(lv)
+    if where == "rho":
+        rho[3, 1, 2, 5] = np.nan
+    elif where == "vel":
+        vel[1, 6, 7, 0, 3] = np.nan
+    with cabi.Context(lib) as c:
+        c.add_level(lv)
+        c.upload(0, cabi.RHO, rho); c.upload(0, cabi.VEL, vel)
+        return c.flow_stats(0)
+
+
+@pytest.mark.parametrize("where", ["none", "rho", "vel"])
+def test_oracle_flow_stats_propagate_nan(oracle_lib, where):
+    """Julia's minimum / maximum propagate NaN (diagnostics.jl:70-77): rho_min is the console table's only divergence indicator."""
+    import math
+    s = _stats_with_nan(oracle_lib, where)
+    assert s["n_fluid"] == 8 * 512
+    assert math.isnan(s["rho_min"]) == (where == "rho") and math.isnan(s["rho_max"]) == (where == "rho")
+    assert math.isnan(s["v_max"]) == (where == "vel")
+    assert math.isnan(s["rho_mean"]) == (where == "rho") and math.isnan(s["kinetic_energy"]) == (where != "none")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("where", ["none", "rho", "vel"])
+def test_cuda_flow_stats_propagate_nan(cuda_lib, oracle_lib, where):
+    import math
+    s, r = _stats_with_nan(cuda_lib, where), _stats_with_nan(oracle_lib, where)
+    for k in s:
+        assert (math.isnan(s[k]) and math.isnan(r[k])) or s[k] == pytest.approx(r[k], rel=1e-12), (k, s[k], r[k])

@@ -33,12 +33,12 @@ def sphere_mesh(n=400, seed=3, centre=(20.0, 16.0, 16.0), radius=3.65):
     return centers, nrm, areas
 
 
-def run(lib, levels, steps, strict, wall_model=True, fine_grained=False, **overrides):
+def run(lib, levels, steps, strict, wall_model=True, fine_grained=False, options=None, **overrides):
     cells = tuple(8 * d for d in DIMS)
     kw = dict(strict=strict, wall_model_active=int(wall_model), use_temporal=1, inlet_turbulence=0.02)
     kw.update(overrides)
     p = default_params(cells, **kw)
-    with cabi.Context(lib) as c:
+    with cabi.Context(lib, options=options) as c:
         for lv in levels:
             c.add_level(lv)
         c.init_equilibrium()
@@ -126,22 +126,38 @@ def test_parameter_variants(oracle_lib, cuda_lib, overrides):
         assert float(np.abs(ref[lvl]["f"] - fast[lvl]["f"]).max()) <= 2e-6, (overrides, lvl)
 
 
-def test_block_prepass_variant_is_bit_identical(tmp_path):
-    """LUDWIG_PREPASS=block (one CTA per ghost block, parent cells staged in shared memory) performs the same arithmetic in
-    the same order as the default one-thread-per-group interface pre-pass: identical bits after 10 two-level steps.
-    The variant is selected once per process, hence the two subprocesses."""
-    import os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import sys; sys.path.insert(0, sys.argv[2]); import numpy as np, test_k1_features_gpu as T\n"
-            "out, *_ = T.run(None, T.build_case(), 10, 0, True)\n"
-            "np.savez(sys.argv[1], **{f'{l}_{n}': a for l, d in out.items() for n, a in d.items()})\n")
-    res = {}
-    for mode in ("thread", "block"):
-        env = dict(os.environ, LUDWIG_PREPASS=mode, PYTHONPATH=root)
-        path = str(tmp_path / f"{mode}.npz")
-        r = subprocess.run([sys.executable, "-c", code, path, os.path.join(root, "tests")], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        res[mode] = np.load(path)
-    assert set(res["thread"].files) == set(res["block"].files) and len(res["thread"].files) >= 6
-    for k in res["thread"].files:
-        assert np.array_equal(res["thread"][k].view(np.int32), res["block"][k].view(np.int32)), k
+def test_block_prepass_variant_is_bit_identical(cuda_lib):
+    """Option prepass = block (one CTA per ghost block, parent cells staged in shared memory) performs the same arithmetic in
+    the same order as the default one-thread-per-group interface pre-pass: identical bits after 10 two-level steps."""
+    levels = build_case()
+    a, *_ = run(cuda_lib, levels, 10, 0, True)
+    b, *_ = run(cuda_lib, levels, 10, 0, True, options={"prepass": "block"})
+    for lvl in a:
+        for name in a[lvl]:
+            assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (lvl, name)
+
+
+@pytest.mark.parametrize("wall_model", [False, True])
+def test_strict_packed_equals_generic_cross_check(cuda_lib, wall_model):
+    """The shipped strict kernels (k1_strict.cu: packed FP32x2, ghost blocks + pre-pass) against the one-thread-per-cell
+    kernel that keeps every branch of the reference inside it (option strict_generic): identical bits, wall model included
+    (both call libdevice powf / logf)."""
+    levels = build_case()
+    a, *_ = run(cuda_lib, levels, 12, 1, wall_model)
+    b, *_ = run(cuda_lib, levels, 12, 1, wall_model, options={"strict_generic": 1})
+    for lvl in a:
+        for name in a[lvl]:
+            assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (lvl, name)
+
+
+def test_options_are_validated(cuda_lib):
+    with cabi.Context(cuda_lib) as c:
+        with pytest.raises(cabi.LudwigError):
+            c.set_option("no_such_option", 1)
+        with pytest.raises(cabi.LudwigError):
+            c.set_option("partition", "hilbert")
+        c.set_option("partition", "rcb_yz")
+        c.add_level(build_case()[0])
+        with pytest.raises(cabi.LudwigError):     # partition rule is fixed once a level exists
+            c.set_option("partition", "morton")
+

@@ -1,6 +1,6 @@
 """Per-rank cost of a partitioned case, measured on ONE GPU (no multi-GPU box time needed).
 
-    python tools/emulate_ranks.py bunny_fine 8 2 [--no-plan]
+    python tools/emulate_ranks.py bunny_fine 8 2 [--no-plan] [--opt partition=rcb_yz] [--opt fork_max_blocks=100000]
 
 All `world` rank contexts are created on device 0 from the same domain and attached in-process
 (ludwig_attach_inprocess), with a no-op barrier; each virtual rank then steps ALONE while the others' state stays
@@ -19,7 +19,8 @@ from open_ludwig_b200.host.cases import CASE_OVERRIDES, case_dir
 from open_ludwig_b200.solver import make_params, ramp_velocity
 
 name, world, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-use_plan = "--no-plan" not in sys.argv
+opts = dict(a.split("=", 1) for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--opt")
+use_plan = "--no-plan" not in sys.argv and "partition" not in opts
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
 case, ov = CASE_OVERRIDES[name]
 t0 = time.time()
@@ -46,7 +47,7 @@ def timed(ctx, n):
 
 ctxs = []
 for r in range(world):
-    c = cabi.Context(device=0)
+    c = cabi.Context(device=0, options=opts)
     c.set_partition(r, world)
     if use_plan:
         c.set_partition_plan(dom.levels)
@@ -81,6 +82,6 @@ t1 /= steps
 print(f"1 rank: {t1:.2f} ms/coarse step  per level: " + " | ".join(f"L{i+1} {d['level_step']/steps:.2f} (pre {d['interface_prepass']/steps:.2f} k1p {d['k1_plain']/steps:.2f} bz {d['bouzidi']/steps:.2f})" for i, d in enumerate(lv1)), flush=True)
 one.close()
 bound = lvl.max(axis=0).sum()
-print(f"EMULATE case={name} world={world} plan={use_plan} ideal={t1/world:.2f} mean_rank={tot.mean():.2f} max_rank={tot.max():.2f} "
+print(f"EMULATE case={name} world={world} plan={use_plan} opts={opts} ideal={t1/world:.2f} mean_rank={tot.mean():.2f} max_rank={tot.max():.2f} "
       f"sum_of_level_max={bound:.2f} ms  -> efficiency bounds: overhead-only {t1/world/tot.mean():.3f}, +imbalance {t1/world/tot.max():.3f}, "
       f"+per-level barriers {t1/world/bound:.3f}", flush=True)

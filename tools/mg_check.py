@@ -22,12 +22,13 @@ def gather_field(ctx, level, which, lv):
     dist.all_reduce(a)
     return a.cpu().numpy()
 
-def run_box(partitioned, steps=9, barrier="native"):
+def run_box(partitioned, steps=9, barrier="native", mirror=False):
     dims = (6, 4, 4)
     lv = syn.make_box_level(*dims)
     f, rho, vel = syn.noise_state(lv)
     p = default_params(tuple(8 * d for d in dims), strict=0)
     ctx = mg.init_context(None, lr) if partitioned else cabi.Context(device=lr)
+    if mirror: ctx.set_option("halo_mirror", 1)
     ctx.add_level(lv)
     if partitioned:
         mg.attach_peers(ctx, dev, barrier)
@@ -53,9 +54,8 @@ def run_two_level(partitioned, steps=10, plan=False):
     levels = T.build_case()
     cells = tuple(8 * d for d in T.DIMS)
     p = default_params(cells, strict=0, wall_model_active=1, use_temporal=1, inlet_turbulence=0.02)
-    if plan == "rcb": os.environ["LUDWIG_PARTITION"] = "rcb"     # read at context creation
     ctx = mg.init_context(None, lr) if partitioned else cabi.Context(device=lr)
-    os.environ.pop("LUDWIG_PARTITION", None)
+    if partitioned and plan in ("rcb", "rcb_yz"): ctx.set_option("partition", plan)
     if partitioned and plan is True:
         ctx.set_partition_plan(levels)
     for lv in levels:
@@ -79,16 +79,14 @@ def run_two_level(partitioned, steps=10, plan=False):
 ok = True
 ref, sref = run_box(False)
 for barrier in ("native", "nccl", "native-mirror"):   # peer-flag barrier kernel / NCCL callback / packed halo mirrors (opt-in)
-    if barrier.endswith("mirror"): os.environ["LUDWIG_HALO_MIRROR"] = "1"
-    got, sgot = run_box(True, barrier=barrier.split("-")[0])
-    os.environ.pop("LUDWIG_HALO_MIRROR", None)
+    got, sgot = run_box(True, barrier=barrier.split("-")[0], mirror=barrier.endswith("mirror"))
     for k in ref:
         same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
         ok &= same
         if rank == 0: print(f"box barrier={barrier} {k}: bit-identical={same} maxdiff={np.abs(ref[k]-got[k]).max():.3e}", flush=True)
 if rank == 0: print("box stats", sref["n_fluid"] == sgot["n_fluid"], abs(sref["rho_mean"] - sgot["rho_mean"]) < 1e-12, sref["rho_min"] == sgot["rho_min"], flush=True)
 ref, aref = run_two_level(False)
-for plan in (False, True, "rcb"):   # per-level cost-weighted Morton cut, the spatially aligned plan, per-level RCB boxes
+for plan in (False, True, "rcb", "rcb_yz"):   # per-level cost-weighted Morton cut, the spatially aligned plan, per-level RCB boxes
     got, agot = run_two_level(True, plan=plan)
     for k in ref:
         same = np.array_equal(ref[k].view(np.int32), got[k].view(np.int32))
