@@ -111,6 +111,9 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   single_stream = 0 | 1             no concurrent launches at all
  *   fork_full = 0 | 1                 domain-face K1 launch beside the plain launch on large levels
  *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default 40000)
+ *   strict_kernel = reg | stash | tma strict K1 variant: pulled populations in registers (2 CTAs / SM), in a shared-memory stash
+ *                                     (3 CTAs / SM), or persistent CTAs with cp.async.bulk (TMA) staged, double-buffered block tiles
+ *   fast_kernel = direct | tma        fast K1 variant: direct loads, or the persistent TMA-staged form (identical bits either way)
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
  *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)
  *   halo_mirror = 0 | 1               packed halo exchange into local mirrors instead of in-kernel NVLink pulls (before the first level)

@@ -416,7 +416,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f;
+    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms;
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -792,6 +792,13 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
     else if (k == "single_stream") ctx->use_side_streams = !on;          // no concurrent launches at all
     else if (k == "fork_full") ctx->fork_full = on;                      // domain-face K1 launch beside the plain launch on large levels
     else if (k == "fork_max_blocks") ctx->fork_max_blocks = atoi(value); // levels up to this size run their K1 classes concurrently
+    else if (k == "strict_kernel") {            // where the strict K1 keeps the 27 pulled populations / how it loads them
+        if (v == "reg") ctx->opt_strict_variant = 0; else if (v == "stash") ctx->opt_strict_variant = 1; else if (v == "tma") ctx->opt_strict_variant = 2;
+        else return fail(ctx, LUDWIG_EINVAL, "strict_kernel: reg | stash | tma");
+    } else if (k == "fast_kernel") {
+        if (v == "direct") ctx->opt_fast_variant = 0; else if (v == "tma") ctx->opt_fast_variant = 2;
+        else return fail(ctx, LUDWIG_EINVAL, "fast_kernel: direct | tma");
+    }
     else if (k == "strict_generic") ctx->opt_strict_generic = on;        // strict mode through the one-thread-per-cell cross-check kernel
     else if (k == "verbose") ctx->verbose = on;
     else if (k == "barrier_timeout_s") { ctx->barrier_timeout_s = atof(value); if (!(ctx->barrier_timeout_s > 0)) return fail(ctx, LUDWIG_EINVAL, "barrier_timeout_s > 0"); }

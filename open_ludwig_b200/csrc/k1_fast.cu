@@ -112,32 +112,17 @@ __device__ __forceinline__ float3 wall_force(float dist_wall, float rho, float u
 
 
 #include "k1_ghost.cuh"
+#include "k1_common.cuh"
 
 
-constexpr long long MISSING = LLONG_MIN;
 
 // FULL : see file header.   VELFB : some axis neighbour may lack a velocity field (ghost block or domain face) ->
 // fall back to the cell's own value (physics_utils.jl:69).
 //        MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh; blocks with features but all 26
 //        neighbours present (the near-body bulk) use FULL without MISS and never carry that code.
-template <bool FULL, bool VELFB, bool MISS, int MINB>
-__global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constant__ K1Args a) {
-    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
-    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
-    const int b = a.list[blockIdx.x];
+template <bool FULL, bool VELFB, bool MISS>
+__device__ __forceinline__ void fast_block(const K1Args& a, const int b, const float* __restrict__ fbase, const long long* s_fo, const long long* s_vo) {
     const int t = threadIdx.x;
-    if (t < 27) {
-        const int nbi = a.nbr[(size_t)b * 27 + t];
-        // indices >= nb address the level's ghost blocks (interface halo, filled by ghost_interp_kernel)
-        // (another GPU's block: offset of the peer-mapped block relative to the local buffer — K1 pulls it over NVLink)
-        s_fo[t] = nbi < 0 ? MISSING
-                  : nbi < a.nb ? (long long)nbi * (Q * BS3)
-                  : nbi < REMOTE_BASE ? a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3)
-                                      : a.roff_f[nbi - REMOTE_BASE];
-        s_vo[t] = nbi < 0 ? MISSING : nbi < a.nb ? (long long)nbi * (3 * BS3) : nbi < REMOTE_BASE ? MISSING : a.roff_v[nbi - REMOTE_BASE];
-    }
-    __syncthreads();
-
     const int p = t & 3, y = (t >> 2) & 7, z = t >> 5;
     const int x0 = 2 * p;
     const int c0 = 2 * t;   // z*64 + y*8 + x0
@@ -148,7 +133,7 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constan
         bflags = (uint32_t)bc.w;
         if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
-    const float* __restrict__ fin_own = a.f_in + (size_t)b * (Q * BS3) + c0;   // own cell A, direction 0
+    const float* __restrict__ fin_own = fbase + s_fo[13] + c0;   // own cell A, direction 0
 
     // source-row bookkeeping per axis: index j = c + 1 for lattice component c in {-1,0,1}; source = coord - c
     int yoff[3], ydir[3], zoff[3], zdir[3];
@@ -170,24 +155,24 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constan
         const int k0 = 1 + 3 * jy + 9 * jz, kp = k0 + 1, km = k0 - 1;
         const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
         if (!MISS || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
-            const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
-            const float* __restrict__ PM = a.f_in + oM + (loc + xM);
-            const float* __restrict__ PP = a.f_in + oP + (loc + xP);
+            const float* __restrict__ P0 = fbase + o0 + (loc + x0);
+            const float* __restrict__ PM = fbase + oM + (loc + xM);
+            const float* __restrict__ PP = fbase + oP + (loc + xP);
             f0 = ld2(P0 + k0 * BS3);
             fp = make_float2(PM[kp * BS3], P0[kp * BS3]);       // cx=+1: sources x0-1, x0
             fm = make_float2(P0[km * BS3 + 1], PP[km * BS3]);   // cx=-1: sources x0+1, x0+2
         } else {
             // some source block is missing: domain face or refinement interface (rare path)
             if (o0 != MISSING) {
-                const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
+                const float* __restrict__ P0 = fbase + o0 + (loc + x0);
                 f0 = ld2(P0 + k0 * BS3); fp.y = P0[kp * BS3]; fm.x = P0[km * BS3 + 1];
             } else {
                 f0.x = pull_missing(a, fin_own, k0, gx, gy, gz); f0.y = pull_missing(a, fin_own + 1, k0, gx + 1, gy, gz);
                 fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
                 fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
             }
-            fp.x = oM != MISSING ? a.f_in[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
-            fm.y = oP != MISSING ? a.f_in[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+            fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
+            fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
         }
     };
 
@@ -423,25 +408,81 @@ __global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constan
     }
 }
 
+
+// FULL : see file header.   VELFB : some axis neighbour may lack a velocity field (ghost block or domain face) ->
+// fall back to the cell's own value (physics_utils.jl:69).
+//        MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh; blocks with features but all 26
+//        neighbours present (the near-body bulk) use FULL without MISS and never carry that code.
+template <bool FULL, bool VELFB, bool MISS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
+    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
+    const int b = a.list[blockIdx.x];
+    if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
+    __syncthreads();
+    fast_block<FULL, VELFB, MISS>(a, b, a.f_in, s_fo, s_vo);
+}
+
+// TMA variant (option fast_kernel = tma): persistent CTAs, the block's own populations staged into shared memory by one
+// cp.async.bulk per block, double-buffered (see k1_strict.cu for the full description).  north_star asks for this form
+// ("block tiles plus halo staged into shared memory with TMA, or cp.async where measured faster"); the measured A/B against the
+// direct-load kernel is in profiles/README.md.  Same fast_block body, same bits.
+template <bool FULL, bool VELFB, bool MISS>
+__global__ void __launch_bounds__(256, 2) k1_fast_tma_kernel(const __grid_constant__ K1Args a) {
+    extern __shared__ __align__(128) float s_tile[];              // [2][TILE_FLOATS]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ long long s_fo[2][27], s_vo[2][27];
+    const int t = threadIdx.x;
+    const int n_iter = (a.n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0 && n_iter > 0) {
+        mbar_expect_tx(&s_bar[0], TILE_BYTES);
+        bulk_load(s_tile, a.f_in + (size_t)a.list[blockIdx.x] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
+    }
+    const float* fbase;   // a.f_in with its global provenance hidden: own-block reads hit shared memory, the loads must be generic
+    asm volatile("mov.u64 %0, %1;" : "=l"(fbase) : "l"(a.f_in));
+    for (int it = 0; it < n_iter; ++it) {
+        const int cur = it & 1;
+        const int b = a.list[blockIdx.x + it * gridDim.x];
+        const float* tile = s_tile + cur * TILE_FLOATS;
+        if (t < 27) neighbour_offsets(a, b, t, (long long)(((long long)(uintptr_t)tile - (long long)(uintptr_t)a.f_in) >> 2), s_fo[cur], s_vo[cur]);
+        __syncthreads();   // publishes the tables; every warp is done with the other stage before the copy engine overwrites it
+        if (it + 1 < n_iter) {
+            const int bn = a.list[blockIdx.x + (it + 1) * gridDim.x];
+            if (t == 0) {
+                mbar_expect_tx(&s_bar[cur ^ 1], TILE_BYTES);
+                bulk_load(s_tile + (cur ^ 1) * TILE_FLOATS, a.f_in + (size_t)bn * TILE_FLOATS, TILE_BYTES, &s_bar[cur ^ 1]);
+            } else if (t >= 32 && t < 32 + 48) {   // the next block's own velocities (6 KiB = 48 lines) into L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_in + (size_t)bn * (3 * BS3) + (t - 32) * 32));
+            }
+        }
+        mbar_wait(&s_bar[cur], (uint32_t)((it >> 1) & 1));
+        fast_block<FULL, VELFB, MISS>(a, b, fbase, s_fo[cur], s_vo[cur]);
+    }
+}
+
 }  // namespace k1f
 
-void launch_k1_plain(const K1Args& a, cudaStream_t s) {
+template <bool FULL, bool VELFB, bool MISS, int MINB>
+void launch_fast(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<false, false, false, 3><<<a.n_list, 256, 0, s>>>(a);
+    if (a.fast_variant == 2) {
+        static const cudaError_t once = cudaFuncSetAttribute(k1f::k1_fast_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)k1f::TILE_BYTES);
+        static const cudaError_t once2 = cudaFuncSetAttribute(k1f::k1_fast_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        (void)once; (void)once2;
+        const int grid = a.n_list < 2 * a.num_sms ? a.n_list : 2 * a.num_sms;
+        k1f::k1_fast_tma_kernel<FULL, VELFB, MISS><<<grid, 256, 2 * k1f::TILE_BYTES, s>>>(a);
+    } else k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB><<<a.n_list, 256, 0, s>>>(a);
 }
-void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) {
-    if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<false, true, false, 3><<<a.n_list, 256, 0, s>>>(a);
-}
-void launch_k1_feat(const K1Args& a, cudaStream_t s) {
-    if (a.n_list <= 0) return;
-    // 80 registers / 3 CTAs per SM measured +12 % over 127 registers / 2 CTAs on Wing_5_deg (A/B on one box)
-    k1f::k1_fast_kernel<true, true, false, 3><<<a.n_list, 256, 0, s>>>(a);
-}
-void launch_k1_full(const K1Args& a, cudaStream_t s) {
-    if (a.n_list <= 0) return;
-    k1f::k1_fast_kernel<true, true, true, 2><<<a.n_list, 256, 0, s>>>(a);
-}
+void launch_k1_plain(const K1Args& a, cudaStream_t s) { launch_fast<false, false, false, 3>(a, s); }
+void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) { launch_fast<false, true, false, 3>(a, s); }
+// feature blocks: 80 registers / 3 CTAs per SM measured +12 % over 127 registers / 2 CTAs on Wing_5_deg (A/B on one box)
+void launch_k1_feat(const K1Args& a, cudaStream_t s) { launch_fast<true, true, false, 3>(a, s); }
+void launch_k1_full(const K1Args& a, cudaStream_t s) { launch_fast<true, true, true, 2>(a, s); }
 void launch_ghost_interp(const GhostArgs& g, bool block_variant, cudaStream_t s) {
     if (g.n <= 0) return;
     if (block_variant && g.gstart) k1f::ghost_interp_block_kernel<<<g.n_ghost, 128, 0, s>>>(g);

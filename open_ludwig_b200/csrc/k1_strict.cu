@@ -12,8 +12,9 @@
 //     mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, and folds a CONSTANT -0 addend away.)
 //   * terms the reference multiplies by a zero lattice component are skipped: x + (+-0) = x, and a sum that stays +-0 only
 //     feeds 1 + 3 cu etc., where the sign of zero cannot matter.  Division and square root are the IEEE ones.
-//   * the 27 pulled populations stay in registers between the moment sums, the Pi loop (which needs f_k - feq_k in k
-//     order) and the collision loop — the price of the reference's operation order (the fast build streams them).
+//   * the 27 pulled populations must be kept between the pull, the Pi loop (which needs f_k - feq_k in k order) and the
+//     collision loop — the price of the reference's operation order (the fast build streams them into 10 moments): in
+//     registers or in a shared-memory stash (FStore below, option strict_stash).
 #include <climits>
 
 #include "ludwig_internal.h"
@@ -23,6 +24,7 @@ namespace k1s {
 
 #include "k1_boundary.cuh"
 #include "k1_ghost.cuh"
+#include "k1_common.cuh"
 
 typedef float2 v2;
 __device__ __forceinline__ v2 V(float s) { return make_float2(s, s); }
@@ -99,26 +101,35 @@ __device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, 
     return F;
 }
 
-constexpr long long MISSING = LLONG_MIN;
+
+// Where the 27 pulled populations (later: the 27 equilibria) of a thread's two cells live between the pull, the Pi loop and the
+// collision loop.  REG: 54 registers (128 registers per thread, 2 CTAs per SM).  STASH: 54 KiB of dynamic shared memory per CTA,
+// slot [k][thread] (consecutive threads -> consecutive 8-byte words: conflict-free 64-bit accesses), ~80 registers, 3 CTAs per
+// SM — the loads of one more block are in flight while two others compute.  Same values, same operation order, same bits.
+template <bool STASH> struct FStore;
+template <> struct FStore<false> {
+    v2 r[27];
+    __device__ __forceinline__ FStore(float2*) {}
+    __device__ __forceinline__ v2 get(int k) const { return r[k]; }
+    __device__ __forceinline__ void set(int k, v2 v) { r[k] = v; }
+};
+template <> struct FStore<true> {
+    float2* s;   // already offset by the thread index
+    __device__ __forceinline__ FStore(float2* base) : s(base + threadIdx.x) {}
+    __device__ __forceinline__ v2 get(int k) const { return s[k * 256]; }
+    __device__ __forceinline__ void set(int k, v2 v) { s[k * 256] = v; }
+};
 
 // FULL : obstacle / sponge / wall-model handling (per-block flag bits gate each feature uniformly)
 // VELFB: some axis neighbour may lack a velocity field (ghost block or domain face) -> the cell's own value (physics_utils.jl:69)
 // MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh
-template <bool FULL, bool VELFB, bool MISS>
-__global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant__ K1Args a) {
-    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
-    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
-    const int b = a.list[blockIdx.x];
+// One 8^3 block: 256 threads, two x-adjacent cells per thread.  fbase + s_fo[d] is neighbour block d's populations (fbase is
+// a.f_in, or — TMA variant — the same address with its global provenance hidden, because s_fo[13] then points into shared memory
+// and the loads must be generic).
+template <bool FULL, bool VELFB, bool MISS, bool STASH>
+__device__ __forceinline__ void strict_block(const K1Args& a, const int b, const float* __restrict__ fbase, const long long* s_fo,
+                                             const long long* s_vo, float2* s_stash) {
     const int t = threadIdx.x;
-    if (t < 27) {
-        const int nbi = a.nbr[(size_t)b * 27 + t];
-        s_fo[t] = nbi < 0 ? MISSING
-                  : nbi < a.nb ? (long long)nbi * (Q * BS3)
-                  : nbi < REMOTE_BASE ? a.ghost_delta + (long long)(nbi - a.nb) * (Q * BS3)
-                                      : a.roff_f[nbi - REMOTE_BASE];
-        s_vo[t] = nbi < 0 ? MISSING : nbi < a.nb ? (long long)nbi * (3 * BS3) : nbi < REMOTE_BASE ? MISSING : a.roff_v[nbi - REMOTE_BASE];
-    }
-    __syncthreads();
     const v2 NZ = V(a.negzero);
 
     const int p = t & 3, y = (t >> 2) & 7, z = t >> 5;
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
         bflags = (uint32_t)bc.w;
         if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
-    const float* __restrict__ fin_own = a.f_in + (size_t)b * (Q * BS3) + c0;
+    const float* __restrict__ fin_own = fbase + s_fo[13] + c0;
 
     int yoff[3], ydir[3], zoff[3], zdir[3];
 #pragma unroll
@@ -142,8 +153,10 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
     const int dM = p > 0 ? 1 : 0, xM = p > 0 ? x0 - 1 : 7;
     const int dP = p < 3 ? 1 : 2, xP = p < 3 ? x0 + 2 : 0;
 
-    // ---- pull-stream (:62-149); combo (jy,jz) yields the three consecutive directions k0-1, k0, k0+1
-    v2 f[27];
+    // ---- pull-stream (:62-149) with the moment sums of :144-148 taken in k order as the values arrive; combo (jy,jz) yields the
+    // three consecutive directions k0-1, k0, k0+1 and the combos are visited in ascending k0
+    FStore<STASH> f(s_stash);
+    v2 rho = V(0.f), jx = V(0.f), jy = V(0.f), jz = V(0.f);
 #pragma unroll
     for (int jzc = 0; jzc < 3; ++jzc) {
 #pragma unroll
@@ -151,26 +164,40 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
             const int loc = zoff[jzc] + yoff[jyc], dir = zdir[jzc] + ydir[jyc];
             const int k0 = 1 + 3 * jyc + 9 * jzc, kp = k0 + 1, km = k0 - 1;
             const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
+            v2 fm, f0, fp;
             if (!MISS || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
-                const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
-                const float* __restrict__ PM = a.f_in + oM + (loc + xM);
-                const float* __restrict__ PP = a.f_in + oP + (loc + xP);
-                f[km] = make_float2(P0[km * BS3 + 1], PP[km * BS3]);   // cx=-1: sources x0+1, x0+2
-                f[k0] = ld2(P0 + k0 * BS3);
-                f[kp] = make_float2(PM[kp * BS3], P0[kp * BS3]);       // cx=+1: sources x0-1, x0
+                const float* __restrict__ P0 = fbase + o0 + (loc + x0);
+                const float* __restrict__ PM = fbase + oM + (loc + xM);
+                const float* __restrict__ PP = fbase + oP + (loc + xP);
+                fm = make_float2(P0[km * BS3 + 1], PP[km * BS3]);   // cx=-1: sources x0+1, x0+2
+                f0 = ld2(P0 + k0 * BS3);
+                fp = make_float2(PM[kp * BS3], P0[kp * BS3]);       // cx=+1: sources x0-1, x0
             } else {
                 // some source block is missing: domain face (rare path)
                 if (o0 != MISSING) {
-                    const float* __restrict__ P0 = a.f_in + o0 + (loc + x0);
-                    f[k0] = ld2(P0 + k0 * BS3); f[kp].y = P0[kp * BS3]; f[km].x = P0[km * BS3 + 1];
+                    const float* __restrict__ P0 = fbase + o0 + (loc + x0);
+                    f0 = ld2(P0 + k0 * BS3); fp.y = P0[kp * BS3]; fm.x = P0[km * BS3 + 1];
                 } else {
-                    f[k0].x = pull_missing(a, fin_own, k0, gx, gy, gz); f[k0].y = pull_missing(a, fin_own + 1, k0, gx + 1, gy, gz);
-                    f[kp].y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
-                    f[km].x = pull_missing(a, fin_own, km, gx, gy, gz);
+                    f0.x = pull_missing(a, fin_own, k0, gx, gy, gz); f0.y = pull_missing(a, fin_own + 1, k0, gx + 1, gy, gz);
+                    fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
+                    fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
                 }
-                f[kp].x = oM != MISSING ? a.f_in[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
-                f[km].y = oP != MISSING ? a.f_in[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+                fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
+                fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
             }
+            f.set(km, fm); f.set(k0, f0); f.set(kp, fp);
+            // rho += f_k; j += f_k c_k  (k = km: cx = -1, k0: cx = 0, kp: cx = +1; cy = jyc - 1, cz = jzc - 1)
+            rho = (jzc == 0 && jyc == 0) ? fm : vadd(rho, fm);
+            jx = vsub(jx, fm);
+            if (jyc == 2) jy = vadd(jy, fm); else if (jyc == 0) jy = vsub(jy, fm);
+            if (jzc == 2) jz = vadd(jz, fm); else if (jzc == 0) jz = vsub(jz, fm);
+            rho = vadd(rho, f0);
+            if (jyc == 2) jy = vadd(jy, f0); else if (jyc == 0) jy = vsub(jy, f0);
+            if (jzc == 2) jz = vadd(jz, f0); else if (jzc == 0) jz = vsub(jz, f0);
+            rho = vadd(rho, fp);
+            jx = vadd(jx, fp);
+            if (jyc == 2) jy = vadd(jy, fp); else if (jyc == 0) jy = vsub(jy, fp);
+            if (jzc == 2) jz = vadd(jz, fp); else if (jzc == 0) jz = vsub(jz, fp);
         }
     }
 
@@ -188,19 +215,15 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
     if (anyobs) {
         if (obsA && obsB) {
 #pragma unroll
-            for (int k = 0; k < 27; ++k) st2(fout + (26 - k) * BS3, f[k]);
+            for (int k = 0; k < 27; ++k) st2(fout + (26 - k) * BS3, f.get(k));
             st2(vout, V(0.f)); st2(vout + BS3, V(0.f)); st2(vout + 2 * BS3, V(0.f)); st2(rout, V(1.0f));
             return;
         }
 #pragma unroll
         for (int k = 0; k < 27; ++k) {
-            if (obsA) fout[(26 - k) * BS3] = f[k].x; else fout[(26 - k) * BS3 + 1] = f[k].y;
+            if (obsA) fout[(26 - k) * BS3] = f.get(k).x; else fout[(26 - k) * BS3 + 1] = f.get(k).y;
         }
     }
-
-    // ---- moments in k order (:144-148)
-    v2 rho = V(0.f), jx = V(0.f), jy = V(0.f), jz = V(0.f);
-    Unroll<0, 27>::run([&]<int K>() { moment_step<K>(f[K], rho, jx, jy, jz); });
 
     // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
     v2 uE[3], uW[3], uN[3], uS[3], uT[3], uB[3];
@@ -238,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
         if (a.sponge_blend == 1) {
             Unroll<0, 27>::run([&]<int K>() {
                 const float feq_t = calc_eq(1.0f, a.u_inlet, 0.0f, 0.0f, lat_w(K), (float)lat_cx(K), (float)lat_cy(K), (float)lat_cz(K));
-                f[K] = vadd(VMUL(f[K], om), VMUL(V(feq_t), sp));
+                f.set(K, vadd(VMUL(f.get(K), om), VMUL(V(feq_t), sp)));
             });
         }
     }
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
         omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
     }
 
-    // ---- Pi loop (:308-322): f[k] is replaced by feq_k
+    // ---- Pi loop (:308-322): the stored f_k is replaced by feq_k
     const v2 usq15 = VMUL(V(1.5f), usq);
     const v2 rw0 = VMUL(rho, V(lat_w(13))), rw1 = VMUL(rho, V(lat_w(12))), rw2 = VMUL(rho, V(lat_w(9))), rw3 = VMUL(rho, V(lat_w(0)));
     v2 Pxx = V(0.f), Pyy = V(0.f), Pzz = V(0.f), Pxy = V(0.f), Pyz = V(0.f), Pzx = V(0.f);
@@ -314,8 +337,8 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
             poly = vsub(vadd(vadd(V(1.0f), VMUL(V(3.0f), cu)), VMUL(VMUL(V(4.5f), cu), cu)), usq15);
         }
         const v2 feq = VMUL(rw, poly);
-        const v2 fneq = vsub(f[K], feq);
-        f[K] = feq;
+        const v2 fneq = vsub(f.get(K), feq);
+        f.set(K, feq);
         if (cx != 0) Pxx = vadd(Pxx, fneq);
         if (cy != 0) Pyy = vadd(Pyy, fneq);
         if (cz != 0) Pzz = vadd(Pzz, fneq);
@@ -343,7 +366,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
         if (cz * cx != 0) { off = have ? (cz * cx > 0 ? vadd(off, Pzx) : vsub(off, Pzx)) : (cz * cx > 0 ? Pzx : vneg(Pzx)); have = true; }
         const v2 inner = have ? vadd(diag, VMUL(V(2.0f), off)) : diag;     // + 2 * 0 changes nothing
         const v2 fnr = VMUL(V(lat_w(K) * 4.5f), inner);
-        v2 out = vadd(f[K], VMUL(om1, fnr));
+        v2 out = vadd(f.get(K), VMUL(om1, fnr));
         if (FULL && has_force) {
             // force_term = (w 3) * (((cx - ux + 3 cu cx) Fx + (cy - uy + 3 cu cy) Fy) + (cz - uz + 3 cu cz) Fz), cu from u_eq, u from u
             const v2 cu = K == 13 ? V(0.f) : cdot<K>(uxe, uye, uze);
@@ -362,20 +385,89 @@ __global__ void __launch_bounds__(256, 2) k1_strict_kernel(const __grid_constant
     });
 }
 
+
+template <bool FULL, bool VELFB, bool MISS, bool STASH>
+__global__ void __launch_bounds__(256, STASH ? 3 : 2) k1_strict_kernel(const __grid_constant__ K1Args a) {
+    extern __shared__ float2 s_stash[];
+    __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
+    __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
+    const int b = a.list[blockIdx.x];
+    if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
+    __syncthreads();
+    strict_block<FULL, VELFB, MISS, STASH>(a, b, a.f_in, s_fo, s_vo, s_stash);
+}
+
+// ---- TMA variant: persistent CTAs, the block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the block-major
+// layout) staged into shared memory by ONE cp.async.bulk per block, double-buffered: while a CTA computes block i the copy
+// engine already fills the other stage with block i + gridDim.x, whatever the register-limited occupancy (2 CTAs x 128
+// registers per SM) would allow the LSU to keep in flight.  What comes from the 26 neighbour blocks (23 % of the pulled values:
+// faces, edges, corners — strided 4-byte elements, not expressible as a bulk copy) and the velocities stay direct loads; the next
+// block's own velocities are prefetched into L2.  Same strict_block body, same bits.
+template <bool FULL, bool VELFB, bool MISS>
+__global__ void __launch_bounds__(256, 2) k1_strict_tma_kernel(const __grid_constant__ K1Args a) {
+    extern __shared__ __align__(128) float s_tile[];              // [2][TILE_FLOATS]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ long long s_fo[2][27], s_vo[2][27];
+    const int t = threadIdx.x;
+    const int n_iter = (a.n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0 && n_iter > 0) {
+        mbar_expect_tx(&s_bar[0], TILE_BYTES);
+        bulk_load(s_tile, a.f_in + (size_t)a.list[blockIdx.x] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
+    }
+    // the same address as a.f_in, but of unknown provenance: the compiler must emit generic loads (own-block reads hit shared memory)
+    const float* fbase;
+    asm volatile("mov.u64 %0, %1;" : "=l"(fbase) : "l"(a.f_in));
+    for (int it = 0; it < n_iter; ++it) {
+        const int cur = it & 1;
+        const int b = a.list[blockIdx.x + it * gridDim.x];
+        const float* tile = s_tile + cur * TILE_FLOATS;
+        if (t < 27) neighbour_offsets(a, b, t, (long long)(((long long)(uintptr_t)tile - (long long)(uintptr_t)a.f_in) >> 2), s_fo[cur], s_vo[cur]);
+        // one barrier per iteration: publishes this block's tables, and every warp has finished reading the OTHER stage (previous
+        // iteration) before thread 0 lets the copy engine overwrite it
+        __syncthreads();
+        if (it + 1 < n_iter) {
+            const int bn = a.list[blockIdx.x + (it + 1) * gridDim.x];
+            if (t == 0) {
+                mbar_expect_tx(&s_bar[cur ^ 1], TILE_BYTES);
+                bulk_load(s_tile + (cur ^ 1) * TILE_FLOATS, a.f_in + (size_t)bn * TILE_FLOATS, TILE_BYTES, &s_bar[cur ^ 1]);
+            } else if (t >= 32 && t < 32 + 48) {   // the next block's own velocities (6 KiB = 48 lines) into L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_in + (size_t)bn * (3 * BS3) + (t - 32) * 32));
+            }
+        }
+        mbar_wait(&s_bar[cur], (uint32_t)((it >> 1) & 1));
+        strict_block<FULL, VELFB, MISS, false>(a, b, fbase, s_fo[cur], s_vo[cur], nullptr);
+    }
+}
+
 }  // namespace k1s
 
-void launch_k1s_plain(const K1Args& a, cudaStream_t s) {
-    if (a.n_list > 0) k1s::k1_strict_kernel<false, false, false><<<a.n_list, 256, 0, s>>>(a);
+constexpr int STASH_BYTES = 27 * 256 * (int)sizeof(float2);   // 55 296
+// variant: 0 registers (2 CTAs / SM), 1 shared-memory stash (3 CTAs / SM), 2 persistent TMA-staged (2 CTAs / SM, double-buffered tiles)
+template <bool FULL, bool VELFB, bool MISS>
+void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
+    if (a.n_list <= 0) return;
+    if (variant == 2) {
+        static const cudaError_t once = cudaFuncSetAttribute(k1s::k1_strict_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)k1s::TILE_BYTES);
+        static const cudaError_t once2 = cudaFuncSetAttribute(k1s::k1_strict_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        (void)once; (void)once2;
+        const int grid = a.n_list < 2 * a.num_sms ? a.n_list : 2 * a.num_sms;
+        k1s::k1_strict_tma_kernel<FULL, VELFB, MISS><<<grid, 256, 2 * k1s::TILE_BYTES, s>>>(a);
+    } else if (variant == 1) {
+        static const cudaError_t once = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STASH_BYTES);
+        static const cudaError_t once2 = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        (void)once; (void)once2;
+        k1s::k1_strict_kernel<FULL, VELFB, MISS, true><<<a.n_list, 256, STASH_BYTES, s>>>(a);
+    } else k1s::k1_strict_kernel<FULL, VELFB, MISS, false><<<a.n_list, 256, 0, s>>>(a);
 }
-void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) {
-    if (a.n_list > 0) k1s::k1_strict_kernel<false, true, false><<<a.n_list, 256, 0, s>>>(a);
-}
-void launch_k1s_feat(const K1Args& a, cudaStream_t s) {
-    if (a.n_list > 0) k1s::k1_strict_kernel<true, true, false><<<a.n_list, 256, 0, s>>>(a);
-}
-void launch_k1s_full(const K1Args& a, cudaStream_t s) {
-    if (a.n_list > 0) k1s::k1_strict_kernel<true, true, true><<<a.n_list, 256, 0, s>>>(a);
-}
+void launch_k1s_plain(const K1Args& a, cudaStream_t s) { launch_strict<false, false, false>(a, a.strict_stash, s); }
+void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) { launch_strict<false, true, false>(a, a.strict_stash, s); }
+void launch_k1s_feat(const K1Args& a, cudaStream_t s) { launch_strict<true, true, false>(a, a.strict_stash, s); }
+void launch_k1s_full(const K1Args& a, cudaStream_t s) { launch_strict<true, true, true>(a, a.strict_stash, s); }
 void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s) {
     if (g.n > 0) k1s::ghost_interp_kernel<<<(g.n + 127) / 128, 128, 0, s>>>(g);
 }

@@ -193,6 +193,8 @@ struct ludwig_ctx {
     bool serial_prepass = false;             // "serial_prepass"
     bool opt_block_prepass = false;          // "prepass" = block
     bool opt_strict_generic = false;         // "strict_generic"
+    int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
+    int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
     bool verbose = false;                    // "verbose"
     std::string remote_order = "morton";     // "remote_order"
     double barrier_timeout_s = 20.0;         // "barrier_timeout_s"
@@ -252,6 +254,9 @@ struct K1Args {
     const int32_t* pptr; int pdimx, pdimy, pdimz;
     float tau, tau_parent, c_wale, nu_bg, u_inlet, inlet_turb, tw;
     int is_l1, is_symmetric, nxg, nyg, nzg, wm, seed, use_temporal, sponge_blend;
+    int strict_stash;       // strict build variant: 0 populations in registers (2 CTAs / SM), 1 shared-memory stash (3 CTAs / SM), 2 persistent TMA-staged
+    int fast_variant;       // fast build variant: 0 direct loads, 2 persistent TMA-staged
+    int num_sms;
     float negzero;          // -0.0f, opaque to ptxas: the strict build's packed multiply is FFMA2(a, b, negzero) (k1_strict.cu)
 };
 

@@ -161,3 +161,27 @@ def test_options_are_validated(cuda_lib):
         with pytest.raises(cabi.LudwigError):     # partition rule is fixed once a level exists
             c.set_option("partition", "morton")
 
+
+
+@pytest.mark.parametrize("variant", ["stash", "tma"])
+@pytest.mark.parametrize("wall_model", [False, True])
+def test_strict_kernel_variants_are_bit_identical(cuda_lib, variant, wall_model):
+    """The three forms of the strict K1 — pulled populations in registers (default), in a shared-memory stash (3 CTAs / SM),
+    persistent CTAs with cp.async.bulk (TMA) staged double-buffered block tiles — run the same strict_block body: same bits on
+    the two-level case with every feature (all four launch classes, ghost blocks, domain faces, obstacles, sponge, wall model)."""
+    levels = build_case()
+    a, *_ = run(cuda_lib, levels, 12, 1, wall_model)
+    b, *_ = run(cuda_lib, levels, 12, 1, wall_model, options={"strict_kernel": variant})
+    for lvl in a:
+        for name in a[lvl]:
+            assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (variant, lvl, name)
+
+
+def test_fast_tma_kernel_variant_is_bit_identical(cuda_lib):
+    """fast_kernel = tma (persistent CTAs, cp.async.bulk staged tiles) runs the same fast_block body as the direct-load kernel."""
+    levels = build_case()
+    a, *_ = run(cuda_lib, levels, 12, 0, True)
+    b, *_ = run(cuda_lib, levels, 12, 0, True, options={"fast_kernel": "tma"})
+    for lvl in a:
+        for name in a[lvl]:
+            assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (lvl, name)

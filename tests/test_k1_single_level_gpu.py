@@ -13,8 +13,8 @@ from util import default_params, fetch_state, load_state, rel_err_rho_u
 pytestmark = pytest.mark.gpu
 
 
-def run(lib, lv, state, params, steps, u=0.03):
-    with cabi.Context(lib) as c:
+def run(lib, lv, state, params, steps, u=0.03, options=None):
+    with cabi.Context(lib, options=options) as c:
         c.add_level(lv)
         load_state(c, 0, *state)
         c.step_batch(1, steps, u, params)
@@ -53,3 +53,28 @@ def test_fast_within_tolerance(oracle_lib, cuda_lib):
         e_rho, e_u = rel_err_rho_u(ref, got)
         assert e_rho <= tol_rho and e_u <= tol_u, (steps, e_rho, e_u)
         assert float(np.max(np.abs(ref["f"] - got["f"]))) < 2e-6
+
+
+@pytest.mark.parametrize("variant", ["stash", "tma"])
+def test_strict_kernel_variants_on_a_box_larger_than_the_persistent_grid(oracle_lib, cuda_lib, variant):
+    """12 x 8 x 8 = 768 blocks > 2 x 148 persistent CTAs: every CTA of the TMA variant walks several blocks (both tile stages,
+    both mbarrier phases) — still the oracle's bits."""
+    dims = (12, 8, 8)
+    lv = syn.make_box_level(*dims)
+    state = syn.noise_state(lv)
+    p = default_params(tuple(8 * d for d in dims), strict=1)
+    ref, _ = run(oracle_lib, lv, state, p, 5)
+    got, _ = run(cuda_lib, lv, state, p, 5, options={"strict_kernel": variant})
+    for name in ref:
+        assert np.array_equal(ref[name].view(np.int32), got[name].view(np.int32)), (variant, name)
+
+
+def test_fast_tma_kernel_variant_on_a_box_larger_than_the_persistent_grid(cuda_lib):
+    dims = (12, 8, 8)
+    lv = syn.make_box_level(*dims)
+    state = syn.noise_state(lv)
+    p = default_params(tuple(8 * d for d in dims), strict=0)
+    ref, _ = run(cuda_lib, lv, state, p, 5)
+    got, _ = run(cuda_lib, lv, state, p, 5, options={"fast_kernel": "tma"})
+    for name in ref:
+        assert np.array_equal(ref[name].view(np.int32), got[name].view(np.int32)), name
