@@ -113,6 +113,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default 40000)
  *   strict_kernel = reg | stash | tma strict K1 variant: pulled populations in registers (2 CTAs / SM), in a shared-memory stash
  *                                     (3 CTAs / SM), or persistent CTAs with cp.async.bulk (TMA) staged, double-buffered block tiles
+ *   cta_threads = 256 | 128 | 64      threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
  *   fast_kernel = direct | tma        fast K1 variant: direct loads, or the persistent TMA-staged form (identical bits either way)
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
  *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)
@@ -150,6 +151,17 @@ int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* d
  * blocks = 1-based reference block indices (b_idx of :27); in a multi-GPU context they must be blocks of this rank. */
 int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const int32_t* blocks, int32_t n_blocks,
                          float* rho_arr, float* vel_mat, uint8_t* obst_arr);
+
+/* io_vtk.jl:17-46: the blocks export_merged_mesh_sync writes — every block that is NOT fully covered by the next finer level (all 8
+ * children active) — computed on the device from the block-pointer tables and cached.  n_valid[level] = their number per level;
+ * blocks (or NULL) receives the 1-based b_idx lists of all levels one after the other (level-major, b_idx ascending: the order of
+ * the reference's `valid_blocks`). */
+int ludwig_output_valid_blocks(ludwig_ctx* ctx, int32_t* n_valid /* [levels] */, int32_t* blocks /* [sum n_valid] or NULL */);
+/* io_vtk.jl:52-58 + 100-111 in one call: the fields of ALL valid blocks in the writer's order, N = 512 * sum(n_valid) cells:
+ * rho_arr Float32[N], vel_mat Float32[3, N], obst_arr UInt8[N], level_arr Int32[N] (or NULL).  Only the valid blocks leave the device,
+ * through pinned, double-buffered staging (the device gathers chunk i + 1 while chunk i is copied out).  In a multi-GPU context
+ * every rank fills the cells of its own blocks and leaves the rest of the arrays untouched. */
+int ludwig_output_export(ludwig_ctx* ctx, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr);
 
 /* main.jl:101  Geometry.upload_mesh_to_gpu (geometry.jl:60-84): Float32 SoA. */
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n_triangles,
@@ -289,6 +301,8 @@ int ludwig_multi_forces_create(ludwig_multi* m, int32_t n_triangles, const float
 int ludwig_multi_compute_aerodynamics(ludwig_multi* m, int32_t handle, int32_t level, const double mesh_offset[3],
                                       double velocity_scale, double rho_phys, int32_t search_radius, double out[18]);   /* main.jl:197,223 */
 int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p, float* sx, float* sy, float* sz);
+int ludwig_multi_output_valid_blocks(ludwig_multi* m, int32_t* n_valid, int32_t* blocks);                               /* io_vtk.jl:17-46 */
+int ludwig_multi_output_export(ludwig_multi* m, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr);   /* io_vtk.jl:52-111 */
 int64_t ludwig_multi_device_bytes(const ludwig_multi* m);
 
 /* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */

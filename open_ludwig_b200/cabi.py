@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_multi_level_download", "ludwig_multi_init_equilibrium", "ludwig_multi_step_batch", "ludwig_multi_sync",
     "ludwig_multi_flow_stats", "ludwig_multi_forces_create", "ludwig_multi_compute_aerodynamics",
     "ludwig_multi_forces_download_maps", "ludwig_multi_device_bytes",
+    "ludwig_output_valid_blocks", "ludwig_output_export", "ludwig_multi_output_valid_blocks", "ludwig_multi_output_export",
 )
 
 BARRIER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)   # returns 0 on success (include/ludwig_b200.h)
@@ -147,6 +148,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_multi_compute_aerodynamics": (C.c_int, [vp, i32, i32, C.POINTER(f64), f64, f64, i32, C.POINTER(f64)]),
         "ludwig_multi_forces_download_maps": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "ludwig_multi_device_bytes": (C.c_int64, [vp]),
+        "ludwig_output_valid_blocks": (C.c_int, [vp, vp, vp]),
+        "ludwig_output_export": (C.c_int, [vp, i64, vp, vp, vp, vp]),
+        "ludwig_multi_output_valid_blocks": (C.c_int, [vp, vp, vp]),
+        "ludwig_multi_output_export": (C.c_int, [vp, i64, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
@@ -274,6 +279,16 @@ class Context:
 
     def device_bytes(self) -> int:
         return int(self.lib.ludwig_device_bytes(self._h))
+
+    _VALID, _EXPORT = "ludwig_output_valid_blocks", "ludwig_output_export"
+
+    def output_valid_blocks(self):
+        """io_vtk.jl:17-46: per level, the 0-based reference indices of the blocks the VTK export writes."""
+        return _valid_blocks(self, len(self.n_blocks))
+
+    def output_export(self, t_step: int):
+        """io_vtk.jl:52-58,100-111 for every valid block: (rho_arr [N], vel_mat [N, 3], obst_arr [N], level_arr [N])."""
+        return _export(self, t_step, len(self.n_blocks))
 
     @property
     def stream_ptr(self) -> int:
@@ -494,6 +509,26 @@ class Context:
         return dict(zip(self.STATS_KEYS, list(out)))
 
 
+def _valid_blocks(obj, n_levels):
+    n = np.zeros(n_levels, np.int32)
+    obj._check(getattr(obj.lib, obj._VALID)(obj._h, _ptr(n), None), obj._VALID)
+    flat = np.empty(int(n.sum()), np.int32)
+    obj._check(getattr(obj.lib, obj._VALID)(obj._h, _ptr(n), _ptr(flat)), obj._VALID)
+    out, o = [], 0
+    for c in n:
+        out.append(flat[o:o + c] - 1); o += c
+    return out
+
+
+def _export(obj, t_step, n_levels):
+    n = np.zeros(n_levels, np.int32)
+    obj._check(getattr(obj.lib, obj._VALID)(obj._h, _ptr(n), None), obj._VALID)
+    N = 512 * int(n.sum())
+    rho = np.zeros(N, np.float32); vel = np.zeros((N, 3), np.float32); obs = np.zeros(N, np.uint8); lvl = np.zeros(N, np.int32)
+    obj._check(getattr(obj.lib, obj._EXPORT)(obj._h, t_step, _ptr(rho), _ptr(vel), _ptr(obs), _ptr(lvl)), obj._EXPORT)
+    return rho, vel, obs, lvl
+
+
 class MultiContext:
     """ludwig_multi: N ranks (N GPUs, or N virtual ranks on one GPU) driven by this one thread.  Same call sequence as
     ``Context`` for what the kept Julia driver does (main.jl:54-249); ``create_forces`` takes the mesh arrays directly."""
@@ -606,3 +641,11 @@ class MultiContext:
 
     def device_bytes(self) -> int:
         return int(self.lib.ludwig_multi_device_bytes(self._h))
+
+    _VALID, _EXPORT = "ludwig_multi_output_valid_blocks", "ludwig_multi_output_export"
+
+    def output_valid_blocks(self):
+        return _valid_blocks(self, len(self.n_blocks))
+
+    def output_export(self, t_step: int):
+        return _export(self, t_step, len(self.n_blocks))

@@ -416,7 +416,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms;
+    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.cta_threads = ctx->opt_cta_threads;
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -499,6 +499,12 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
         auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream, bool ghosts) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
+            if ((strict ? a.strict_stash : a.fast_variant) == 2) {   // persistent variant: its ticket counter (one per launch class)
+                const int cls = fn == k_plain ? 0 : fn == k_plain_g ? 1 : fn == k_feat ? 2 : 3;
+                const int grid = n < 2 * ctx->num_sms ? n : 2 * ctx->num_sms;
+                a.ticket = ctx->d_ticket + cls; a.ticket_base = ctx->ticket_base[cls];
+                ctx->ticket_base[cls] += (unsigned long long)n + (unsigned long long)grid;   // every CTA draws one ticket past the end
+            }
             if ((!fork && !(fork_full && fn == k_full)) || main_stream) {
                 if (overlap_pre && ghosts) { CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0)); overlap_pre = false; }
                 fn(a, ctx->stream);
@@ -748,6 +754,10 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
         if (!ok) { delete ctx; return LUDWIG_ECUDA; }
     }
     // Every behaviour switch is an explicit option (ludwig_ctx_set_option); the library reads no environment variable.
+    if (cudaMalloc((void**)&ctx->d_ticket, 4 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(ctx->d_ticket, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return LUDWIG_ENOMEM;
+    }
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {
         delete ctx;
@@ -761,11 +771,13 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     if (!ctx) return LUDWIG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ludwig_output_state_free(ctx);
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (Level* L : ctx->levels) free_level(L);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->h_bar_err) cudaFreeHost(ctx->h_bar_err);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -795,6 +807,10 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
     else if (k == "strict_kernel") {            // where the strict K1 keeps the 27 pulled populations / how it loads them
         if (v == "reg") ctx->opt_strict_variant = 0; else if (v == "stash") ctx->opt_strict_variant = 1; else if (v == "tma") ctx->opt_strict_variant = 2;
         else return fail(ctx, LUDWIG_EINVAL, "strict_kernel: reg | stash | tma");
+    } else if (k == "cta_threads") {            // threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
+        const int n = atoi(value);
+        if (n != 256 && n != 128 && n != 64) return fail(ctx, LUDWIG_EINVAL, "cta_threads: 256 | 128 | 64");
+        ctx->opt_cta_threads = n;
     } else if (k == "fast_kernel") {
         if (v == "direct") ctx->opt_fast_variant = 0; else if (v == "tma") ctx->opt_fast_variant = 2;
         else return fail(ctx, LUDWIG_EINVAL, "fast_kernel: direct | tma");
@@ -1204,38 +1220,6 @@ int ludwig_level_download(ludwig_ctx* ctx, int32_t level, int32_t which, void* d
     int rc = resolve_field(ctx, L, which, false, &p, &ncomp);
     if (rc) return rc;
     return download_field(ctx, L, p, (float*)dst, ncomp);
-}
-
-// N3 (io_vtk.jl:52-58,100-111): device-side gather of the listed blocks into the VTK writer's arrays.
-int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const int32_t* blocks, int32_t n_blocks,
-                         float* rho_arr, float* vel_mat, uint8_t* obst_arr) {
-    if (!level_ok(ctx, level) || !blocks || n_blocks < 0 || !rho_arr || !vel_mat || !obst_arr) return fail(ctx, LUDWIG_EINVAL, "bad gather args");
-    if (n_blocks == 0) return LUDWIG_OK;
-    CU(cudaSetDevice(ctx->device));
-    Level& L = *ctx->levels[level];
-    std::vector<int32_t> sel(n_blocks);
-    for (int i = 0; i < n_blocks; ++i) {
-        const int br = blocks[i] - 1;
-        if (br < 0 || br >= L.nb_global) return fail(ctx, LUDWIG_EINVAL, "gather: block index out of range");
-        const int loc = L.ref2int[br] - L.part_start;
-        if (loc < 0 || loc >= L.nb) return fail(ctx, LUDWIG_EINVAL, "gather: block belongs to another rank");
-        sel[i] = loc;
-    }
-    const size_t nc = (size_t)n_blocks * BS3;
-    int32_t* d_sel = nullptr; float* d_out = nullptr; uint8_t* d_obs = nullptr;
-    struct Free { int32_t*& a; float*& b; uint8_t*& c; ~Free() { if (a) cudaFree(a); if (b) cudaFree(b); if (c) cudaFree(c); } } guard{d_sel, d_out, d_obs};
-    CU(cudaMalloc((void**)&d_sel, (size_t)n_blocks * 4));
-    CU(cudaMalloc((void**)&d_out, nc * 4 * sizeof(float)));   // rho [nc] followed by vel [3 nc]
-    CU(cudaMalloc((void**)&d_obs, nc));
-    CU(cudaMemcpyAsync(d_sel, sel.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const float* vel = (t_step % 2 == 0) ? L.d_vel[1] : L.d_vel[0];   // io_vtk.jl:56
-    launch_output_gather(d_sel, n_blocks, L.d_rho[L.rho_cur], vel, L.d_obstacle, d_out, d_out + nc, d_obs, ctx->stream);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(rho_arr, d_out, nc * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(vel_mat, d_out + nc, nc * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(obst_arr, d_obs, nc, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return LUDWIG_OK;
 }
 
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n, const float* cx, const float* cy, const float* cz, const float* nx, const float* ny,
@@ -1916,6 +1900,18 @@ int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p,
         if (rc) return mpass(m, m->ctx[r], rc);
         for (int j = 0; j < 4; ++j) if (dst[j]) for (int i = r; i < n; i += W) dst[j][i] = t[j][i];
     }
+    return LUDWIG_OK;
+}
+
+// io_vtk.jl:17-59 over all ranks: the valid-block list is the same on every rank; every rank writes its own blocks' cells
+// into the caller's arrays (disjoint positions)
+int ludwig_multi_output_valid_blocks(ludwig_multi* m, int32_t* n_valid, int32_t* blocks) {
+    if (!m) return LUDWIG_EINVAL;
+    return mpass(m, m->ctx[0], ludwig_output_valid_blocks(m->ctx[0], n_valid, blocks));
+}
+int ludwig_multi_output_export(ludwig_multi* m, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_output_export(c, t_step, rho_arr, vel_mat, obst_arr, level_arr); if (rc) return mpass(m, c, rc); }
     return LUDWIG_OK;
 }
 

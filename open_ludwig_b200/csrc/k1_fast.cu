@@ -121,8 +121,7 @@ __device__ __forceinline__ float3 wall_force(float dist_wall, float rho, float u
 //        MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh; blocks with features but all 26
 //        neighbours present (the near-body bulk) use FULL without MISS and never carry that code.
 template <bool FULL, bool VELFB, bool MISS>
-__device__ __forceinline__ void fast_block(const K1Args& a, const int b, const float* __restrict__ fbase, const long long* s_fo, const long long* s_vo) {
-    const int t = threadIdx.x;
+__device__ __forceinline__ void fast_block(const K1Args& a, const int b, const int t, const float* __restrict__ fbase, const long long* s_fo, const long long* s_vo) {
     const int p = t & 3, y = (t >> 2) & 7, z = t >> 5;
     const int x0 = 2 * p;
     const int c0 = 2 * t;   // z*64 + y*8 + x0
@@ -413,14 +412,15 @@ __device__ __forceinline__ void fast_block(const K1Args& a, const int b, const f
 // fall back to the cell's own value (physics_utils.jl:69).
 //        MISS : some neighbour block may be absent (domain face) -> k1_boundary.cuh; blocks with features but all 26
 //        neighbours present (the near-body bulk) use FULL without MISS and never carry that code.
-template <bool FULL, bool VELFB, bool MISS, int MINB>
-__global__ void __launch_bounds__(256, MINB) k1_fast_kernel(const __grid_constant__ K1Args a) {
+template <bool FULL, bool VELFB, bool MISS, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB * (256 / NT)) k1_fast_kernel(const __grid_constant__ K1Args a) {
     __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
     __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
-    const int b = a.list[blockIdx.x];
+    constexpr int PARTS = 256 / NT;  // NT = 128 / 64: a CTA takes 4 / 2 of the block's z-planes (option cta_threads)
+    const int b = a.list[blockIdx.x / PARTS];
     if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
     __syncthreads();
-    fast_block<FULL, VELFB, MISS>(a, b, a.f_in, s_fo, s_vo);
+    fast_block<FULL, VELFB, MISS>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo);
 }
 
 // TMA variant (option fast_kernel = tma): persistent CTAs, the block's own populations staged into shared memory by one
@@ -432,27 +432,36 @@ __global__ void __launch_bounds__(256, 2) k1_fast_tma_kernel(const __grid_consta
     extern __shared__ __align__(128) float s_tile[];              // [2][TILE_FLOATS]
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ long long s_fo[2][27], s_vo[2][27];
+    __shared__ int s_blk[2];          // block of this / the next iteration (-1: the list is exhausted)
     const int t = threadIdx.x;
-    const int n_iter = (a.n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (t == 0) {
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long i0 = atomicAdd(a.ticket, 1ull) - a.ticket_base;
+        s_blk[0] = i0 < (unsigned long long)a.n_list ? a.list[i0] : -1;
     }
     __syncthreads();
-    if (t == 0 && n_iter > 0) {
+    if (t == 0 && s_blk[0] >= 0) {
         mbar_expect_tx(&s_bar[0], TILE_BYTES);
-        bulk_load(s_tile, a.f_in + (size_t)a.list[blockIdx.x] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
+        bulk_load(s_tile, a.f_in + (size_t)s_blk[0] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
     }
     const float* fbase;   // a.f_in with its global provenance hidden: own-block reads hit shared memory, the loads must be generic
     asm volatile("mov.u64 %0, %1;" : "=l"(fbase) : "l"(a.f_in));
-    for (int it = 0; it < n_iter; ++it) {
+    for (int it = 0;; ++it) {
         const int cur = it & 1;
-        const int b = a.list[blockIdx.x + it * gridDim.x];
+        const int b = s_blk[cur];
+        if (b < 0) break;
         const float* tile = s_tile + cur * TILE_FLOATS;
         if (t < 27) neighbour_offsets(a, b, t, (long long)(((long long)(uintptr_t)tile - (long long)(uintptr_t)a.f_in) >> 2), s_fo[cur], s_vo[cur]);
-        __syncthreads();   // publishes the tables; every warp is done with the other stage before the copy engine overwrites it
-        if (it + 1 < n_iter) {
-            const int bn = a.list[blockIdx.x + (it + 1) * gridDim.x];
+        if (t == 32) {   // the next ticket: blocks are handed out in list (Morton) order, whichever CTA asks first
+            const unsigned long long i1 = atomicAdd(a.ticket, 1ull) - a.ticket_base;
+            s_blk[cur ^ 1] = i1 < (unsigned long long)a.n_list ? a.list[i1] : -1;
+        }
+        // one barrier per iteration: publishes this block's tables and the next block's index, and every warp is done with the
+        // OTHER stage (previous iteration) before thread 0 lets the copy engine overwrite it
+        __syncthreads();
+        const int bn = s_blk[cur ^ 1];
+        if (bn >= 0) {
             if (t == 0) {
                 mbar_expect_tx(&s_bar[cur ^ 1], TILE_BYTES);
                 bulk_load(s_tile + (cur ^ 1) * TILE_FLOATS, a.f_in + (size_t)bn * TILE_FLOATS, TILE_BYTES, &s_bar[cur ^ 1]);
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(256, 2) k1_fast_tma_kernel(const __grid_consta
             }
         }
         mbar_wait(&s_bar[cur], (uint32_t)((it >> 1) & 1));
-        fast_block<FULL, VELFB, MISS>(a, b, fbase, s_fo[cur], s_vo[cur]);
+        fast_block<FULL, VELFB, MISS>(a, b, t, fbase, s_fo[cur], s_vo[cur]);
     }
 }
 
@@ -476,7 +485,9 @@ void launch_fast(const K1Args& a, cudaStream_t s) {
         (void)once; (void)once2;
         const int grid = a.n_list < 2 * a.num_sms ? a.n_list : 2 * a.num_sms;
         k1f::k1_fast_tma_kernel<FULL, VELFB, MISS><<<grid, 256, 2 * k1f::TILE_BYTES, s>>>(a);
-    } else k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB><<<a.n_list, 256, 0, s>>>(a);
+    } else if (a.cta_threads == 128) k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB, 128><<<2 * a.n_list, 128, 0, s>>>(a);
+    else if (a.cta_threads == 64) k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB, 64><<<4 * a.n_list, 64, 0, s>>>(a);
+    else k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB, 256><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1_plain(const K1Args& a, cudaStream_t s) { launch_fast<false, false, false, 3>(a, s); }
 void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) { launch_fast<false, true, false, 3>(a, s); }

@@ -115,7 +115,7 @@ template <> struct FStore<false> {
 };
 template <> struct FStore<true> {
     float2* s;   // already offset by the thread index
-    __device__ __forceinline__ FStore(float2* base) : s(base + threadIdx.x) {}
+    __device__ __forceinline__ FStore(float2* base) : s(base + threadIdx.x) {}   // (the stash variant runs whole-block CTAs)
     __device__ __forceinline__ v2 get(int k) const { return s[k * 256]; }
     __device__ __forceinline__ void set(int k, v2 v) { s[k * 256] = v; }
 };
@@ -127,9 +127,8 @@ template <> struct FStore<true> {
 // a.f_in, or — TMA variant — the same address with its global provenance hidden, because s_fo[13] then points into shared memory
 // and the loads must be generic).
 template <bool FULL, bool VELFB, bool MISS, bool STASH>
-__device__ __forceinline__ void strict_block(const K1Args& a, const int b, const float* __restrict__ fbase, const long long* s_fo,
+__device__ __forceinline__ void strict_block(const K1Args& a, const int b, const int t, const float* __restrict__ fbase, const long long* s_fo,
                                              const long long* s_vo, float2* s_stash) {
-    const int t = threadIdx.x;
     const v2 NZ = V(a.negzero);
 
     const int p = t & 3, y = (t >> 2) & 7, z = t >> 5;
@@ -386,15 +385,18 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
 }
 
 
-template <bool FULL, bool VELFB, bool MISS, bool STASH>
-__global__ void __launch_bounds__(256, STASH ? 3 : 2) k1_strict_kernel(const __grid_constant__ K1Args a) {
+// NT threads per CTA: 256 = one CTA per block; 128 / 64 = a CTA takes 4 / 2 of the block's z-planes, so that more, smaller CTAs are
+// resident per SM and their load and compute phases interleave (the register-limited occupancy is the same number of warps).
+template <bool FULL, bool VELFB, bool MISS, bool STASH, int NT>
+__global__ void __launch_bounds__(NT, (STASH ? 3 : 2) * (256 / NT)) k1_strict_kernel(const __grid_constant__ K1Args a) {
     extern __shared__ float2 s_stash[];
     __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
     __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
-    const int b = a.list[blockIdx.x];
+    constexpr int PARTS = 256 / NT;
+    const int b = a.list[blockIdx.x / PARTS];
     if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
     __syncthreads();
-    strict_block<FULL, VELFB, MISS, STASH>(a, b, a.f_in, s_fo, s_vo, s_stash);
+    strict_block<FULL, VELFB, MISS, STASH>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo, s_stash);
 }
 
 // ---- TMA variant: persistent CTAs, the block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the block-major
@@ -408,30 +410,36 @@ __global__ void __launch_bounds__(256, 2) k1_strict_tma_kernel(const __grid_cons
     extern __shared__ __align__(128) float s_tile[];              // [2][TILE_FLOATS]
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ long long s_fo[2][27], s_vo[2][27];
+    __shared__ int s_blk[2];          // block of this / the next iteration (-1: the list is exhausted)
     const int t = threadIdx.x;
-    const int n_iter = (a.n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (t == 0) {
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long i0 = atomicAdd(a.ticket, 1ull) - a.ticket_base;
+        s_blk[0] = i0 < (unsigned long long)a.n_list ? a.list[i0] : -1;
     }
     __syncthreads();
-    if (t == 0 && n_iter > 0) {
+    if (t == 0 && s_blk[0] >= 0) {
         mbar_expect_tx(&s_bar[0], TILE_BYTES);
-        bulk_load(s_tile, a.f_in + (size_t)a.list[blockIdx.x] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
+        bulk_load(s_tile, a.f_in + (size_t)s_blk[0] * TILE_FLOATS, TILE_BYTES, &s_bar[0]);
     }
-    // the same address as a.f_in, but of unknown provenance: the compiler must emit generic loads (own-block reads hit shared memory)
-    const float* fbase;
+    const float* fbase;   // a.f_in with its global provenance hidden: own-block reads hit shared memory, the loads must be generic
     asm volatile("mov.u64 %0, %1;" : "=l"(fbase) : "l"(a.f_in));
-    for (int it = 0; it < n_iter; ++it) {
+    for (int it = 0;; ++it) {
         const int cur = it & 1;
-        const int b = a.list[blockIdx.x + it * gridDim.x];
+        const int b = s_blk[cur];
+        if (b < 0) break;
         const float* tile = s_tile + cur * TILE_FLOATS;
         if (t < 27) neighbour_offsets(a, b, t, (long long)(((long long)(uintptr_t)tile - (long long)(uintptr_t)a.f_in) >> 2), s_fo[cur], s_vo[cur]);
-        // one barrier per iteration: publishes this block's tables, and every warp has finished reading the OTHER stage (previous
-        // iteration) before thread 0 lets the copy engine overwrite it
+        if (t == 32) {   // the next ticket: blocks are handed out in list (Morton) order, whichever CTA asks first
+            const unsigned long long i1 = atomicAdd(a.ticket, 1ull) - a.ticket_base;
+            s_blk[cur ^ 1] = i1 < (unsigned long long)a.n_list ? a.list[i1] : -1;
+        }
+        // one barrier per iteration: publishes this block's tables and the next block's index, and every warp is done with the
+        // OTHER stage (previous iteration) before thread 0 lets the copy engine overwrite it
         __syncthreads();
-        if (it + 1 < n_iter) {
-            const int bn = a.list[blockIdx.x + (it + 1) * gridDim.x];
+        const int bn = s_blk[cur ^ 1];
+        if (bn >= 0) {
             if (t == 0) {
                 mbar_expect_tx(&s_bar[cur ^ 1], TILE_BYTES);
                 bulk_load(s_tile + (cur ^ 1) * TILE_FLOATS, a.f_in + (size_t)bn * TILE_FLOATS, TILE_BYTES, &s_bar[cur ^ 1]);
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_tma_kernel(const __grid_cons
             }
         }
         mbar_wait(&s_bar[cur], (uint32_t)((it >> 1) & 1));
-        strict_block<FULL, VELFB, MISS, false>(a, b, fbase, s_fo[cur], s_vo[cur], nullptr);
+        strict_block<FULL, VELFB, MISS, false>(a, b, t, fbase, s_fo[cur], s_vo[cur], nullptr);
     }
 }
 
@@ -458,11 +466,13 @@ void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
         const int grid = a.n_list < 2 * a.num_sms ? a.n_list : 2 * a.num_sms;
         k1s::k1_strict_tma_kernel<FULL, VELFB, MISS><<<grid, 256, 2 * k1s::TILE_BYTES, s>>>(a);
     } else if (variant == 1) {
-        static const cudaError_t once = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STASH_BYTES);
-        static const cudaError_t once2 = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        static const cudaError_t once = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, STASH_BYTES);
+        static const cudaError_t once2 = cudaFuncSetAttribute(k1s::k1_strict_kernel<FULL, VELFB, MISS, true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         (void)once; (void)once2;
-        k1s::k1_strict_kernel<FULL, VELFB, MISS, true><<<a.n_list, 256, STASH_BYTES, s>>>(a);
-    } else k1s::k1_strict_kernel<FULL, VELFB, MISS, false><<<a.n_list, 256, 0, s>>>(a);
+        k1s::k1_strict_kernel<FULL, VELFB, MISS, true, 256><<<a.n_list, 256, STASH_BYTES, s>>>(a);
+    } else if (a.cta_threads == 128) k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 128><<<2 * a.n_list, 128, 0, s>>>(a);
+    else if (a.cta_threads == 64) k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64><<<4 * a.n_list, 64, 0, s>>>(a);
+    else k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 256><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1s_plain(const K1Args& a, cudaStream_t s) { launch_strict<false, false, false>(a, a.strict_stash, s); }
 void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) { launch_strict<false, true, false>(a, a.strict_stash, s); }

@@ -195,12 +195,15 @@ struct ludwig_ctx {
     bool opt_strict_generic = false;         // "strict_generic"
     int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
+    int opt_cta_threads = 256;               // "cta_threads" = 256 | 128 | 64
     bool verbose = false;                    // "verbose"
     std::string remote_order = "morton";     // "remote_order"
     double barrier_timeout_s = 20.0;         // "barrier_timeout_s"
     std::vector<ludwig::Level*> levels;
     std::string err;
     int64_t bytes = 0;
+    unsigned long long* d_ticket = nullptr;   // [4] ticket counters of the persistent K1 variants, one per launch class
+    unsigned long long ticket_base[4] = {0, 0, 0, 0};
     double* d_stats = nullptr;   // flow-stats partials
     double* h_stats = nullptr;   // pinned
     int num_sms = 148;
@@ -223,6 +226,7 @@ struct ludwig_ctx {
     bool bar_failed = false;                  // sticky: once a barrier failed every stepping / result call returns LUDWIG_ESTATE
     unsigned int bar_epoch = 0;
     int64_t launches = 0;
+    void* output_state = nullptr;   // output.cu: cached valid-block lists + pinned double-buffered staging (N3)
     // K1 profiling (ludwig_profile_enable)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs (start, stop)
@@ -233,6 +237,8 @@ struct ludwig_ctx {
     size_t ev_used = 0;
     int64_t prof_cells = 0;
 };
+
+void ludwig_output_state_free(ludwig_ctx* ctx);   // output.cu
 
 namespace ludwig {
 
@@ -257,6 +263,10 @@ struct K1Args {
     int strict_stash;       // strict build variant: 0 populations in registers (2 CTAs / SM), 1 shared-memory stash (3 CTAs / SM), 2 persistent TMA-staged
     int fast_variant;       // fast build variant: 0 direct loads, 2 persistent TMA-staged
     int num_sms;
+    int cta_threads;        // 256 (one CTA per block), 128 or 64 (a CTA takes 4 / 2 z-planes of a block)
+    // persistent (TMA) variants: blocks are handed out in list order through an atomic ticket counter, so that the CTAs in flight always
+    // work on a compact window of the Morton curve (halo sectors stay L2 hits); the counter is never reset: block = ticket - ticket_base
+    unsigned long long* ticket; unsigned long long ticket_base;
     float negzero;          // -0.0f, opaque to ptxas: the strict build's packed multiply is FFMA2(a, b, negzero) (k1_strict.cu)
 };
 

@@ -637,6 +637,53 @@ int ludwig_output_gather(ludwig_ctx* ctx, int32_t level, int64_t t_step, const i
     return LUDWIG_OK;
 }
 
+// io_vtk.jl:17-46 restated: a block is exported unless all 8 of its children (2 bx - 1 + dbx, ... in 1-based coordinates) are
+// active blocks of the next finer level; level-major, b_idx ascending (the order of `valid_blocks`).
+static std::vector<std::vector<int32_t>> valid_blocks_of(const ludwig_ctx* ctx) {
+    std::vector<std::vector<int32_t>> out(ctx->levels.size());
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        const Level& L = *ctx->levels[l];
+        const Level* N = l + 1 < ctx->levels.size() ? ctx->levels[l + 1].get() : nullptr;
+        for (int b = 0; b < L.nb; ++b) {
+            bool should_export = true;
+            if (N) {
+                int children = 0;
+                for (int dbz = 0; dbz < 2; ++dbz) for (int dby = 0; dby < 2; ++dby) for (int dbx = 0; dbx < 2; ++dbx) {
+                    const int x = 2 * L.map_x[b] - 1 + dbx, y = 2 * L.map_y[b] - 1 + dby, z = 2 * L.map_z[b] - 1 + dbz;   // 1-based
+                    if (x <= N->dimx && y <= N->dimy && z <= N->dimz && N->block_pointer[(x - 1) + (size_t)N->dimx * ((y - 1) + (size_t)N->dimy * (z - 1))] > 0) ++children;
+                }
+                if (children == 8) should_export = false;
+            }
+            if (should_export) out[l].push_back(b + 1);
+        }
+    }
+    return out;
+}
+int ludwig_output_valid_blocks(ludwig_ctx* ctx, int32_t* n_valid, int32_t* blocks) {
+    if (!ctx || !n_valid) return fail(ctx, LUDWIG_EINVAL, "bad valid-block args");
+    auto v = valid_blocks_of(ctx);
+    size_t o = 0;
+    for (size_t l = 0; l < v.size(); ++l) {
+        n_valid[l] = (int32_t)v[l].size();
+        if (blocks) { std::memcpy(blocks + o, v[l].data(), v[l].size() * sizeof(int32_t)); o += v[l].size(); }
+    }
+    return LUDWIG_OK;
+}
+// io_vtk.jl:52-58,100-111 for all of them
+int ludwig_output_export(ludwig_ctx* ctx, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr) {
+    if (!ctx || !rho_arr || !vel_mat || !obst_arr) return fail(ctx, LUDWIG_EINVAL, "bad export args");
+    auto v = valid_blocks_of(ctx);
+    size_t base = 0;
+    for (size_t l = 0; l < v.size(); ++l) {
+        const size_t o = base * 512;
+        int rc = v[l].empty() ? LUDWIG_OK : ludwig_output_gather(ctx, (int32_t)l, t_step, v[l].data(), (int32_t)v[l].size(), rho_arr + o, vel_mat + 3 * o, obst_arr + o);
+        if (rc) return rc;
+        if (level_arr) std::fill(level_arr + o, level_arr + o + v[l].size() * 512, (int32_t)ctx->levels[l]->level_id);
+        base += v[l].size();
+    }
+    return LUDWIG_OK;
+}
+
 int ludwig_mesh_create(ludwig_ctx* ctx, int32_t n, const float* cx, const float* cy, const float* cz, const float* nx,
                        const float* ny, const float* nz, const float* area, ludwig_mesh** out) {
     if (!ctx || n <= 0 || !out) return fail(ctx, LUDWIG_EINVAL, "bad mesh");
@@ -923,6 +970,8 @@ int ludwig_multi_forces_create(ludwig_multi*, int32_t, const float*, const float
 int ludwig_multi_compute_aerodynamics(ludwig_multi*, int32_t, int32_t, const double*, double, double, int32_t, double*) { return LUDWIG_ESTATE; }
 int ludwig_multi_forces_download_maps(ludwig_multi*, int32_t, float*, float*, float*, float*) { return LUDWIG_ESTATE; }
 int64_t ludwig_multi_device_bytes(const ludwig_multi*) { return 0; }
+int ludwig_multi_output_valid_blocks(ludwig_multi*, int32_t*, int32_t*) { return LUDWIG_ESTATE; }
+int ludwig_multi_output_export(ludwig_multi*, int64_t, float*, float*, uint8_t*, int32_t*) { return LUDWIG_ESTATE; }
 int ludwig_attach_inprocess(ludwig_ctx* ctx, ludwig_ctx* const*, int32_t) { return fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank"); }
 int ludwig_profile_read(ludwig_ctx*, double* ms, int64_t* n, int64_t* c) { if (ms) *ms = 0; if (n) *n = 0; if (c) *c = 0; return LUDWIG_OK; }
 
