@@ -302,7 +302,7 @@ def run_ours(args, rank, local_rank, world):
         try:
             strong = mg.run_case_strong(args.strong_case, args.strong_steps, local_rank, strict=bool(strict),
                                         options={**opts, **({"partition": args.strong_partition} if world > 1 and args.strong_partition != "plan" else {})},
-                                        plan=(world > 1 and args.strong_partition == "plan"), ramp_steps=args.strong_ramp, profile_steps=2,
+                                        plan=(world > 1 and args.strong_partition == "plan"), uniform_start=True, profile_steps=2,
                                         log=lambda m: print(m, file=sys.stderr, flush=True))
             t1 = T1_MS_COMMITTED.get((args.strong_case, "strict" if strict else "fast"))
             if strong["n_gpus"] == 1:
@@ -375,7 +375,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--strong-case", default="bunny_fine", help="case of the strong-scaling record (BASELINE config 5); 'none' skips it")
     ap.add_argument("--strong-steps", type=int, default=24)
-    ap.add_argument("--strong-ramp", type=int, default=16, help="ramp length for the strong record, so that Cd is O(1) after a few coarse steps")
     ap.add_argument("--strong-partition", default=DEFAULT_STRONG_PARTITION, choices=["plan", "morton", "rcb", "rcb_yz"])
     ap.add_argument("--fast-init", action="store_true", help="device-side rest-state initialisation instead of the hashed noise "
                     "state of config 2 (for ncu captures; the line is marked and is not a bench value)")

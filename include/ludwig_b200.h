@@ -113,12 +113,14 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default 40000)
  *   strict_kernel = reg | stash | tma strict K1 variant: pulled populations in registers (2 CTAs / SM), in a shared-memory stash
  *                                     (3 CTAs / SM), or persistent CTAs with cp.async.bulk (TMA) staged, double-buffered block tiles
- *   cta_threads = 256 | 128 | 64      threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
+ *   cta_threads = auto | 256 | 128 | 64   threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
+ *                                     (auto: 64 in strict mode, 128 in fast mode - the measured optimum)
  *   fast_kernel = direct | tma        fast K1 variant: direct loads, or the persistent TMA-staged form (identical bits either way)
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
  *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)
  *   halo_mirror = 0 | 1               packed halo exchange into local mirrors instead of in-kernel NVLink pulls (before the first level)
  *   remote_order = morton | first | last | interleave   place of the blocks that pull from a peer in the plain launch
+ *   graphs = auto | 0 | 1             replay coarse steps as CUDA graphs (auto: multi-level cases on one GPU)
  *   barrier_timeout_s = seconds       time-out of the native cross-GPU barrier (default 20)
  *   verbose = 0 | 1                   per-level table sizes on stderr */
 int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value);
@@ -180,6 +182,11 @@ int ludwig_forces_destroy(ludwig_forces* forces);
 
 /* main.jl:109-135  init_eq! on every level. */
 int ludwig_init_equilibrium(ludwig_ctx* ctx);
+
+/* K0 with a prescribed uniform state instead of rest: f = f_temp = feq(1, (ux, 0, 0)), vel = (ux, 0, 0) (0 in obstacle cells),
+ * rho = 1 on every level.  No reference counterpart (init_eq! is the rest state); it is the initial condition of bench.py's
+ * strong-scaling record: an impulsively started flow gives O(1) surface forces within a few coarse steps. */
+int ludwig_init_uniform_flow(ludwig_ctx* ctx, float ux);
 
 /* solver_control.jl:145-165  execute_timestep_batch!: `batch_size` coarse steps
  * t_start .. t_start+batch_size-1 with the whole recursive 2:1 sub-cycling
@@ -291,6 +298,7 @@ int ludwig_multi_level_upload(ludwig_multi* m, int32_t level, int32_t which, con
 int ludwig_multi_level_download(ludwig_multi* m, int32_t level, int32_t which, void* dst);         /* io_vtk.jl:55-57 */
 int ludwig_multi_init_equilibrium(ludwig_multi* m);                                                /* main.jl:109-135 */
 int ludwig_multi_step_batch(ludwig_multi* m, int64_t t_start, int32_t batch_size, float u_curr, const ludwig_params* params);  /* solver_control.jl:145-165 */
+int ludwig_multi_init_uniform_flow(ludwig_multi* m, float ux);
 int ludwig_multi_sync(ludwig_multi* m);
 int ludwig_multi_flow_stats(ludwig_multi* m, int32_t level, double out[6]);                        /* main.jl:186, reduced over the ranks */
 /* main.jl:101,145: mesh + ForceData on every rank; *out_handle identifies them in the two calls below. */
@@ -310,8 +318,10 @@ int64_t ludwig_multi_device_bytes(const ludwig_multi* m);
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a host framework can
  * record its own events on it or order other work against it.  NULL for a CPU backend. */
 void* ludwig_ctx_stream(ludwig_ctx* ctx);
-/* Number of kernels this library has launched on the context since creation. */
+/* Number of kernels this library has launched on the context since creation (kernels inside a replayed CUDA graph included). */
 int64_t ludwig_launch_count(const ludwig_ctx* ctx);
+/* Number of coarse steps executed by replaying a captured CUDA graph (option graphs). */
+int64_t ludwig_graph_replays(const ludwig_ctx* ctx);
 /* Per-kernel device timing of K1's dominant kernel: when enabled, every launch of the plain-interior K1 kernel
  * is bracketed by CUDA events on the context's stream.  ludwig_profile_read synchronises, returns the summed
  * duration [ms], the number of bracketed launches and the lattice cells they updated, and resets the counters. */

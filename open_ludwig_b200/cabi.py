@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_multi_level_download", "ludwig_multi_init_equilibrium", "ludwig_multi_step_batch", "ludwig_multi_sync",
     "ludwig_multi_flow_stats", "ludwig_multi_forces_create", "ludwig_multi_compute_aerodynamics",
     "ludwig_multi_forces_download_maps", "ludwig_multi_device_bytes",
+    "ludwig_graph_replays", "ludwig_init_uniform_flow", "ludwig_multi_init_uniform_flow",
     "ludwig_output_valid_blocks", "ludwig_output_export", "ludwig_multi_output_valid_blocks", "ludwig_multi_output_export",
 )
 
@@ -148,6 +149,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_multi_compute_aerodynamics": (C.c_int, [vp, i32, i32, C.POINTER(f64), f64, f64, i32, C.POINTER(f64)]),
         "ludwig_multi_forces_download_maps": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "ludwig_multi_device_bytes": (C.c_int64, [vp]),
+        "ludwig_graph_replays": (C.c_int64, [vp]),
+        "ludwig_init_uniform_flow": (C.c_int, [vp, f32]),
+        "ludwig_multi_init_uniform_flow": (C.c_int, [vp, f32]),
         "ludwig_output_valid_blocks": (C.c_int, [vp, vp, vp]),
         "ludwig_output_export": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "ludwig_multi_output_valid_blocks": (C.c_int, [vp, vp, vp]),
@@ -297,6 +301,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ludwig_launch_count(self._h))
+
+    def graph_replays(self) -> int:
+        return int(self.lib.ludwig_graph_replays(self._h))
+
+    def init_uniform_flow(self, ux: float):
+        self._check(self.lib.ludwig_init_uniform_flow(self._h, C.c_float(ux)), "ludwig_init_uniform_flow")
 
     def profile_enable(self, on: bool = True):
         self._check(self.lib.ludwig_profile_enable(self._h, int(on)), "ludwig_profile_enable")
@@ -607,6 +617,9 @@ class MultiContext:
 
     def init_equilibrium(self):
         self._check(self.lib.ludwig_multi_init_equilibrium(self._h), "ludwig_multi_init_equilibrium")
+
+    def init_uniform_flow(self, ux: float):
+        self._check(self.lib.ludwig_multi_init_uniform_flow(self._h, C.c_float(ux)), "ludwig_multi_init_uniform_flow")
 
     def step_batch(self, t_start: int, batch: int, u_curr: float, params: Params):
         self._check(self.lib.ludwig_multi_step_batch(self._h, t_start, batch, C.c_float(u_curr), C.byref(params)), "ludwig_multi_step_batch")

@@ -380,7 +380,12 @@ int ensure_bouzidi_links(ludwig_ctx* ctx, Level& L, float q_min) {
 // perform_timestep_v2! (physics_v2.jl:26-97): K1 then K2, in three phases so that the cross-rank barriers between them can be
 // placed by the caller (one context: rank_barrier; several contexts driven by one thread: an event barrier over the group).
 enum : int { PH_K1 = 1, PH_GATHER = 2, PH_FINISH = 4, PH_ALL = 7 };
-int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p, int phase) {
+// Set while a coarse step is being captured into a CUDA graph: the kernels then take the step counter and the inlet velocity from
+// device memory (DynScalars) instead of immediates, so that the captured graph can be replayed for any later coarse step of the
+// same buffer parity.
+struct GraphCtl { const DynScalars* dyn; int64_t t_coarse; };
+int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_sub, float tw, float u_curr, const ludwig_params& p, int phase,
+                     const GraphCtl* gc = nullptr) {
     const int in = (t_sub % 2 == 0) ? 0 : 1, out = 1 - in;   // solver_control.jl:35-41
     ctx->prof_level = L.level_id - 1;
     int rho_out = L.rho_cur;
@@ -413,10 +418,11 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
     a.tw = tw; a.is_symmetric = p.symmetric; a.wm = p.wall_model_active;
     a.seed = (int)(t_sub % 1000000);           // physics_v2.jl:76
     a.use_temporal = p.use_temporal; a.sponge_blend = p.sponge_blend;
+    if (gc) { a.dyn = gc->dyn; a.dyn_shift = L.level_id - 1; a.dyn_add = (int)(t_sub - (gc->t_coarse << (L.level_id - 1))); }
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.cta_threads = ctx->opt_cta_threads;
+    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -604,14 +610,15 @@ int group_barrier(Group& g) {
 }
 
 // One level step of every context of the group, phase by phase, with the cross-rank barriers in between.
-int group_step_level(Group& g, size_t lvl, const std::vector<ParentView>* pvs, int64_t t_sub, float tw, float u, const ludwig_params& p) {
+int group_step_level(Group& g, size_t lvl, const std::vector<ParentView>* pvs, int64_t t_sub, float tw, float u, const ludwig_params& p,
+                     const GraphCtl* gc = nullptr) {
     const bool mg = g.c[0]->world > 1;
     const bool bz = g.c[0]->levels[lvl]->bouzidi;
     auto run = [&](int phase) -> int {
         for (size_t r = 0; r < g.c.size(); ++r) {
             ludwig_ctx* ctx = g.c[r];
             if (g.c.size() > 1) CU(cudaSetDevice(ctx->device));
-            int rc = step_level_phase(ctx, *ctx->levels[lvl], pvs ? &(*pvs)[r] : nullptr, t_sub, tw, u, p, phase);
+            int rc = step_level_phase(ctx, *ctx->levels[lvl], pvs ? &(*pvs)[r] : nullptr, t_sub, tw, u, p, phase, gc);
             if (rc) { if (ctx != g.c[0]) g.c[0]->err = ctx->err; return rc; }
         }
         return LUDWIG_OK;
@@ -644,15 +651,97 @@ int prepare_tables(ludwig_ctx* ctx, const ludwig_params& p) {
 }
 
 // recursive_step! / recursive_step_temporal! (solver_control.jl:21-143)
-int recursive_step(Group& g, size_t lvl, int64_t t_sub, const std::vector<ParentView>* pvs, float tw, float u, const ludwig_params& p) {
+int recursive_step(Group& g, size_t lvl, int64_t t_sub, const std::vector<ParentView>* pvs, float tw, float u, const ludwig_params& p,
+                   const GraphCtl* gc = nullptr) {
     if (lvl >= g.c[0]->levels.size()) return LUDWIG_OK;
-    int rc = group_step_level(g, lvl, pvs, t_sub, tw, u, p);
+    int rc = group_step_level(g, lvl, pvs, t_sub, tw, u, p, gc);
     if (rc) return rc;
     if (lvl + 1 < g.c[0]->levels.size()) {
         std::vector<ParentView> me;
         for (ludwig_ctx* ctx : g.c) me.push_back(make_parent_view(*ctx->levels[lvl], t_sub, /*explicit_old=*/false));
-        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub, &me, 0.0f, u, p))) return rc;
-        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p))) return rc;
+        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub, &me, 0.0f, u, p, gc))) return rc;
+        if ((rc = recursive_step(g, lvl + 1, 2 * t_sub + 1, &me, 0.5f, u, p, gc))) return rc;
+    }
+    return LUDWIG_OK;
+}
+
+// ---- CUDA-graph replay of a coarse step (one context).  The reference synchronises the host after EVERY kernel
+// (physics_v2.jl:85,95, solver_control.jl:164); this library launches asynchronously, but a multi-level coarse step is still 7-63
+// level steps of up to seven small launches each plus the event fork / join traffic of the concurrent launch classes, and on small
+// levels the launch path, not the GPU, sets the pace.  All kernel arguments of a coarse step repeat with period 2 (A-B buffer
+// parity of level 1; finer levels take an even number of sub-steps) except the noise seed and the ramped inlet velocity, which the
+// kernels read from device memory during replay (DynScalars).  So: capture the whole recursion once per (parity, parameter set)
+// with stream capture — the side-stream forks become graph branches — and afterwards one tiny kernel (the two scalars) plus one
+// cudaGraphLaunch per coarse step.  Bit-identical to the eager path (tests/test_graph_replay_gpu.py).
+__global__ void set_dyn_kernel(DynScalars* d, long long t, float u) { d->t_coarse = t; d->u_inlet = u; }
+
+void drop_graphs(ludwig_ctx* ctx) {
+    for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+}
+
+bool graphs_enabled(ludwig_ctx* ctx, const ludwig_params& p) {
+    if (ctx->world != 1 || ctx->profiling || ctx->graph_failed) return false;
+    if ((p.strict_fp ? ctx->opt_strict_variant : ctx->opt_fast_variant) == 2) return false;   // persistent variants draw tickets: per-launch arguments
+    if (p.strict_fp && ctx->opt_strict_generic) return false;
+    if (ctx->opt_graphs == 0) return false;
+    if (ctx->opt_graphs == 1) return true;
+    return ctx->levels.size() >= 2;   // auto: multi-level cases (many small launches per coarse step); a single big level gains nothing
+}
+
+int graph_coarse_step(Group& g, int64_t t, float u_curr, const ludwig_params& p) {
+    ludwig_ctx* ctx = g.c[0];
+    if (!ctx->d_dyn) CU(cudaMalloc((void**)&ctx->d_dyn, sizeof(DynScalars)));
+    if (std::memcmp(&ctx->graph_params, &p, sizeof(p)) != 0) { drop_graphs(ctx); ctx->graph_params = p; }
+    // every lazily built table must exist before the capture starts (building them synchronises and allocates)
+    for (Level* L : ctx->levels) {
+        int rc = ensure_fast_tables(ctx, *L, p);
+        if (rc) return rc;
+        if (L->bouzidi && (rc = ensure_bouzidi_links(ctx, *L, p.q_min_threshold))) return rc;
+    }
+    uint64_t key = (uint64_t)(t & 1);
+    for (size_t l = 0; l < ctx->levels.size(); ++l) key |= (uint64_t)(ctx->levels[l]->rho_cur & 1) << (1 + l);
+    set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_dyn, (long long)t, u_curr);
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        const int64_t launches0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = LUDWIG_OK;
+        if (e == cudaSuccess) {
+            GraphCtl gc{ctx->d_dyn, t};
+            rc = recursive_step(g, 0, t, nullptr, 0.0f, u_curr, p, &gc);      // advances the host-side bookkeeping like a real step
+            e = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        ludwig_ctx::GraphEntry ent;
+        if (rc == LUDWIG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ent.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != LUDWIG_OK || e != cudaSuccess || !ent.exec) {
+            // capture is an optimisation: fall back to eager stepping for good.  The bookkeeping has advanced but nothing ran: undo it.
+            cudaGetLastError();
+            ctx->graph_failed = true;
+            for (size_t l = 0; l < ctx->levels.size(); ++l) {
+                Level& L = *ctx->levels[l];
+                if (L.d_rho[1] && ((1ll << l) & 1)) L.rho_cur ^= 1;
+                L.last_t_sub = (t << l) - 1;
+            }
+            ctx->launches = launches0;
+            if (rc != LUDWIG_OK) return rc;
+            return recursive_step(g, 0, t, nullptr, 0.0f, u_curr, p);
+        }
+        ent.launches = ctx->launches - launches0;
+        it = ctx->graphs.emplace(key, ent).first;
+        CU(cudaGraphLaunch(it->second.exec, ctx->stream));
+        ctx->launches += 1;
+        return LUDWIG_OK;
+    }
+    CU(cudaGraphLaunch(it->second.exec, ctx->stream));
+    ctx->launches += it->second.launches + 1;
+    ctx->graph_replays += 1;
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {     // the host-side bookkeeping of 2^l steps of level l
+        Level& L = *ctx->levels[l];
+        if (L.d_rho[1] && l == 0) L.rho_cur ^= 1;          // levels >= 2 take an even number of sub-steps: unchanged
+        L.last_t_sub = ((t + 1) << l) - 1;
     }
     return LUDWIG_OK;
 }
@@ -675,8 +764,12 @@ int group_step_batch(Group& g, int64_t t_start, int32_t batch_size, float u_curr
     // align the ranks first: a peer may still be uploading / initialising the state this rank is about to pull from
     int rc;
     if (g.c[0]->world > 1 && (rc = group_barrier(g))) return rc;
-    for (int t_offset = 0; t_offset < batch_size; ++t_offset)
-        if ((rc = recursive_step(g, 0, t_start + t_offset, nullptr, 0.0f, u_curr, p))) return rc;
+    for (int t_offset = 0; t_offset < batch_size; ++t_offset) {
+        const int64_t t = t_start + t_offset;
+        if (g.c.size() == 1 && graphs_enabled(g.c[0], p)) {
+            if ((rc = graph_coarse_step(g, t, u_curr, p))) return rc;
+        } else if ((rc = recursive_step(g, 0, t, nullptr, 0.0f, u_curr, p))) return rc;
+    }
     return LUDWIG_OK;
 }
 
@@ -772,6 +865,8 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ludwig_output_state_free(ctx);
+    drop_graphs(ctx);
+    if (ctx->d_dyn) cudaFree(ctx->d_dyn);
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (Level* L : ctx->levels) free_level(L);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
@@ -796,6 +891,7 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
     const std::string k(key), v(value);
     const bool on = v == "1" || v == "true" || v == "on";
     const bool before_levels = ctx->levels.empty();
+    drop_graphs(ctx);   // captured graphs bake the options in
     auto need_early = [&]() { return fail(ctx, LUDWIG_ESTATE, "option '" + k + "' must be set before the first ludwig_level_create"); };
     if (k == "prepass") {                       // "thread" (default) | "block": block-cooperative interface pre-pass
         if (v != "thread" && v != "block") return fail(ctx, LUDWIG_EINVAL, "prepass: thread | block");
@@ -808,14 +904,15 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         if (v == "reg") ctx->opt_strict_variant = 0; else if (v == "stash") ctx->opt_strict_variant = 1; else if (v == "tma") ctx->opt_strict_variant = 2;
         else return fail(ctx, LUDWIG_EINVAL, "strict_kernel: reg | stash | tma");
     } else if (k == "cta_threads") {            // threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
-        const int n = atoi(value);
-        if (n != 256 && n != 128 && n != 64) return fail(ctx, LUDWIG_EINVAL, "cta_threads: 256 | 128 | 64");
+        const int n = v == "auto" ? 0 : atoi(value);
+        if (n != 0 && n != 256 && n != 128 && n != 64) return fail(ctx, LUDWIG_EINVAL, "cta_threads: auto | 256 | 128 | 64");
         ctx->opt_cta_threads = n;
     } else if (k == "fast_kernel") {
         if (v == "direct") ctx->opt_fast_variant = 0; else if (v == "tma") ctx->opt_fast_variant = 2;
         else return fail(ctx, LUDWIG_EINVAL, "fast_kernel: direct | tma");
     }
     else if (k == "strict_generic") ctx->opt_strict_generic = on;        // strict mode through the one-thread-per-cell cross-check kernel
+    else if (k == "graphs") { ctx->opt_graphs = v == "auto" ? -1 : (on ? 1 : 0); }   // CUDA-graph replay of coarse steps: auto (multi-level cases) | 0 | 1
     else if (k == "verbose") ctx->verbose = on;
     else if (k == "barrier_timeout_s") { ctx->barrier_timeout_s = atof(value); if (!(ctx->barrier_timeout_s > 0)) return fail(ctx, LUDWIG_EINVAL, "barrier_timeout_s > 0"); }
     else if (k == "halo_mirror") { if (!before_levels) return need_early(); ctx->use_mirror = on; }   // packed halo exchange into local mirrors
@@ -837,6 +934,7 @@ int64_t ludwig_device_bytes(const ludwig_ctx* ctx) { return ctx ? ctx->bytes : 0
 
 void* ludwig_ctx_stream(ludwig_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t ludwig_launch_count(const ludwig_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t ludwig_graph_replays(const ludwig_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on) {
     if (!ctx) return LUDWIG_EINVAL;
     ctx->profiling = on != 0;
@@ -1287,6 +1385,21 @@ int ludwig_init_equilibrium(ludwig_ctx* ctx) {
             launch_fill(L.d_rho_old, 1.0f, (size_t)L.nb * BS3, ctx->stream);
             CU(cudaMemsetAsync(L.d_vel_old, 0, (size_t)L.nb * BS3 * 3 * 4, ctx->stream));
         }
+    }
+    CU(cudaGetLastError());
+    return LUDWIG_OK;
+}
+
+// K0 with a prescribed uniform state instead of rest: f = f_temp = feq(rho = 1, u = (ux, 0, 0)), vel = vel_temp = u (0 in obstacle
+// cells), rho = 1 on every level.  Not a reference call site (its init_eq! is the rest state): the initial condition of the
+// strong-scaling record of bench.py, where an impulsively started flow gives O(1) surface forces after a few coarse steps.
+int ludwig_init_uniform_flow(ludwig_ctx* ctx, float ux) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    for (Level* Lp : ctx->levels) {
+        Level& L = *Lp;
+        launch_init_uniform(L.d_f[0], L.d_f[1], L.d_vel[0], L.d_vel[1], L.d_rho[0], L.d_rho[1], L.d_obstacle, L.nb, ux, ctx->stream);
+        ctx->launches += 1;
     }
     CU(cudaGetLastError());
     return LUDWIG_OK;
@@ -1776,6 +1889,12 @@ int ludwig_multi_level_create(ludwig_multi* m, const ludwig_level_desc* desc, in
 int ludwig_multi_init_equilibrium(ludwig_multi* m) {
     if (!m) return LUDWIG_EINVAL;
     for (ludwig_ctx* c : m->ctx) { int rc = ludwig_init_equilibrium(c); if (rc) return mpass(m, c, rc); }
+    return LUDWIG_OK;
+}
+
+int ludwig_multi_init_uniform_flow(ludwig_multi* m, float ux) {
+    if (!m) return LUDWIG_EINVAL;
+    for (ludwig_ctx* c : m->ctx) { int rc = ludwig_init_uniform_flow(c, ux); if (rc) return mpass(m, c, rc); }
     return LUDWIG_OK;
 }
 

@@ -32,6 +32,12 @@ __device__ __forceinline__ float calc_eq(float rho, float ux, float uy, float uz
 __device__ __forceinline__ float pow32(float x, float y) { return (float)exp2(log2((double)x) * (double)y); }
 __device__ __forceinline__ float log32(float x) { return (float)log((double)x); }
 
+// inlet velocity and noise seed of this launch: immediates, or (CUDA-graph replay of a coarse step) derived from device memory
+__device__ __forceinline__ float k1_u_inlet(const K1Args& a) { return a.dyn ? a.dyn->u_inlet : a.u_inlet; }
+__device__ __forceinline__ int k1_seed(const K1Args& a) {
+    return a.dyn ? (int)(((a.dyn->t_coarse << a.dyn_shift) + (long long)a.dyn_add) % 1000000LL) : a.seed;
+}
+
 struct Corner { float v[5]; bool ok; };
 
 __device__ __forceinline__ Corner get_blended(const K1Args& a, int pgx, int pgy, int pgz, int k, float w_k) {
@@ -125,14 +131,15 @@ __device__ __noinline__ float pull_missing(const K1Args& a, const float* __restr
     bool is_inlet = src_gx < 1, is_outlet = src_gx > a.nxg;
     bool is_y_min = src_gy < 1, is_y_max = src_gy > a.nyg;
     bool is_z_min = src_gz < 1, is_z_max = src_gz > a.nzg;
+    const float u_inlet = k1_u_inlet(a);
     if (is_inlet) {
-        float noise = a.inlet_turb > 0.0f ? gradient_noise(gy, gz, a.seed, 1234) * a.inlet_turb * a.u_inlet : 0.0f;
-        float u_inst = a.u_inlet + noise;
+        float noise = a.inlet_turb > 0.0f ? gradient_noise(gy, gz, k1_seed(a), 1234) * a.inlet_turb * u_inlet : 0.0f;
+        float u_inst = u_inlet + noise;
         float cu_in = (float)cx * u_inst;
         return w_k * (1.0f + 3.0f * cu_in + 4.5f * cu_in * cu_in - 1.5f * u_inst * u_inst);
     } else if (is_outlet) {
-        float cu_out = (float)cx * a.u_inlet;
-        return w_k * (1.0f + 3.0f * cu_out + 4.5f * cu_out * cu_out - 1.5f * a.u_inlet * a.u_inlet);
+        float cu_out = (float)cx * u_inlet;
+        return w_k * (1.0f + 3.0f * cu_out + 4.5f * cu_out * cu_out - 1.5f * u_inlet * u_inlet);
     } else if (is_y_min || is_y_max) {   // (the symmetric flag makes no difference, physics_kernels.jl:115-118)
         return fin_cell[(k - 6 * cy) * BS3];
     } else if (is_z_min || is_z_max) {

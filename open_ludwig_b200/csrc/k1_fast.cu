@@ -265,11 +265,12 @@ __device__ __forceinline__ void fast_block(const K1Args& a, const int b, const i
         const v2 om = vsub(V(1.0f), sp);
         rho = vfma(rho, om, sp);
         drho = vmul(drho, om);                       // rho' - 1 = (rho - 1)(1 - sp)
-        ux = vfma(ux, om, vmul(V(a.u_inlet), sp));
+        const float u_in = k1_u_inlet(a);
+        ux = vfma(ux, om, vmul(V(u_in), sp));
         uy = vmul(uy, om);
         uz = vmul(uz, om);
         if (a.sponge_blend == 1) {
-            const float ui2 = a.u_inlet * a.u_inlet;
+            const float ui2 = u_in * u_in;
             // raw second moments of feq(1, u_inlet, 0, 0): delta/3 + u u  (cross terms vanish)
             // (shifted moments: the delta/3 parts cancel, only u_inlet^2 remains on xx)
             m.Pxx = vfma(m.Pxx, om, vmul(V(ui2), sp));

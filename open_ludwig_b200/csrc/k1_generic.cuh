@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 2) K1_KERNEL_NAME(const K1Args a) {
     if (bflags & BF_SPONGE) {
         float sp = a.sponge[cell];
         if (sp > 0.0f) {
-            const float rho_target = 1.0f, ux_target = a.u_inlet;
+            const float rho_target = 1.0f, ux_target = k1_u_inlet(a);
             rho = rho * (1.0f - sp) + rho_target * sp;
             ux = ux * (1.0f - sp) + ux_target * sp;
             uy = uy * (1.0f - sp);

@@ -254,12 +254,13 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         const v2 sp = ld2(a.sponge + (size_t)b * BS3 + c0);
         const v2 om = vsub(V(1.0f), sp);
         rho = vadd(VMUL(rho, om), VMUL(V(1.0f), sp));
-        ux = vadd(VMUL(ux, om), VMUL(V(a.u_inlet), sp));
+        const float u_in = k1_u_inlet(a);
+        ux = vadd(VMUL(ux, om), VMUL(V(u_in), sp));
         uy = VMUL(uy, om);
         uz = VMUL(uz, om);
         if (a.sponge_blend == 1) {
             Unroll<0, 27>::run([&]<int K>() {
-                const float feq_t = calc_eq(1.0f, a.u_inlet, 0.0f, 0.0f, lat_w(K), (float)lat_cx(K), (float)lat_cy(K), (float)lat_cz(K));
+                const float feq_t = calc_eq(1.0f, u_in, 0.0f, 0.0f, lat_w(K), (float)lat_cx(K), (float)lat_cy(K), (float)lat_cz(K));
                 f.set(K, vadd(VMUL(f.get(K), om), VMUL(V(feq_t), sp)));
             });
         }

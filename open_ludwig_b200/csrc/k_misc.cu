@@ -30,6 +30,31 @@ void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s) 
     init_eq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f0, f1, f_old, n);
 }
 
+// uniform-flow variant of K0 (ludwig_init_uniform_flow): equilibrium of (1, (ux, 0, 0)) in the reference's expression order
+__global__ void init_uniform_kernel(float* __restrict__ f0, float* __restrict__ f1, float* __restrict__ v0, float* __restrict__ v1,
+                                    float* __restrict__ r0, float* __restrict__ r1, const uint8_t* __restrict__ obstacle, size_t ncell, float ux) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const size_t b = c >> 9, loc = c & 511;
+    const float u = obstacle[c] ? 0.0f : ux;
+    for (int k = 0; k < Q; ++k) {
+        const int cx = k % 3 - 1, cy = (k / 3) % 3 - 1, cz = k / 9 - 1;
+        const int d2 = cx * cx + cy * cy + cz * cz;
+        const float w = d2 == 0 ? 8.0f / 27.0f : d2 == 1 ? 2.0f / 27.0f : d2 == 2 ? 1.0f / 54.0f : 1.0f / 216.0f;
+        const float cu = __fmul_rn((float)cx, u);
+        const float feq = __fmul_rn(w, __fsub_rn(__fadd_rn(__fadd_rn(1.0f, __fmul_rn(3.0f, cu)), __fmul_rn(__fmul_rn(4.5f, cu), cu)), __fmul_rn(1.5f, __fmul_rn(u, u))));
+        f0[(b * Q + k) * BS3 + loc] = feq; f1[(b * Q + k) * BS3 + loc] = feq;
+    }
+    v0[b * 3 * BS3 + loc] = u; v1[b * 3 * BS3 + loc] = u;
+    v0[(b * 3 + 1) * BS3 + loc] = 0.f; v1[(b * 3 + 1) * BS3 + loc] = 0.f; v0[(b * 3 + 2) * BS3 + loc] = 0.f; v1[(b * 3 + 2) * BS3 + loc] = 0.f;
+    r0[c] = 1.0f;
+    if (r1) r1[c] = 1.0f;
+}
+void launch_init_uniform(float* f0, float* f1, float* v0, float* v1, float* r0, float* r1, const uint8_t* obstacle, int nb, float ux, cudaStream_t s) {
+    const size_t n = (size_t)nb * BS3;
+    init_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f0, f1, v0, v1, r0, r1, obstacle, n, ux);
+}
+
 __global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,15 @@ struct PeerPtrs {
 struct PeerBytes {
     const uint8_t* p[MAX_RANKS];
 };
+
+// The two scalars of a K1 launch that change from one coarse step to the next (physics_v2.jl:76 seed = t_sub % 1000000, main.jl:173
+// the ramped inlet velocity), kept in device memory when a coarse step is replayed as a CUDA graph: every other kernel argument of
+// a coarse step repeats with period 2 (buffer parity).
+struct DynScalars {
+    long long t_coarse;
+    float u_inlet;
+};
+
 
 // physics_v2.jl:99-117: k = (dx+1) + 3(dy+1) + 9(dz+1), dx fastest.
 __host__ __device__ constexpr int lat_cx(int k) { return k % 3 - 1; }
@@ -195,7 +205,7 @@ struct ludwig_ctx {
     bool opt_strict_generic = false;         // "strict_generic"
     int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
-    int opt_cta_threads = 256;               // "cta_threads" = 256 | 128 | 64
+    int opt_cta_threads = 0;                 // "cta_threads" = auto (64 strict / 128 fast) | 256 | 128 | 64
     bool verbose = false;                    // "verbose"
     std::string remote_order = "morton";     // "remote_order"
     double barrier_timeout_s = 20.0;         // "barrier_timeout_s"
@@ -226,6 +236,14 @@ struct ludwig_ctx {
     bool bar_failed = false;                  // sticky: once a barrier failed every stepping / result call returns LUDWIG_ESTATE
     unsigned int bar_epoch = 0;
     int64_t launches = 0;
+    // CUDA-graph replay of coarse steps (abi.cu graph_coarse_step): one instantiated graph per buffer-parity pattern
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    std::map<uint64_t, GraphEntry> graphs;
+    ludwig::DynScalars* d_dyn = nullptr;
+    ludwig_params graph_params{};
+    int opt_graphs = -1;            // "graphs": -1 auto, 0 off, 1 on
+    bool graph_failed = false;
+    int64_t graph_replays = 0;
     void* output_state = nullptr;   // output.cu: cached valid-block lists + pinned double-buffered staging (N3)
     // K1 profiling (ludwig_profile_enable)
     bool profiling = false;
@@ -267,6 +285,8 @@ struct K1Args {
     // persistent (TMA) variants: blocks are handed out in list order through an atomic ticket counter, so that the CTAs in flight always
     // work on a compact window of the Morton curve (halo sectors stay L2 hits); the counter is never reset: block = ticket - ticket_base
     unsigned long long* ticket; unsigned long long ticket_base;
+    // graph replay: seed = ((dyn->t_coarse << dyn_shift) + dyn_add) % 1000000 and u_inlet = dyn->u_inlet replace the immediates above
+    const DynScalars* dyn; int dyn_shift, dyn_add;
     float negzero;          // -0.0f, opaque to ptxas: the strict build's packed multiply is FFMA2(a, b, negzero) (k1_strict.cu)
 };
 
@@ -307,6 +327,7 @@ void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s);
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);
 void launch_fill(float* p, float v, size_t n, cudaStream_t s);
+void launch_init_uniform(float* f0, float* f1, float* v0, float* v1, float* r0, float* r1, const uint8_t* obstacle, int nb, float ux, cudaStream_t s);
 void launch_bouzidi(const Level& L, float* f_out, const long long* roff_f_out, bool strict, int phase, cudaStream_t s);
 void launch_ref_to_int(const float* src_ref_k, float* dst, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);
 void launch_int_to_ref(const float* src, float* dst_ref_k, const int32_t* int2ref, int nb, int ncomp, int k, cudaStream_t s);

@@ -22,16 +22,26 @@ def init_context(lib_path=None, local_rank=None) -> cabi.Context:
     return ctx
 
 
+def _comm_device(device):
+    """Tensors of the plumbing collectives live on the GPU for NCCL and on the host for gloo (several ranks sharing one GPU:
+    NCCL refuses duplicate devices)."""
+    return device if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
 def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = None):
     """Exchange the IPC handles of every rank's state.  Call after the last ctx.add_level().
 
     barrier = "native" (default): the library's own peer-flag barrier kernel (flag stores over NVLink, stream-ordered,
-    no host call per barrier).  barrier = "nccl": a stream-ordered NCCL all-reduce of one float registered through
-    ludwig_set_barrier_callback (the round-1 path, kept for A/B measurements)."""
+    no host call per barrier).  "nccl": a stream-ordered NCCL all-reduce of one float registered through
+    ludwig_set_barrier_callback (the round-1 path, kept for A/B measurements).  "host": a blocking host barrier (stream
+    synchronise + dist.barrier()) — slow, but the only safe choice when several ranks share ONE GPU (a spinning barrier
+    kernel would wait for a peer whose kernels cannot run beside it); used to test the one-process-per-GPU path on a
+    one-GPU box."""
     barrier = barrier or "native"
     world = dist.get_world_size()
     mine = ctx.ipc_export()
-    t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+    cd = _comm_device(device)
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=cd)
     allt = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(allt, t)
     blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allt)
@@ -39,6 +49,12 @@ def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = 
     dist.barrier()          # every rank has opened every peer mapping before anyone steps
     if barrier == "native":
         return None
+    if barrier == "host":
+        def host_barrier():
+            torch.cuda.synchronize(device)
+            dist.barrier()
+        ctx.set_barrier(host_barrier)
+        return host_barrier
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
     flag = torch.zeros(1, device=device)
 
@@ -55,6 +71,7 @@ def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = 
 
 def reduce_stats(stats: dict, device: torch.device) -> dict:
     """Combine per-rank ludwig_flow_stats results (diagnostics.jl:56-94 over the whole level)."""
+    device = _comm_device(device)
     s = torch.tensor([stats["n_fluid"], stats["rho_mean"] * stats["n_fluid"], stats["kinetic_energy"]], dtype=torch.float64, device=device)
     mn = torch.tensor([stats["rho_min"]], dtype=torch.float64, device=device)
     mx = torch.tensor([stats["rho_max"], stats["v_max"]], dtype=torch.float64, device=device)
@@ -74,7 +91,7 @@ def reduce_stats(stats: dict, device: torch.device) -> dict:
 def reduce_aero(aero: dict, device: torch.device) -> dict:
     """Every output of ludwig_compute_aerodynamics is linear in the per-rank partial sums."""
     keys = list(aero)
-    t = torch.tensor([aero[k] for k in keys], dtype=torch.float64, device=device)
+    t = torch.tensor([aero[k] for k in keys], dtype=torch.float64, device=_comm_device(device))
     dist.all_reduce(t)
     return dict(zip(keys, t.tolist()))
 
@@ -114,11 +131,15 @@ def load_domain_shared(name: str, log=None):
 
 
 def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = False, options: dict | None = None, plan: bool = False,
-                    ramp_steps: int | None = None, profile_steps: int = 0, log=None, dom=None, all_ranks_levels: bool = False) -> dict:
+                    ramp_steps: int | None = None, profile_steps: int = 0, log=None, dom=None, all_ranks_levels: bool = False,
+                    uniform_start: bool = False) -> dict:
     """One strong-scaling measurement of a named case (open_ludwig_b200.host.cases) over the ranks of the current process
     group (or a single GPU when torch.distributed is not initialised): every rank creates its partitioned context from the
     shared domain (load_domain_shared), attaches the peers and steps `steps` coarse steps along the driver's cosine ramp
     (main.jl:168-176, one batch per step).  Device time = max over ranks of CUDA events on the library's stream.
+    uniform_start: instead of the rest state and the ramp, the whole domain starts as a uniform flow at the target inlet velocity
+    (ludwig_init_uniform_flow) — an impulsive start, so that the body carries O(1) forces after a few coarse steps and the
+    Cd / Cl printed for 1 and N GPUs compare a developed force, not round-off around zero.
     Returns the record (identical on every rank)."""
     import time
     from .solver import make_params, ramp_velocity
@@ -144,11 +165,14 @@ def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = Fa
         mesh = ctx.create_mesh(m.centers, m.normals, m.areas)
         p = dom.params
         forces = ctx.create_forces(mesh, p.rho_physical, p.u_physical, p.reference_area, p.reference_chord, p.moment_center, dom.cfg.symmetric)
-        ctx.init_equilibrium()
+        if uniform_start:
+            ctx.init_uniform_flow(float(dom.cfg.u_target))
+        else:
+            ctx.init_equilibrium()
         params = make_params(dom, strict=strict)
         ctx.sync()
         upload_s = time.time() - t0
-        ramp = ramp_steps or dom.cfg.ramp_steps
+        ramp = 1 if uniform_start else (ramp_steps or dom.cfg.ramp_steps)
         stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
         t = 1
         for _ in range(2):                                     # warm-up (builds the lazily built tables)
@@ -197,7 +221,7 @@ def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = Fa
         ctx.close()
     upd = dom.cell_updates_per_coarse_step
     return {"case": name, "n_gpus": world, "cells": dom.total_cells, "levels": len(dom.levels), "cell_updates_per_coarse_step": upd,
-            "coarse_steps": steps, "steps_run": t - 1, "ramp_steps": ramp, "ms_per_coarse_step": ms, "mlups_true": upd / (ms * 1e-3) / 1e6,
+            "coarse_steps": steps, "steps_run": t - 1, "ramp_steps": ramp, "initial_state": "uniform flow at u_target (impulsive start)" if uniform_start else "rest + cosine ramp", "ms_per_coarse_step": ms, "mlups_true": upd / (ms * 1e-3) / 1e6,
             "mlups_reference_style": dom.total_cells / (ms * 1e-3) / 1e6, "fp_mode": "strict" if strict else "fast",
             "Cd": aero["Cd"], "Cl": aero["Cl"], "rho_min": stats["rho_min"], "rho_max": stats["rho_max"], "v_max": stats["v_max"],
             "partition": (options or {}).get("partition", "plan" if plan else "morton"), "options": options or {},

@@ -908,6 +908,25 @@ int ludwig_flow_stats(ludwig_ctx* ctx, int32_t level, double out[6]) {
 }
 
 int64_t ludwig_device_bytes(const ludwig_ctx*) { return 0; }
+// bench / test initial condition (no reference counterpart): uniform flow (1, (ux, 0, 0)), see include/ludwig_b200.h
+int ludwig_init_uniform_flow(ludwig_ctx* ctx, float ux) {
+    if (!ctx) return LUDWIG_EINVAL;
+    for (auto& Lp : ctx->levels) {
+        Level& L = *Lp;
+        const size_t s = 512 * (size_t)L.nb;
+        for (size_t c = 0; c < s; ++c) {
+            const float u = L.obstacle[c] ? 0.0f : ux;
+            for (int k = 0; k < 27; ++k) {
+                const float v = calculate_equilibrium(1.0f, u, 0.0f, 0.0f, LAT.w[k], (float)LAT.cx[k], (float)LAT.cy[k], (float)LAT.cz[k]);
+                L.f[c + s * k] = v; L.f_temp[c + s * k] = v;
+            }
+            L.vel[c] = u; L.vel_temp[c] = u; L.vel[c + s] = 0; L.vel_temp[c + s] = 0; L.vel[c + 2 * s] = 0; L.vel_temp[c + 2 * s] = 0;
+            L.rho[c] = 1.0f;
+            if (!L.rho_old.empty()) L.rho_old[c] = 1.0f;
+        }
+    }
+    return LUDWIG_OK;
+}
 // multi-GPU entry points: the oracle is single-process; it only shares the (host-side) partition rule
 int ludwig_partition_starts(int32_t n_blocks, int32_t world, int32_t* starts) {
     if (n_blocks < 0 || world < 1 || world > 8) return LUDWIG_EINVAL;
@@ -942,6 +961,8 @@ int ludwig_ipc_export(ludwig_ctx*, void*, int64_t, int64_t* needed) { if (needed
 int ludwig_ipc_attach(ludwig_ctx* ctx, const void*, int64_t) { return fail(ctx, LUDWIG_ESTATE, "the CPU oracle is single-rank"); }
 void* ludwig_ctx_stream(ludwig_ctx*) { return nullptr; }
 int64_t ludwig_launch_count(const ludwig_ctx*) { return 0; }
+int64_t ludwig_graph_replays(const ludwig_ctx*) { return 0; }
+int ludwig_multi_init_uniform_flow(ludwig_multi*, float) { return LUDWIG_ESTATE; }
 int ludwig_profile_enable(ludwig_ctx*, int32_t) { return LUDWIG_OK; }
 int ludwig_profile_classes(ludwig_ctx*, double out[8]) { for (int i = 0; i < 8; ++i) out[i] = 0; return LUDWIG_OK; }
 int ludwig_profile_levels(ludwig_ctx*, double* out, int32_t capacity) { for (int i = 0; i < capacity; ++i) out[i] = 0; return LUDWIG_OK; }

@@ -188,11 +188,11 @@ def test_fast_tma_kernel_variant_is_bit_identical(cuda_lib):
 
 
 @pytest.mark.parametrize("strict", [0, 1])
-@pytest.mark.parametrize("threads", [128, 64])
+@pytest.mark.parametrize("threads", [256, 128, 64])
 def test_cta_threads_option_is_bit_identical(cuda_lib, strict, threads):
     """cta_threads = 128 / 64: a CTA takes 4 / 2 z-planes of a block instead of all 8 — same per-cell code, same bits."""
     levels = build_case()
-    a, *_ = run(cuda_lib, levels, 10, strict, True)
+    a, *_ = run(cuda_lib, levels, 10, strict, True)                                   # auto: 64 strict / 128 fast
     b, *_ = run(cuda_lib, levels, 10, strict, True, options={"cta_threads": threads})
     for lvl in a:
         for name in a[lvl]:

@@ -29,6 +29,7 @@ ap.add_argument("case"); ap.add_argument("steps", type=int)
 ap.add_argument("--fp-mode", default="fast", choices=["fast", "strict"])
 ap.add_argument("--ramp", type=int, default=None, help="ramp length override (coarse steps)")
 ap.add_argument("--profile", type=int, default=0, help="coarse steps of the per-level profiling pass")
+ap.add_argument("--uniform-start", action="store_true", help="start from a uniform flow at u_target instead of rest + ramp (O(1) forces at once)")
 ap.add_argument("--variant", action="append", default=[])
 ap.add_argument("--json", default=None, help="write the records here (rank 0)")
 args = ap.parse_args()
@@ -44,7 +45,7 @@ for v in (args.variant or [""]):
     plan = "plan" in items
     opts = dict(x.split("=", 1) for x in items if x != "plan")
     rec = mg.run_case_strong(args.case, args.steps, lr, strict=args.fp_mode == "strict", options=opts, plan=plan, ramp_steps=args.ramp,
-                             profile_steps=args.profile, log=log, dom=dom, all_ranks_levels=args.profile > 0)
+                             profile_steps=args.profile, log=log, dom=dom, all_ranks_levels=args.profile > 0, uniform_start=args.uniform_start)
     rec["variant"] = v or "default"; rec["domain_build_s"] = build_s
     records.append(rec)
     if rank == 0:
