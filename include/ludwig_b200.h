@@ -110,7 +110,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   serial_prepass = 0 | 1            pre-pass on the main stream instead of beside the plain K1 launch
  *   single_stream = 0 | 1             no concurrent launches at all
  *   fork_full = 0 | 1                 domain-face K1 launch beside the plain launch on large levels
- *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default 40000)
+ *   fork_max_blocks = N               levels up to N blocks run their K1 launch classes concurrently (default: every level)
  *   strict_kernel = reg | stash | tma strict K1 variant: pulled populations in registers (2 CTAs / SM), in a shared-memory stash
  *                                     (3 CTAs / SM), or persistent CTAs with cp.async.bulk (TMA) staged, double-buffered block tiles
  *   cta_threads = auto | 256 | 128 | 64   threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
@@ -312,6 +312,25 @@ int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p,
 int ludwig_multi_output_valid_blocks(ludwig_multi* m, int32_t* n_valid, int32_t* blocks);                               /* io_vtk.jl:17-46 */
 int ludwig_multi_output_export(ludwig_multi* m, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr);   /* io_vtk.jl:52-111 */
 int64_t ludwig_multi_device_bytes(const ludwig_multi* m);
+
+/* -- domain build on the device (N2: the step BEFORE the hot path; the kept Julia driver's setup code calls these instead of its
+ * threaded CPU loops).  Host pointers in and out, Float64 geometry in the reference's operation order: the tables are bit-identical
+ * to the CPU build.  coords = Int32[nb][3] active block coordinates (1-based, the order of active_block_coords); grid_ptr =
+ * Int32[dimx][dimy][dimz] (C order) block index of every block coordinate, 1-based, 0 = none; tris = Float64[n_tri][3][3] in STL
+ * coordinates, offset = mesh_offset.  Errors: negative LUDWIG_E* return, message from ludwig_domain_last_error(). ------------------- */
+const char* ludwig_domain_last_error(void);
+/* domain_generation.jl:34-112  build_block_triangle_map + voxelize_blocks!: sets obstacle[b][z][y][x] = 1 for the shell cells */
+int ludwig_domain_voxelize(int device, const double* tris, int64_t n_tri, const double offset[3], double dx, const int32_t* coords, int32_t nb,
+                           const int32_t* grid_ptr, int32_t dimx, int32_t dimy, int32_t dimz, uint8_t* obstacle /* in/out [nb][512] */);
+/* domain_generation.jl:371-431  compute_wall_distances!: neighbor_table as in ludwig_level_desc; returns the number of near-wall cells */
+int64_t ludwig_domain_wall_distance(int device, const int32_t* neighbor_table, int32_t nb, const uint8_t* obstacle, double dx,
+                                    float* wall_dist /* in/out [nb][512], 100 = far */);
+/* bouzidi_setup.jl:12-54,64-166 + bouzidi_math.jl:9-102  compute_q_map!: sparse result, one row per boundary cell in the order
+ * (block, z, y, x): out_cells Int32[n][4] = 1-based (block, x, y, z), out_q Float64[n][27], out_tri Int32[n][27] (1-based triangle of
+ * every link, 0 = none).  Returns n; call with NULL outputs (or a too small capacity) to get n first. */
+int64_t ludwig_domain_qmap(int device, const double* tris, int64_t n_tri, const double offset[3], double dx, const int32_t* coords, int32_t nb,
+                           const int32_t* grid_ptr, int32_t dimx, int32_t dimy, int32_t dimz, int64_t capacity, int32_t* out_cells, double* out_q,
+                           int32_t* out_tri);
 
 /* -- instrumentation (no reference counterpart: the reference only has wall-clock prints, main.jl:37-42,189) -- */
 

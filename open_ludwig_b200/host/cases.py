@@ -28,6 +28,8 @@ CASE_OVERRIDES = {
     "wing5_small": ("Wing_5_deg", {"basic": {"surface_resolution": 150, "num_levels": 3, "simulation": {"steps": 300, "ramp_steps": 400}},
                                    "advanced": {"diagnostics": {"freq": 100}}}),
     "bunny": ("Stanford_bunny", None),
+    # config 5's case file at a size the CPU oracle can afford (3 levels, 2.5 M cells, 25 825 Bouzidi cells, wall model, inlet turbulence)
+    "bunny_small": ("Stanford_bunny", {"basic": {"surface_resolution": 80, "num_levels": 3}}),
     # config 5: the bunny scaled to fine resolution: 6 levels, 339 M cells, 9.4 G cell-updates per coarse step
     "bunny_fine": ("Stanford_bunny", {"basic": {"surface_resolution": 1300, "num_levels": 6}}),
 }

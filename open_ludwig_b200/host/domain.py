@@ -139,9 +139,20 @@ def build_neighbor_table(coords: np.ndarray, dims) -> tuple:
 # ---- domain.jl ----------------------------------------------------------------------------------------
 
 def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, verbose: bool = False,
-                            build_tri_map: bool = True) -> Domain:
-    """domain.jl:20-280."""
+                            build_tri_map: bool = True, gpu_device: Optional[int] = None) -> Domain:
+    """domain.jl:20-280.  gpu_device: run the three brute-force phases (voxelisation, wall distance, q-map ray casting) on that
+    CUDA device through libludwig_b200.so's ludwig_domain_* entry points (N2) instead of the host threads; the tables are
+    byte-identical either way (tests/test_domain_gpu.py)."""
     lib = host_lib()
+    glib = None
+    if gpu_device is not None:
+        from .. import cabi
+        glib = cabi.load_library()
+
+    def gcheck(rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what} failed ({rc}): {glib.ludwig_domain_last_error().decode()}")
+        return rc
     if mesh is None:
         stl = os.path.join(cfg.case_dir, cfg.stl_file)
         if not os.path.isfile(stl):
@@ -202,24 +213,38 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
         sponge = np.zeros((nb, 8, 8, 8), np.float32)
         wall_dist = np.full((nb, 8, 8, 8), 100.0, np.float32)
         cflat = np.ascontiguousarray(coords)
-        lib.ludwig_host_voxelize(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), _p(obstacle))
+        grid_ptr = np.ascontiguousarray(full_ptr, np.int32)       # [bx][by][bz], 1-based block index, 0 = none
+        if glib is not None:
+            gcheck(glib.ludwig_domain_voxelize(gpu_device, _p(tris), n_tri, _p(off), dx, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1], dims[2],
+                                               _p(obstacle)), "ludwig_domain_voxelize")
+        else:
+            lib.ludwig_host_voxelize(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), _p(obstacle))
         shell = int(obstacle.sum())
         filled = int(lib.ludwig_host_flood_fill(_p(obstacle), _p(cflat), nb, _p(full_ptr_cm), dims[0], dims[1], dims[2]))
         lib.ludwig_host_sponge(_p(cflat), nb, dx, params.domain_size[0], params.domain_size[1], params.domain_size[2],
                                float(cfg.sponge_thickness), int(cfg.symmetric), _p(sponge))
         near = 0
         if cfg.wall_model_enabled:
-            near = int(lib.ludwig_host_wall_distance(_p(cflat), nb, _p(obstacle), dx, _p(wall_dist)))
+            if glib is not None:
+                nt_c = np.ascontiguousarray(nt, np.int32)
+                near = int(gcheck(glib.ludwig_domain_wall_distance(gpu_device, _p(nt_c), nb, _p(obstacle), dx, _p(wall_dist)), "ludwig_domain_wall_distance"))
+            else:
+                near = int(lib.ludwig_host_wall_distance(_p(cflat), nb, _p(obstacle), dx, _p(wall_dist)))
 
         use_bouzidi = cfg.boundary_method == "bouzidi" and lvl > (num_levels - cfg.bouzidi_levels)   # bouzidi_common.jl:28-34
         q_map = tri_map = cell_block = cell_x = cell_y = cell_z = None
         n_bc = links = 0
         if use_bouzidi:
-            n_bc = int(lib.ludwig_host_qmap(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), 0, None, None, None))
+            def qmap(cap, c_, q_, t_):
+                if glib is not None:
+                    return int(gcheck(glib.ludwig_domain_qmap(gpu_device, _p(tris), n_tri, _p(off), dx, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1],
+                                                              dims[2], cap, c_, q_, t_), "ludwig_domain_qmap"))
+                return int(lib.ludwig_host_qmap(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), cap, c_, q_, t_))
+            n_bc = qmap(0, None, None, None)
             cells = np.zeros((max(n_bc, 1), 4), np.int32)
             qv = np.zeros((max(n_bc, 1), 27), np.float64)
             tv = np.zeros((max(n_bc, 1), 27), np.int32)
-            got = int(lib.ludwig_host_qmap(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), n_bc, _p(cells), _p(qv), _p(tv)))
+            got = qmap(n_bc, _p(cells), _p(qv), _p(tv))
             assert got == n_bc
             cells, qv, tv = cells[:n_bc], qv[:n_bc], tv[:n_bc]
             q_map = np.zeros((27, nb, 8, 8, 8), np.float16)
@@ -251,9 +276,11 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
     return Domain(cfg, params, mesh, levels, reports)
 
 
-def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False, build_tri_map: bool = True) -> Domain:
+def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False, build_tri_map: bool = True,
+              gpu_device: Optional[int] = None) -> Domain:
     """load_case_configuration + setup_multilevel_domain (main.jl:259-260, :90)."""
-    return setup_multilevel_domain(load_case_configuration(case_dir, overrides), verbose=verbose, build_tri_map=build_tri_map)
+    return setup_multilevel_domain(load_case_configuration(case_dir, overrides), verbose=verbose, build_tri_map=build_tri_map,
+                                   gpu_device=gpu_device)
 
 
 # ---- domain cache (multi-rank launches: one rank builds, the others map the arrays) -------------------

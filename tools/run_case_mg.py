@@ -5,7 +5,7 @@
         [--variant "partition=rcb_yz"] [--variant "plan"] [--variant "partition=rcb,fork_max_blocks=100000"] ...
 
 The domain is built ONCE (rank 0, every host thread; the other ranks map it from /dev/shm) and every --variant — a comma-
-separated list of library options (ludwig_ctx_set_option) and/or the word "plan" (spatially aligned partition plan) — is
+separated list of library options (ludwig_ctx_set_option), "fp=fast|strict" and/or the word "plan" (spatially aligned partition plan) — is
 measured on the same processes, one after the other: contexts are re-created, the domain is not.  Prints one RESULT line per
 variant (true MLUPS from the max over ranks of CUDA-event device time) and, with --profile, every rank's per-level,
 per-kernel-class device times.
@@ -44,7 +44,8 @@ for v in (args.variant or [""]):
     items = [x for x in v.split(",") if x]
     plan = "plan" in items
     opts = dict(x.split("=", 1) for x in items if x != "plan")
-    rec = mg.run_case_strong(args.case, args.steps, lr, strict=args.fp_mode == "strict", options=opts, plan=plan, ramp_steps=args.ramp,
+    fp = opts.pop("fp", args.fp_mode)                      # "fp=fast" / "fp=strict" inside a variant overrides --fp-mode
+    rec = mg.run_case_strong(args.case, args.steps, lr, strict=fp == "strict", options=opts, plan=plan, ramp_steps=args.ramp,
                              profile_steps=args.profile, log=log, dom=dom, all_ranks_levels=args.profile > 0, uniform_start=args.uniform_start)
     rec["variant"] = v or "default"; rec["domain_build_s"] = build_s
     records.append(rec)
