@@ -33,14 +33,15 @@ import numpy as np  # noqa: E402
 
 BYTES_PER_LU = 216  # 27 x 4 B read + 27 x 4 B write
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per lattice update, from ncu captures under profiles/
-TRAFFIC_BYTES_PER_LU = {"fast": (2090983680 + 1903583488) / (30720 * 512), "strict": None}
-TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum per LU (profiles/r1c_dram_traffic_k1_256cube.csv) x LU per launch",
-                  "strict": None}
-DEFAULT_FP_MODE = "fast"
-DEFAULT_STRONG_PARTITION = "plan"
+# (captured at the benched size, 512^3: 253 952 plain blocks per launch)
+TRAFFIC_BYTES_PER_LU = {"fast": (17274605312 + 16087857920) / (253952 * 512), "strict": (17255133696 + 16074985984) / (253952 * 512)}
+TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<plain> at 512^3 (profiles/r2a_dram_traffic_k1_512cube_fast.csv) per LU x LU per launch",
+                  "strict": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_strict_kernel<plain> at 512^3 (profiles/r2a_dram_traffic_k1_512cube_strict.csv) per LU x LU per launch"}
+DEFAULT_FP_MODE = "strict"          # the mode whose results are bit-identical to the reference restatement; fast is reported beside it
+DEFAULT_STRONG_PARTITION = "rcb_yz"
 # 1-GPU time per coarse step of the strong-scaling case measured by this file's own strong record (profiles/), for the
 # efficiency shown at N > 1: (case, fp_mode) -> ms
-T1_MS_COMMITTED = {("bunny_fine", "fast"): 496.8}
+T1_MS_COMMITTED = {("bunny_fine", "fast"): 495.6, ("bunny_fine", "strict"): 588.0}   # profiles/r2e_bunny_fine_1gpu_*.log
 
 
 def measured_peaks():

@@ -119,6 +119,29 @@ __device__ __noinline__ float interpolate_with_rescaling(const K1Args& a, int fi
     return feq_int + f_neq * scale;
 }
 
+// The two x-face cases of pull_missing (below) in closed form, once per thread instead of once per pulled population: every
+// population a cell at global x = 1 pulls from x = 0 has c_x = +1 and is the inlet equilibrium w_k * P_in with the same
+// P_in = 1 + 3 u + 4.5 u u - 1.5 u u, u = u_inlet + noise(gy, gz, seed) (physics_kernels.jl:99-107: the noise is a function of the
+// PULLING cell's gy, gz); every population a cell at x = nx pulls from x = nx + 1 has c_x = -1 and is w_k * P_out with cu = -u_inlet
+// (:108-113).  Same expressions in the same order as pull_missing, so the products w_k * P are the same bits.
+struct XFace { float p_in, p_out; };
+__device__ __forceinline__ XFace x_face_equilibria(const K1Args& a, int gy, int gz) {
+    const float u_inlet = k1_u_inlet(a);
+    const float noise = a.inlet_turb > 0.0f ? gradient_noise(gy, gz, k1_seed(a), 1234) * a.inlet_turb * u_inlet : 0.0f;
+    const float u_inst = u_inlet + noise;
+    const float cu_in = 1.0f * u_inst, cu_out = -1.0f * u_inlet;
+    XFace f;
+    f.p_in = 1.0f + 3.0f * cu_in + 4.5f * cu_in * cu_in - 1.5f * u_inst * u_inst;
+    f.p_out = 1.0f + 3.0f * cu_out + 4.5f * cu_out * cu_out - 1.5f * u_inlet * u_inlet;
+    return f;
+}
+__host__ __device__ constexpr float lat_w_of(int k) {
+    return ((k % 3 != 1) + ((k / 3) % 3 != 1) + (k / 9 != 1)) == 0   ? 8.0f / 27.0f
+           : ((k % 3 != 1) + ((k / 3) % 3 != 1) + (k / 9 != 1)) == 1 ? 2.0f / 27.0f
+           : ((k % 3 != 1) + ((k / 3) % 3 != 1) + (k / 9 != 1)) == 2 ? 1.0f / 54.0f
+                                                                     : 1.0f / 216.0f;
+}
+
 // Everything that can happen to a population whose source cell is in a block that does not exist
 // (physics_kernels.jl:88-140).  Kept out of line: it is the rare path.
 __device__ __noinline__ float pull_missing(const K1Args& a, const float* __restrict__ fin_cell, int k, int gx, int gy, int gz) {

@@ -132,6 +132,11 @@ __device__ __forceinline__ void fast_block(const K1Args& a, const int b, const i
         bflags = (uint32_t)bc.w;
         if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
+    // domain x faces in closed form (cell A on the inlet plane / cell B on the outlet plane; an inlet source wins over y / z faces
+    // and over the outlet test exactly as in pull_missing: physics_kernels.jl:99-113)
+    const bool at_inlet = MISS && gx == 1, at_outlet = MISS && gx + 1 == a.nxg && a.nxg > 1;
+    XFace xf{0.f, 0.f};
+    if (MISS && (at_inlet || at_outlet)) xf = x_face_equilibria(a, gy, gz);
     const float* __restrict__ fin_own = fbase + s_fo[13] + c0;   // own cell A, direction 0
 
     // source-row bookkeeping per axis: index j = c + 1 for lattice component c in {-1,0,1}; source = coord - c
@@ -170,8 +175,8 @@ __device__ __forceinline__ void fast_block(const K1Args& a, const int b, const i
                 fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
                 fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
             }
-            fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
-            fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+            fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : at_inlet ? lat_w_of(kp) * xf.p_in : pull_missing(a, fin_own, kp, gx, gy, gz);
+            fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : at_outlet ? lat_w_of(km) * xf.p_out : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
         }
     };
 

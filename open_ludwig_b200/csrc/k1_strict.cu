@@ -140,6 +140,11 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         bflags = (uint32_t)bc.w;
         if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
+    // domain x faces in closed form (cell A on the inlet plane / cell B on the outlet plane; an inlet source wins over y / z faces
+    // and over the outlet test exactly as in pull_missing: physics_kernels.jl:99-113)
+    const bool at_inlet = MISS && gx == 1, at_outlet = MISS && gx + 1 == a.nxg && a.nxg > 1;
+    XFace xf{0.f, 0.f};
+    if (MISS && (at_inlet || at_outlet)) xf = x_face_equilibria(a, gy, gz);
     const float* __restrict__ fin_own = fbase + s_fo[13] + c0;
 
     int yoff[3], ydir[3], zoff[3], zdir[3];
@@ -151,6 +156,61 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
     }
     const int dM = p > 0 ? 1 : 0, xM = p > 0 ? x0 - 1 : 7;
     const int dP = p < 3 ? 1 : 2, xP = p < 3 ? x0 + 2 : 0;
+
+    // The relaxation rate depends only on the PREVIOUS step's velocities of the six axis neighbours, not on the populations: it is
+    // computed first, so that the 18 neighbour velocities (36 registers) are dead before the 27 pulled populations (54 registers)
+    // become live.
+    // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
+    v2 uE[3], uW[3], uN[3], uS[3], uT[3], uB[3];
+    {
+        const int row = z * 64 + y * 8;
+        const float* __restrict__ vo = a.vel_in + s_vo[13] + c0;
+        const long long oM = s_vo[12 + dM], oP = s_vo[13 + (dP - 1)];
+        const long long oN = s_vo[y < 7 ? 13 : 16], oS = s_vo[y > 0 ? 13 : 10], oT = s_vo[z < 7 ? 13 : 22], oB = s_vo[z > 0 ? 13 : 4];
+        const int lN = z * 64 + ((y + 1) & 7) * 8 + x0, lS = z * 64 + ((y - 1) & 7) * 8 + x0;
+        const int lT = ((z + 1) & 7) * 64 + y * 8 + x0, lB = ((z - 1) & 7) * 64 + y * 8 + x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const v2 own = ld2(vo + c * BS3);
+            uW[c] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + c * BS3] : own.x, own.x);
+            uE[c] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + c * BS3] : own.y);
+            uN[c] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + c * BS3) : own;
+            uS[c] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + c * BS3) : own;
+            uT[c] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + c * BS3) : own;
+            uB[c] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + c * BS3) : own;
+        }
+    }
+
+    // ---- WALE (:251-300) in the reference's expression order
+    v2 omega;
+    {
+        const v2 h = V(0.5f);
+        const v2 g11 = VMUL(h, vsub(uE[0], uW[0])), g12 = VMUL(h, vsub(uN[0], uS[0])), g13 = VMUL(h, vsub(uT[0], uB[0]));
+        const v2 g21 = VMUL(h, vsub(uE[1], uW[1])), g22 = VMUL(h, vsub(uN[1], uS[1])), g23 = VMUL(h, vsub(uT[1], uB[1]));
+        const v2 g31 = VMUL(h, vsub(uE[2], uW[2])), g32 = VMUL(h, vsub(uN[2], uS[2])), g33 = VMUL(h, vsub(uT[2], uB[2]));
+#define DOT3(a1, b1, a2, b2, a3, b3) vadd(vadd(VMUL(a1, b1), VMUL(a2, b2)), VMUL(a3, b3))
+        const v2 gsq11 = DOT3(g11, g11, g12, g21, g13, g31), gsq12 = DOT3(g11, g12, g12, g22, g13, g32), gsq13 = DOT3(g11, g13, g12, g23, g13, g33);
+        const v2 gsq21 = DOT3(g21, g11, g22, g21, g23, g31), gsq22 = DOT3(g21, g12, g22, g22, g23, g32), gsq23 = DOT3(g21, g13, g22, g23, g23, g33);
+        const v2 gsq31 = DOT3(g31, g11, g32, g21, g33, g31), gsq32 = DOT3(g31, g12, g32, g22, g33, g32), gsq33 = DOT3(g31, g13, g32, g23, g33, g33);
+        const v2 tr_gsq = vadd(vadd(gsq11, gsq22), gsq33);
+        const v2 tr_term = vdiv(tr_gsq, V(3.0f));
+        const v2 Sd11 = vsub(gsq11, tr_term), Sd22 = vsub(gsq22, tr_term), Sd33 = vsub(gsq33, tr_term);
+        const v2 Sd12 = VMUL(h, vadd(gsq12, gsq21)), Sd13 = VMUL(h, vadd(gsq13, gsq31)), Sd23 = VMUL(h, vadd(gsq23, gsq32));
+        const v2 S12 = VMUL(h, vadd(g12, g21)), S13 = VMUL(h, vadd(g13, g31)), S23 = VMUL(h, vadd(g23, g32));
+        const v2 OP1 = vadd(DOT3(Sd11, Sd11, Sd22, Sd22, Sd33, Sd33), VMUL(V(2.0f), DOT3(Sd12, Sd12, Sd13, Sd13, Sd23, Sd23)));
+        const v2 OP2 = vadd(DOT3(g11, g11, g22, g22, g33, g33), VMUL(V(2.0f), DOT3(S12, S12, S13, S13, S23, S23)));
+#undef DOT3
+        const v2 OP1_32 = VMUL(OP1, vsqrt(OP1));
+        const v2 OP2_52 = VMUL(VMUL(OP2, OP2), vsqrt(vmaxs(OP2, 1.0e-12f)));
+        const v2 denom = vadd(OP2_52, VMUL(OP1, vsqrt(vsqrt(vmaxs(OP1, 1.0e-12f)))));
+        const float cw2 = __fmul_rn(a.c_wale, a.c_wale);
+        float ne0 = 0.0f, ne1 = 0.0f;
+        if (OP1.x > 1.0e-12f && denom.x > 1.0e-12f) ne0 = __fdiv_rn(__fmul_rn(cw2, OP1_32.x), denom.x);
+        if (OP1.y > 1.0e-12f && denom.y > 1.0e-12f) ne1 = __fdiv_rn(__fmul_rn(cw2, OP1_32.y), denom.y);
+        const v2 nu_eddy = vmaxs(make_float2(ne0, ne1), a.nu_bg);
+        const v2 tau_turb = vadd(V(a.tau), VMUL(nu_eddy, V(3.0f)));
+        omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
+    }
 
     // ---- pull-stream (:62-149) with the moment sums of :144-148 taken in k order as the values arrive; combo (jy,jz) yields the
     // three consecutive directions k0-1, k0, k0+1 and the combos are visited in ascending k0
@@ -181,8 +241,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
                     fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
                     fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
                 }
-                fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : pull_missing(a, fin_own, kp, gx, gy, gz);
-                fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+                fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : at_inlet ? lat_w_of(kp) * xf.p_in : pull_missing(a, fin_own, kp, gx, gy, gz);
+                fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : at_outlet ? lat_w_of(km) * xf.p_out : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
             }
             f.set(km, fm); f.set(k0, f0); f.set(kp, fp);
             // rho += f_k; j += f_k c_k  (k = km: cx = -1, k0: cx = 0, kp: cx = +1; cy = jyc - 1, cz = jzc - 1)
@@ -221,27 +281,6 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
 #pragma unroll
         for (int k = 0; k < 27; ++k) {
             if (obsA) fout[(26 - k) * BS3] = f.get(k).x; else fout[(26 - k) * BS3 + 1] = f.get(k).y;
-        }
-    }
-
-    // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
-    v2 uE[3], uW[3], uN[3], uS[3], uT[3], uB[3];
-    {
-        const int row = z * 64 + y * 8;
-        const float* __restrict__ vo = a.vel_in + s_vo[13] + c0;
-        const long long oM = s_vo[12 + dM], oP = s_vo[13 + (dP - 1)];
-        const long long oN = s_vo[y < 7 ? 13 : 16], oS = s_vo[y > 0 ? 13 : 10], oT = s_vo[z < 7 ? 13 : 22], oB = s_vo[z > 0 ? 13 : 4];
-        const int lN = z * 64 + ((y + 1) & 7) * 8 + x0, lS = z * 64 + ((y - 1) & 7) * 8 + x0;
-        const int lT = ((z + 1) & 7) * 64 + y * 8 + x0, lB = ((z - 1) & 7) * 64 + y * 8 + x0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const v2 own = ld2(vo + c * BS3);
-            uW[c] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + c * BS3] : own.x, own.x);
-            uE[c] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + c * BS3] : own.y);
-            uN[c] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + c * BS3) : own;
-            uS[c] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + c * BS3) : own;
-            uT[c] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + c * BS3) : own;
-            uB[c] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + c * BS3) : own;
         }
     }
 
@@ -290,37 +329,6 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         else { vout[1] = 0.f; vout[BS3 + 1] = 0.f; vout[2 * BS3 + 1] = 0.f; rout[1] = 1.f; vout[0] = ux.x; vout[BS3] = uy.x; vout[2 * BS3] = uz.x; rout[0] = rho.x; }
     } else {
         st2(vout, ux); st2(vout + BS3, uy); st2(vout + 2 * BS3, uz); st2(rout, rho);
-    }
-
-    // ---- WALE (:251-300) in the reference's expression order
-    v2 omega;
-    {
-        const v2 h = V(0.5f);
-        const v2 g11 = VMUL(h, vsub(uE[0], uW[0])), g12 = VMUL(h, vsub(uN[0], uS[0])), g13 = VMUL(h, vsub(uT[0], uB[0]));
-        const v2 g21 = VMUL(h, vsub(uE[1], uW[1])), g22 = VMUL(h, vsub(uN[1], uS[1])), g23 = VMUL(h, vsub(uT[1], uB[1]));
-        const v2 g31 = VMUL(h, vsub(uE[2], uW[2])), g32 = VMUL(h, vsub(uN[2], uS[2])), g33 = VMUL(h, vsub(uT[2], uB[2]));
-#define DOT3(a1, b1, a2, b2, a3, b3) vadd(vadd(VMUL(a1, b1), VMUL(a2, b2)), VMUL(a3, b3))
-        const v2 gsq11 = DOT3(g11, g11, g12, g21, g13, g31), gsq12 = DOT3(g11, g12, g12, g22, g13, g32), gsq13 = DOT3(g11, g13, g12, g23, g13, g33);
-        const v2 gsq21 = DOT3(g21, g11, g22, g21, g23, g31), gsq22 = DOT3(g21, g12, g22, g22, g23, g32), gsq23 = DOT3(g21, g13, g22, g23, g23, g33);
-        const v2 gsq31 = DOT3(g31, g11, g32, g21, g33, g31), gsq32 = DOT3(g31, g12, g32, g22, g33, g32), gsq33 = DOT3(g31, g13, g32, g23, g33, g33);
-        const v2 tr_gsq = vadd(vadd(gsq11, gsq22), gsq33);
-        const v2 tr_term = vdiv(tr_gsq, V(3.0f));
-        const v2 Sd11 = vsub(gsq11, tr_term), Sd22 = vsub(gsq22, tr_term), Sd33 = vsub(gsq33, tr_term);
-        const v2 Sd12 = VMUL(h, vadd(gsq12, gsq21)), Sd13 = VMUL(h, vadd(gsq13, gsq31)), Sd23 = VMUL(h, vadd(gsq23, gsq32));
-        const v2 S12 = VMUL(h, vadd(g12, g21)), S13 = VMUL(h, vadd(g13, g31)), S23 = VMUL(h, vadd(g23, g32));
-        const v2 OP1 = vadd(DOT3(Sd11, Sd11, Sd22, Sd22, Sd33, Sd33), VMUL(V(2.0f), DOT3(Sd12, Sd12, Sd13, Sd13, Sd23, Sd23)));
-        const v2 OP2 = vadd(DOT3(g11, g11, g22, g22, g33, g33), VMUL(V(2.0f), DOT3(S12, S12, S13, S13, S23, S23)));
-#undef DOT3
-        const v2 OP1_32 = VMUL(OP1, vsqrt(OP1));
-        const v2 OP2_52 = VMUL(VMUL(OP2, OP2), vsqrt(vmaxs(OP2, 1.0e-12f)));
-        const v2 denom = vadd(OP2_52, VMUL(OP1, vsqrt(vsqrt(vmaxs(OP1, 1.0e-12f)))));
-        const float cw2 = __fmul_rn(a.c_wale, a.c_wale);
-        float ne0 = 0.0f, ne1 = 0.0f;
-        if (OP1.x > 1.0e-12f && denom.x > 1.0e-12f) ne0 = __fdiv_rn(__fmul_rn(cw2, OP1_32.x), denom.x);
-        if (OP1.y > 1.0e-12f && denom.y > 1.0e-12f) ne1 = __fdiv_rn(__fmul_rn(cw2, OP1_32.y), denom.y);
-        const v2 nu_eddy = vmaxs(make_float2(ne0, ne1), a.nu_bg);
-        const v2 tau_turb = vadd(V(a.tau), VMUL(nu_eddy, V(3.0f)));
-        omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
     }
 
     // ---- Pi loop (:308-322): the stored f_k is replaced by feq_k
@@ -388,8 +396,10 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
 
 // NT threads per CTA: 256 = one CTA per block; 128 / 64 = a CTA takes 4 / 2 of the block's z-planes, so that more, smaller CTAs are
 // resident per SM and their load and compute phases interleave (the register-limited occupancy is the same number of warps).
-template <bool FULL, bool VELFB, bool MISS, bool STASH, int NT>
-__global__ void __launch_bounds__(NT, (STASH ? 3 : 2) * (256 / NT)) k1_strict_kernel(const __grid_constant__ K1Args a) {
+// OCC: resident warps per SM in units of four (16 / 20 / 24 warps -> 128 / 96 / 80 registers per thread).  With the relaxation rate
+// computed before the pull (see strict_block) 96 registers cost 32 bytes of spills and 80 registers 112 bytes.
+template <bool FULL, bool VELFB, bool MISS, bool STASH, int NT, int OCC = 4>
+__global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT) k1_strict_kernel(const __grid_constant__ K1Args a) {
     extern __shared__ float2 s_stash[];
     __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
     __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
@@ -472,8 +482,14 @@ void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
         (void)once; (void)once2;
         k1s::k1_strict_kernel<FULL, VELFB, MISS, true, 256><<<a.n_list, 256, STASH_BYTES, s>>>(a);
     } else if (a.cta_threads == 128) k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 128><<<2 * a.n_list, 128, 0, s>>>(a);
-    else if (a.cta_threads == 64) k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64><<<4 * a.n_list, 64, 0, s>>>(a);
-    else k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 256><<<a.n_list, 256, 0, s>>>(a);
+    else if (a.cta_threads == 64) {
+        // (the feature / domain-face instantiations would spill ~0.5-1 KB per thread at 96 / 80 registers: plain classes only)
+        if constexpr (!FULL) {
+            if (a.strict_occ == 6) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 6><<<4 * a.n_list, 64, 0, s>>>(a); return; }
+            if (a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5><<<4 * a.n_list, 64, 0, s>>>(a); return; }
+        }
+        k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 4><<<4 * a.n_list, 64, 0, s>>>(a);
+    } else k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 256><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1s_plain(const K1Args& a, cudaStream_t s) { launch_strict<false, false, false>(a, a.strict_stash, s); }
 void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) { launch_strict<false, true, false>(a, a.strict_stash, s); }

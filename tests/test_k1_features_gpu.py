@@ -197,3 +197,13 @@ def test_cta_threads_option_is_bit_identical(cuda_lib, strict, threads):
     for lvl in a:
         for name in a[lvl]:
             assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (threads, lvl, name)
+
+
+@pytest.mark.parametrize("occ", [4, 6])
+def test_strict_occupancy_option_is_bit_identical(cuda_lib, occ):
+    levels = build_case()
+    a, *_ = run(cuda_lib, levels, 10, 1, True)
+    b, *_ = run(cuda_lib, levels, 10, 1, True, options={"strict_occupancy": occ})
+    for lvl in a:
+        for name in a[lvl]:
+            assert np.array_equal(a[lvl][name].view(np.int32), b[lvl][name].view(np.int32)), (occ, lvl, name)
