@@ -422,7 +422,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.strict_occ = ctx->opt_strict_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
+    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.strict_occ = ctx->opt_strict_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -850,6 +850,14 @@ int ludwig_ctx_create(ludwig_ctx** out, int device) {
     if (cudaMalloc((void**)&ctx->d_ticket, 4 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(ctx->d_ticket, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return LUDWIG_ENOMEM;
+    }
+    {   // the wall model's constant factor, with the device's own Float64 log2 / exp2 (what the strict kernels would compute per cell)
+        launch_wall_model_constant((float*)ctx->d_ticket, ctx->stream);
+        if (cudaMemcpyAsync(&ctx->wm_c166, ctx->d_ticket, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaMemset(ctx->d_ticket, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+            delete ctx;
+            return LUDWIG_ECUDA;
+        }
     }
     if (cudaMalloc((void**)&ctx->d_stats, 4096 * 6 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_stats, 4096 * 6 * sizeof(double)) != cudaSuccess) {

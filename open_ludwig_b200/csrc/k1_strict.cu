@@ -72,13 +72,14 @@ struct Unroll<KEND, KEND> {
 };
 
 // Wall-model force of one cell in the reference's operation order (physics_kernels.jl:206-236); scalar, near-wall cells only.
-__device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, float uy, float uz, float tau) {
+// c166 = (2 * 8.3)^(-1/7), evaluated ONCE per context by wall_model_constant_kernel with the same pow32 (a third of this function's cost).
+__device__ __noinline__ float3 wall_force(float dist_wall, float rho, float ux, float uy, float uz, float tau, float c166) {
     float3 F = make_float3(0.f, 0.f, 0.f);
     if (dist_wall > 0.0f && dist_wall < 10.0f) {
         float u_mag = sqrtf(ux * ux + uy * uy + uz * uz);
         float nu_visc = (tau - 0.5f) / 3.0f;
         if (u_mag > 1.0e-6f && nu_visc > 1.0e-10f) {
-            float u_tau = u_mag * pow32(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * pow32(2.0f * 8.3f, -1.0f / 7.0f);
+            float u_tau = u_mag * pow32(nu_visc / (dist_wall * u_mag + 1.0e-10f), 1.0f / 7.0f) * c166;
             u_tau = fmaxf(u_tau, 1.0e-6f);
             float y_p = u_tau * dist_wall / nu_visc;
             if (y_p > 11.81f) {
@@ -310,8 +311,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
     bool has_force = false;
     if (FULL && a.wm == 1 && (bflags & BF_WALLDIST)) {
         const v2 dw = ld2(a.wall_dist + (size_t)b * BS3 + c0);
-        if (dw.x > 0.0f && dw.x < 10.0f && !obsA) { float3 F = wall_force(dw.x, rho.x, ux.x, uy.x, uz.x, a.tau); Fx.x = F.x; Fy.x = F.y; Fz.x = F.z; }
-        if (dw.y > 0.0f && dw.y < 10.0f && !obsB) { float3 F = wall_force(dw.y, rho.y, ux.y, uy.y, uz.y, a.tau); Fx.y = F.x; Fy.y = F.y; Fz.y = F.z; }
+        if (dw.x > 0.0f && dw.x < 10.0f && !obsA) { float3 F = wall_force(dw.x, rho.x, ux.x, uy.x, uz.x, a.tau, a.wm_c166); Fx.x = F.x; Fy.x = F.y; Fz.x = F.z; }
+        if (dw.y > 0.0f && dw.y < 10.0f && !obsB) { float3 F = wall_force(dw.y, rho.y, ux.y, uy.y, uz.y, a.tau, a.wm_c166); Fx.y = F.x; Fy.y = F.y; Fz.y = F.z; }
         has_force = true;
     }
     // u_eq = u + 0.5 F inv_rho with the PRE-sponge 1/rho (:238); without a force it is u (+0 changes no value)
@@ -495,6 +496,9 @@ void launch_k1s_plain(const K1Args& a, cudaStream_t s) { launch_strict<false, fa
 void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) { launch_strict<false, true, false>(a, a.strict_stash, s); }
 void launch_k1s_feat(const K1Args& a, cudaStream_t s) { launch_strict<true, true, false>(a, a.strict_stash, s); }
 void launch_k1s_full(const K1Args& a, cudaStream_t s) { launch_strict<true, true, true>(a, a.strict_stash, s); }
+__global__ void wall_model_constant_kernel(float* out) { *out = k1s::pow32(2.0f * 8.3f, -1.0f / 7.0f); }
+void launch_wall_model_constant(float* d_out, cudaStream_t s) { wall_model_constant_kernel<<<1, 1, 0, s>>>(d_out); }
+
 void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s) {
     if (g.n > 0) k1s::ghost_interp_kernel<<<(g.n + 127) / 128, 128, 0, s>>>(g);
 }

@@ -238,6 +238,7 @@ struct ludwig_ctx {
     bool bar_failed = false;                  // sticky: once a barrier failed every stepping / result call returns LUDWIG_ESTATE
     unsigned int bar_epoch = 0;
     int64_t launches = 0;
+    float wm_c166 = 0.f;            // see K1Args.wm_c166
     // CUDA-graph replay of coarse steps (abi.cu graph_coarse_step): one instantiated graph per buffer-parity pattern
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
     std::map<uint64_t, GraphEntry> graphs;
@@ -290,6 +291,7 @@ struct K1Args {
     unsigned long long* ticket; unsigned long long ticket_base;
     // graph replay: seed = ((dyn->t_coarse << dyn_shift) + dyn_add) % 1000000 and u_inlet = dyn->u_inlet replace the immediates above
     const DynScalars* dyn; int dyn_shift, dyn_add;
+    float wm_c166;          // (2 * 8.3)^(-1/7) of the wall model, evaluated once per context on the device (k1_strict.cu)
     float negzero;          // -0.0f, opaque to ptxas: the strict build's packed multiply is FFMA2(a, b, negzero) (k1_strict.cu)
 };
 
@@ -326,6 +328,7 @@ void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s);
 void launch_k1s_feat(const K1Args& a, cudaStream_t s);
 void launch_k1s_full(const K1Args& a, cudaStream_t s);
 void launch_ghost_interp_strict(const GhostArgs& g, cudaStream_t s);
+void launch_wall_model_constant(float* d_out, cudaStream_t s);
 
 // k_misc.cu
 void launch_init_eq(float* f0, float* f1, float* f_old, int nb, cudaStream_t s);

@@ -137,6 +137,49 @@ end
 
 sync(ctx::Context) = check(ctx, ccall((:ludwig_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h), "ludwig_sync")
 
+# every behaviour switch of the library is an explicit option (it reads no environment variable); see include/ludwig_b200.h
+set_option!(ctx::Context, key::AbstractString, value) =
+    check(ctx, ccall((:ludwig_ctx_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring), ctx.h, key, string(value)), "ludwig_ctx_set_option($key)")
+
+# io_vtk.jl:17-46  valid_blocks: per level the 1-based b_idx of the blocks that are not fully covered by the next finer level
+function output_valid_blocks(ctx::Context, n_levels::Integer)
+    n = zeros(Int32, n_levels)
+    check(ctx, ccall((:ludwig_output_valid_blocks, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), ctx.h, n, C_NULL), "ludwig_output_valid_blocks")
+    flat = Vector{Int32}(undef, sum(n))
+    check(ctx, ccall((:ludwig_output_valid_blocks, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), ctx.h, n, flat), "ludwig_output_valid_blocks")
+    return n, flat
+end
+
+# io_vtk.jl:52-58 + 100-111 in ONE call: rho_arr, vel_mat (3 x N), obst_arr, level_arr of every valid block in the writer's own order
+# (level-major, b_idx ascending).  Only those blocks leave the device, through pinned double-buffered staging.
+function output_export!(ctx::Context, t_step::Integer, rho_arr::Vector{Float32}, vel_mat::Matrix{Float32}, obst_arr::Vector{UInt8}, level_arr::Vector{Int32})
+    GC.@preserve rho_arr vel_mat obst_arr level_arr check(ctx, ccall((:ludwig_output_export, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Ptr{Int32}),
+        ctx.h, t_step, pointer(rho_arr), pointer(vel_mat), pointer(obst_arr), pointer(level_arr)), "ludwig_output_export")
+end
+
+# ---- domain build on the device (N2): drop-in for the threaded CPU loops of domain_generation.jl / bouzidi_setup.jl ------------------
+# tris: 3 x 3 x n_tri Float64 (vertex component fastest), coords: 3 x nb Int32 (active_block_coords), grid_ptr: the level's FULL
+# block-pointer grid as Int32[bz, by, bx]-major memory = permutedims(block_pointer_full, (3, 2, 1)), 1-based, 0 = none
+function domain_check(rc, what)
+    rc >= 0 && return rc
+    error("$what failed ($rc): " * unsafe_string(ccall((:ludwig_domain_last_error, LIB), Cstring, ())))
+end
+# domain_generation.jl:74-112  voxelize_blocks!
+voxelize!(device, tris, offset, dx, coords, grid_ptr, dims, obstacle::Array{UInt8,4}) =
+    domain_check(ccall((:ludwig_domain_voxelize, LIB), Cint, (Cint, Ptr{Float64}, Int64, Ptr{Float64}, Float64, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{UInt8}),
+                       device, tris, size(tris, 3), Float64[offset...], dx, coords, size(coords, 2), grid_ptr, dims[1], dims[2], dims[3], obstacle), "ludwig_domain_voxelize")
+# domain_generation.jl:371-431  compute_wall_distances!  (returns the number of near-wall cells)
+wall_distance!(device, neighbor_table::Matrix{Int32}, obstacle::Array{UInt8,4}, dx, wall_dist::Array{Float32,4}) =
+    domain_check(ccall((:ludwig_domain_wall_distance, LIB), Int64, (Cint, Ptr{Int32}, Int32, Ptr{UInt8}, Float64, Ptr{Float32}),
+                       device, neighbor_table, size(neighbor_table, 1), obstacle, dx, wall_dist), "ludwig_domain_wall_distance")
+# bouzidi_setup.jl:64-166  compute_q_map!: sparse rows (cells 4 x n, q 27 x n Float64, tri 27 x n); call once with capacity 0 for n
+qmap!(device, tris, offset, dx, coords, grid_ptr, dims, capacity, cells, q, tri) =
+    domain_check(ccall((:ludwig_domain_qmap, LIB), Int64,
+                       (Cint, Ptr{Float64}, Int64, Ptr{Float64}, Float64, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Int32, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}),
+                       device, tris, size(tris, 3), Float64[offset...], dx, coords, size(coords, 2), grid_ptr, dims[1], dims[2], dims[3], capacity,
+                       cells === nothing ? C_NULL : cells, q === nothing ? C_NULL : q, tri === nothing ? C_NULL : tri), "ludwig_domain_qmap")
+
 # io_vtk.jl:52-58,100-111 for one level: fills the slices of rho_arr / vel_mat / obst_arr that belong to the level's valid blocks
 # (b_idx list of io_vtk.jl:27-45, in the order they appear in valid_blocks) without downloading whole arrays.
 function output_gather!(ctx::Context, level::Integer, t_step::Integer, b_idx::Vector{Int32},
@@ -161,5 +204,41 @@ function attach_peers!(ctx::Context, allgather::Function)
     all = allgather(buf)
     GC.@preserve all check(ctx, ccall((:ludwig_ipc_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, pointer(all), need[]), "ludwig_ipc_attach")
 end
+
+# ---- more than one GPU, ONE process (the kept single-process driver, main.jl:54-249, unchanged in structure) ------------------------
+# Multi(n) owns one context per GPU; the same sequence of calls as for one GPU: add_level!, init_equilibrium!, step_batch!, flow_stats,
+# compute_aerodynamics!.  The library partitions every level, attaches the ranks in-process and steps them in lock-step from this
+# thread; cross-rank barriers are stream-ordered event waits.
+mutable struct Multi
+    h::Ptr{Cvoid}
+end
+function mcheck(m::Multi, rc::Cint, what)
+    rc == 0 && return
+    error("$what failed ($rc): " * unsafe_string(ccall((:ludwig_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m.h)))
+end
+function Multi(n_ranks::Integer, devices::Vector{Int32}=Int32.(0:n_ranks-1))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:ludwig_multi_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Int32, Ptr{Int32}), h, n_ranks, devices)
+    rc == 0 || error("ludwig_multi_create failed ($rc)")
+    m = Multi(h[])
+    finalizer(x -> ccall((:ludwig_multi_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), m)
+    return m
+end
+set_option!(m::Multi, key::AbstractString, value) =
+    mcheck(m, ccall((:ludwig_multi_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring), m.h, key, string(value)), "ludwig_multi_set_option($key)")
+# add_level!(m, g): build the LevelDesc exactly as add_level!(ctx, g) does and pass it to ludwig_multi_level_create
+level_create!(m::Multi, d::LevelDesc) = (idx = Ref{Int32}(-1);
+    mcheck(m, ccall((:ludwig_multi_level_create, LIB), Cint, (Ptr{Cvoid}, Ref{LevelDesc}, Ref{Int32}), m.h, d, idx), "ludwig_multi_level_create"); idx[])
+init_equilibrium!(m::Multi) = mcheck(m, ccall((:ludwig_multi_init_equilibrium, LIB), Cint, (Ptr{Cvoid},), m.h), "ludwig_multi_init_equilibrium")
+step_batch!(m::Multi, t_start::Integer, batch::Integer, u_curr::Float32, p::Params) =
+    mcheck(m, ccall((:ludwig_multi_step_batch, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Float32, Ref{Params}), m.h, t_start, batch, u_curr, p), "ludwig_multi_step_batch")
+sync(m::Multi) = mcheck(m, ccall((:ludwig_multi_sync, LIB), Cint, (Ptr{Cvoid},), m.h), "ludwig_multi_sync")
+function flow_stats(m::Multi, level::Integer=0)
+    out = zeros(Float64, 6)
+    mcheck(m, ccall((:ludwig_multi_flow_stats, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), m.h, level, out), "ludwig_multi_flow_stats")
+    return (n_fluid=Int(out[1]), rho_mean=out[2], rho_min=out[3], rho_max=out[4], v_max=out[5], kinetic_energy=out[6])
+end
+# ludwig_multi_forces_create / ludwig_multi_compute_aerodynamics / ludwig_multi_output_export follow the single-context signatures
+# with the handle index instead of the mesh / forces pointers (include/ludwig_b200.h).
 
 end # module
