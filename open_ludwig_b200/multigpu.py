@@ -96,6 +96,20 @@ def reduce_aero(aero: dict, device: torch.device) -> dict:
     return dict(zip(keys, t.tolist()))
 
 
+def use_all_host_threads() -> int:
+    """Size the OpenMP team of the host-side domain builder at run time: torchrun exports OMP_NUM_THREADS=1 to its workers and
+    libgomp reads that when it is loaded, so a rank that builds the domain would otherwise do it on one core."""
+    import ctypes
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return 1
+
+
 def load_domain_shared(name: str, log=None):
     """The domain of a named case on every rank of the process group: rank 0 builds it with every host thread and the
     other ranks map the arrays from a private /dev/shm directory (mkdtemp, 0700, name broadcast by rank 0: nobody else can
@@ -109,6 +123,10 @@ def load_domain_shared(name: str, log=None):
     rank, world = (dist.get_rank(), dist.get_world_size()) if mg else (0, 1)
     case, ov = CASE_OVERRIDES[name]
     t0 = time.time()
+    if rank == 0:
+        from .host import domain as _d
+        _d.host_lib()                 # load the builder (and its OpenMP runtime) ...
+        use_all_host_threads()        # ... then give it every core this process may use
     if world > 1:
         box = [tempfile.mkdtemp(prefix="ludwig_domain_", dir="/dev/shm") if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)

@@ -1,0 +1,58 @@
+"""BASELINE configs 4 and 5 AS SHIPPED (CASES/Wing_5_deg: 5 levels, 77.3 M cells, symmetric half model, WMLES; CASES/Stanford_bunny:
+5 levels, 79.5 M cells) against field-level fixtures the CPU oracle produced offline (tools/make_golden_fields.py →
+tests/golden/<case>_fields_cpu_oracle.json: one coarse step is 1.0-1.1 G cell updates, minutes on the CPU).
+
+STRICT: SHA-256 of rho / vel / vel_temp of every level must equal the oracle's — identity at full size, not a tolerance.
+FAST: sums and extrema within round-off, Cd / Cl / Cmy within north_star's 0.1 %.
+"""
+import json
+import os
+import sys
+
+import pytest
+
+from open_ludwig_b200.host.cases import have_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+CASES = {"bunny": "Stanford_bunny", "wing5": "Wing_5_deg"}
+
+
+def fixture(name):
+    p = os.path.join(ROOT, "tests", "golden", f"{name}_fields_cpu_oracle.json")
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not generated")
+    if not have_case(CASES[name]):
+        pytest.skip("reference case files not available")
+    with open(p) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["bunny", "wing5"])
+def test_shipped_case_strict_fields_identical_to_oracle(cuda_lib, name):
+    import make_golden_fields as G
+    fx = fixture(name)
+    got = G.run(name, fx["steps"], cuda_lib, strict=True)
+    assert got["blocks"] == fx["blocks"] and got["cells"] == fx["cells"]
+    for l, (a, b) in enumerate(zip(fx["levels"], got["levels"])):
+        for k in ("rho_sha256", "vel_sha256", "vel_temp_sha256"):
+            assert a[k] == b[k], (name, l, k, a["rho_sum"], b["rho_sum"], a["vel_abs_sum"], b["vel_abs_sum"])
+    assert abs(fx["aero"]["Cd"]) > 1.0                                          # a developed force, not round-off around zero
+    for k in ("Cd", "Cl", "Cmy"):                                                # K3 maps identical; K4: FP64 tree vs the reference's FP32 sequential sum
+        assert got["aero"][k] == pytest.approx(fx["aero"][k], rel=3e-4, abs=1e-6), k
+    for k in ("n_fluid", "rho_min", "rho_max", "v_max"):
+        assert got["stats"][k] == fx["stats"][k], k
+
+
+@pytest.mark.parametrize("name", ["bunny", "wing5"])
+def test_shipped_case_fast_within_round_off(cuda_lib, name):
+    import make_golden_fields as G
+    fx = fixture(name)
+    got = G.run(name, fx["steps"], cuda_lib, strict=False)
+    for l, (a, b) in enumerate(zip(fx["levels"], got["levels"])):
+        assert b["rho_sum"] == pytest.approx(a["rho_sum"], rel=1e-7), (name, l)
+        assert b["vel_abs_sum"] == pytest.approx(a["vel_abs_sum"], rel=1e-5), (name, l)
+        assert abs(b["rho_min"] - a["rho_min"]) <= 5e-6 and abs(b["rho_max"] - a["rho_max"]) <= 5e-6 and abs(b["vel_max"] - a["vel_max"]) <= 2e-6, (name, l)
+    for k in ("Cd", "Cl", "Cmy"):
+        assert got["aero"][k] == pytest.approx(fx["aero"][k], rel=1e-3, abs=1e-6), k     # north_star: 0.1 %
