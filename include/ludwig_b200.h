@@ -116,6 +116,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   cta_threads = auto | 256 | 128 | 64   threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
  *                                     (auto: 64 in strict mode, 128 in fast mode - the measured optimum)
  *   strict_occupancy = 4 | 5 | 6       strict K1 register budget: 16 / 20 / 24 resident warps per SM (128 / 96 / 80 registers per thread)
+ *   prefetch_distance = N             K1 CTAs prefetch the lines of the block N list entries ahead into L2 (0 = off)
  *   fast_kernel = direct | tma        fast K1 variant: direct loads, or the persistent TMA-staged form (identical bits either way)
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
  *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)

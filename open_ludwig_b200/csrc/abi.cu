@@ -422,7 +422,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.strict_occ = ctx->opt_strict_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
+    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.prefetch_distance = ctx->opt_prefetch_distance; a.strict_occ = ctx->opt_strict_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -911,6 +911,9 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
     else if (k == "strict_kernel") {            // where the strict K1 keeps the 27 pulled populations / how it loads them
         if (v == "reg") ctx->opt_strict_variant = 0; else if (v == "stash") ctx->opt_strict_variant = 1; else if (v == "tma") ctx->opt_strict_variant = 2;
         else return fail(ctx, LUDWIG_EINVAL, "strict_kernel: reg | stash | tma");
+    } else if (k == "prefetch_distance") {      // K1: every CTA prefetches the lines of the list entry this many blocks ahead into L2 (0 = off)
+        ctx->opt_prefetch_distance = atoi(value);
+        if (ctx->opt_prefetch_distance < 0) return fail(ctx, LUDWIG_EINVAL, "prefetch_distance >= 0");
     } else if (k == "strict_occupancy") {       // strict K1 (64-thread CTAs): resident warps per SM / 4 -> register budget 128 / 96 / 80
         const int n = atoi(value);
         if (n != 4 && n != 5 && n != 6) return fail(ctx, LUDWIG_EINVAL, "strict_occupancy: 4 | 5 | 6");

@@ -17,6 +17,26 @@ __device__ __forceinline__ void neighbour_offsets(const K1Args& a, int b, int t,
     s_vo[t] = nbi < 0 ? MISSING : nbi < a.nb ? (long long)nbi * (3 * BS3) : nbi < REMOTE_BASE ? MISSING : a.roff_v[nbi - REMOTE_BASE];
 }
 
+// Software prefetch into L2 (option prefetch_distance = D blocks): the hardware hands out CTAs in list order, so the CTA working on
+// list entry i asks the memory system for the part of entry i + D it corresponds to (its z-planes of the 27 population planes and of
+// the 3 velocity planes: 128-byte lines) — the loads that arrive D blocks later find their lines in the 126 MB L2 instead of
+// paying the full DRAM latency, with no shared-memory staging, no barrier and no extra DRAM traffic (every line is still fetched once).
+template <int NT>
+__device__ __forceinline__ void prefetch_block_part(const K1Args& a, int entry, int part) {
+    if (a.prefetch_distance <= 0) return;
+    const int e = entry + a.prefetch_distance;
+    if (e >= a.n_list) return;
+    const int pb = a.list[e];
+    constexpr int LINES_PER_PLANE_PART = (NT * 2 * 4) / 128;            // this CTA's cells of one direction plane, in 128-byte lines (64 threads: 4)
+    constexpr int N_LINES = (Q + 3) * LINES_PER_PLANE_PART;
+    for (int i = threadIdx.x; i < N_LINES; i += NT) {
+        const int plane = i / LINES_PER_PLANE_PART, line = i % LINES_PER_PLANE_PART;
+        const float* ptr = plane < Q ? a.f_in + ((size_t)pb * Q + plane) * BS3 + part * (NT * 2) + line * 32
+                                     : a.vel_in + ((size_t)pb * 3 + (plane - Q)) * BS3 + part * (NT * 2) + line * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+}
+
 // ---- TMA variant primitives: one cp.async.bulk moves a block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the
 // block-major layout) into shared memory and signals an mbarrier with the byte count
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

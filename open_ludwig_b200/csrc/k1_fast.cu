@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(NT, MINB * (256 / NT)) k1_fast_kernel(const __
     const int b = a.list[blockIdx.x / PARTS];
     if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
     __syncthreads();
+    prefetch_block_part<NT>(a, (int)(blockIdx.x / PARTS), (int)(blockIdx.x % PARTS));
     fast_block<FULL, VELFB, MISS>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo);
 }
 

@@ -127,7 +127,7 @@ template <> struct FStore<true> {
 // One 8^3 block: 256 threads, two x-adjacent cells per thread.  fbase + s_fo[d] is neighbour block d's populations (fbase is
 // a.f_in, or — TMA variant — the same address with its global provenance hidden, because s_fo[13] then points into shared memory
 // and the loads must be generic).
-template <bool FULL, bool VELFB, bool MISS, bool STASH>
+template <bool FULL, bool VELFB, bool MISS, bool STASH, bool WALE_FIRST>
 __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const int t, const float* __restrict__ fbase, const long long* s_fo,
                                              const long long* s_vo, float2* s_stash) {
     const v2 NZ = V(a.negzero);
@@ -158,60 +158,65 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
     const int dM = p > 0 ? 1 : 0, xM = p > 0 ? x0 - 1 : 7;
     const int dP = p < 3 ? 1 : 2, xP = p < 3 ? x0 + 2 : 0;
 
-    // The relaxation rate depends only on the PREVIOUS step's velocities of the six axis neighbours, not on the populations: it is
-    // computed first, so that the 18 neighbour velocities (36 registers) are dead before the 27 pulled populations (54 registers)
-    // become live.
-    // ---- previous-step velocities of the six axis neighbours (physics_utils.jl:45-83)
+    // The relaxation rate depends only on the PREVIOUS step's velocities of the six axis neighbours (physics_utils.jl:45-83), not on
+    // the populations.  WALE_FIRST: it is computed before the pull, so that the 18 neighbour velocities (36 registers) are dead before
+    // the 27 pulled populations (54 registers) become live — the 96- / 80-register forms.  Otherwise (128 registers) the velocity
+    // loads follow the pull and the rate is computed just before the Pi loop, all loads of the thread in flight together.
     v2 uE[3], uW[3], uN[3], uS[3], uT[3], uB[3];
-    {
-        const int row = z * 64 + y * 8;
-        const float* __restrict__ vo = a.vel_in + s_vo[13] + c0;
-        const long long oM = s_vo[12 + dM], oP = s_vo[13 + (dP - 1)];
-        const long long oN = s_vo[y < 7 ? 13 : 16], oS = s_vo[y > 0 ? 13 : 10], oT = s_vo[z < 7 ? 13 : 22], oB = s_vo[z > 0 ? 13 : 4];
-        const int lN = z * 64 + ((y + 1) & 7) * 8 + x0, lS = z * 64 + ((y - 1) & 7) * 8 + x0;
-        const int lT = ((z + 1) & 7) * 64 + y * 8 + x0, lB = ((z - 1) & 7) * 64 + y * 8 + x0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const v2 own = ld2(vo + c * BS3);
-            uW[c] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + c * BS3] : own.x, own.x);
-            uE[c] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + c * BS3] : own.y);
-            uN[c] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + c * BS3) : own;
-            uS[c] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + c * BS3) : own;
-            uT[c] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + c * BS3) : own;
-            uB[c] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + c * BS3) : own;
-        }
-    }
-
-    // ---- WALE (:251-300) in the reference's expression order
     v2 omega;
+    auto load_neighbour_velocities = [&]() {
     {
-        const v2 h = V(0.5f);
-        const v2 g11 = VMUL(h, vsub(uE[0], uW[0])), g12 = VMUL(h, vsub(uN[0], uS[0])), g13 = VMUL(h, vsub(uT[0], uB[0]));
-        const v2 g21 = VMUL(h, vsub(uE[1], uW[1])), g22 = VMUL(h, vsub(uN[1], uS[1])), g23 = VMUL(h, vsub(uT[1], uB[1]));
-        const v2 g31 = VMUL(h, vsub(uE[2], uW[2])), g32 = VMUL(h, vsub(uN[2], uS[2])), g33 = VMUL(h, vsub(uT[2], uB[2]));
+            const int row = z * 64 + y * 8;
+            const float* __restrict__ vo = a.vel_in + s_vo[13] + c0;
+            const long long oM = s_vo[12 + dM], oP = s_vo[13 + (dP - 1)];
+            const long long oN = s_vo[y < 7 ? 13 : 16], oS = s_vo[y > 0 ? 13 : 10], oT = s_vo[z < 7 ? 13 : 22], oB = s_vo[z > 0 ? 13 : 4];
+            const int lN = z * 64 + ((y + 1) & 7) * 8 + x0, lS = z * 64 + ((y - 1) & 7) * 8 + x0;
+            const int lT = ((z + 1) & 7) * 64 + y * 8 + x0, lB = ((z - 1) & 7) * 64 + y * 8 + x0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const v2 own = ld2(vo + c * BS3);
+                uW[c] = make_float2((!VELFB || oM != MISSING) ? a.vel_in[oM + (row + xM) + c * BS3] : own.x, own.x);
+                uE[c] = make_float2(own.y, (!VELFB || oP != MISSING) ? a.vel_in[oP + (row + xP) + c * BS3] : own.y);
+                uN[c] = (!VELFB || oN != MISSING) ? ld2(a.vel_in + oN + lN + c * BS3) : own;
+                uS[c] = (!VELFB || oS != MISSING) ? ld2(a.vel_in + oS + lS + c * BS3) : own;
+                uT[c] = (!VELFB || oT != MISSING) ? ld2(a.vel_in + oT + lT + c * BS3) : own;
+                uB[c] = (!VELFB || oB != MISSING) ? ld2(a.vel_in + oB + lB + c * BS3) : own;
+            }
+        }
+
+    };
+    auto relaxation_rate = [&]() {      // WALE (:251-300) in the reference's expression order
+    {
+            const v2 h = V(0.5f);
+            const v2 g11 = VMUL(h, vsub(uE[0], uW[0])), g12 = VMUL(h, vsub(uN[0], uS[0])), g13 = VMUL(h, vsub(uT[0], uB[0]));
+            const v2 g21 = VMUL(h, vsub(uE[1], uW[1])), g22 = VMUL(h, vsub(uN[1], uS[1])), g23 = VMUL(h, vsub(uT[1], uB[1]));
+            const v2 g31 = VMUL(h, vsub(uE[2], uW[2])), g32 = VMUL(h, vsub(uN[2], uS[2])), g33 = VMUL(h, vsub(uT[2], uB[2]));
 #define DOT3(a1, b1, a2, b2, a3, b3) vadd(vadd(VMUL(a1, b1), VMUL(a2, b2)), VMUL(a3, b3))
-        const v2 gsq11 = DOT3(g11, g11, g12, g21, g13, g31), gsq12 = DOT3(g11, g12, g12, g22, g13, g32), gsq13 = DOT3(g11, g13, g12, g23, g13, g33);
-        const v2 gsq21 = DOT3(g21, g11, g22, g21, g23, g31), gsq22 = DOT3(g21, g12, g22, g22, g23, g32), gsq23 = DOT3(g21, g13, g22, g23, g23, g33);
-        const v2 gsq31 = DOT3(g31, g11, g32, g21, g33, g31), gsq32 = DOT3(g31, g12, g32, g22, g33, g32), gsq33 = DOT3(g31, g13, g32, g23, g33, g33);
-        const v2 tr_gsq = vadd(vadd(gsq11, gsq22), gsq33);
-        const v2 tr_term = vdiv(tr_gsq, V(3.0f));
-        const v2 Sd11 = vsub(gsq11, tr_term), Sd22 = vsub(gsq22, tr_term), Sd33 = vsub(gsq33, tr_term);
-        const v2 Sd12 = VMUL(h, vadd(gsq12, gsq21)), Sd13 = VMUL(h, vadd(gsq13, gsq31)), Sd23 = VMUL(h, vadd(gsq23, gsq32));
-        const v2 S12 = VMUL(h, vadd(g12, g21)), S13 = VMUL(h, vadd(g13, g31)), S23 = VMUL(h, vadd(g23, g32));
-        const v2 OP1 = vadd(DOT3(Sd11, Sd11, Sd22, Sd22, Sd33, Sd33), VMUL(V(2.0f), DOT3(Sd12, Sd12, Sd13, Sd13, Sd23, Sd23)));
-        const v2 OP2 = vadd(DOT3(g11, g11, g22, g22, g33, g33), VMUL(V(2.0f), DOT3(S12, S12, S13, S13, S23, S23)));
+            const v2 gsq11 = DOT3(g11, g11, g12, g21, g13, g31), gsq12 = DOT3(g11, g12, g12, g22, g13, g32), gsq13 = DOT3(g11, g13, g12, g23, g13, g33);
+            const v2 gsq21 = DOT3(g21, g11, g22, g21, g23, g31), gsq22 = DOT3(g21, g12, g22, g22, g23, g32), gsq23 = DOT3(g21, g13, g22, g23, g23, g33);
+            const v2 gsq31 = DOT3(g31, g11, g32, g21, g33, g31), gsq32 = DOT3(g31, g12, g32, g22, g33, g32), gsq33 = DOT3(g31, g13, g32, g23, g33, g33);
+            const v2 tr_gsq = vadd(vadd(gsq11, gsq22), gsq33);
+            const v2 tr_term = vdiv(tr_gsq, V(3.0f));
+            const v2 Sd11 = vsub(gsq11, tr_term), Sd22 = vsub(gsq22, tr_term), Sd33 = vsub(gsq33, tr_term);
+            const v2 Sd12 = VMUL(h, vadd(gsq12, gsq21)), Sd13 = VMUL(h, vadd(gsq13, gsq31)), Sd23 = VMUL(h, vadd(gsq23, gsq32));
+            const v2 S12 = VMUL(h, vadd(g12, g21)), S13 = VMUL(h, vadd(g13, g31)), S23 = VMUL(h, vadd(g23, g32));
+            const v2 OP1 = vadd(DOT3(Sd11, Sd11, Sd22, Sd22, Sd33, Sd33), VMUL(V(2.0f), DOT3(Sd12, Sd12, Sd13, Sd13, Sd23, Sd23)));
+            const v2 OP2 = vadd(DOT3(g11, g11, g22, g22, g33, g33), VMUL(V(2.0f), DOT3(S12, S12, S13, S13, S23, S23)));
 #undef DOT3
-        const v2 OP1_32 = VMUL(OP1, vsqrt(OP1));
-        const v2 OP2_52 = VMUL(VMUL(OP2, OP2), vsqrt(vmaxs(OP2, 1.0e-12f)));
-        const v2 denom = vadd(OP2_52, VMUL(OP1, vsqrt(vsqrt(vmaxs(OP1, 1.0e-12f)))));
-        const float cw2 = __fmul_rn(a.c_wale, a.c_wale);
-        float ne0 = 0.0f, ne1 = 0.0f;
-        if (OP1.x > 1.0e-12f && denom.x > 1.0e-12f) ne0 = __fdiv_rn(__fmul_rn(cw2, OP1_32.x), denom.x);
-        if (OP1.y > 1.0e-12f && denom.y > 1.0e-12f) ne1 = __fdiv_rn(__fmul_rn(cw2, OP1_32.y), denom.y);
-        const v2 nu_eddy = vmaxs(make_float2(ne0, ne1), a.nu_bg);
-        const v2 tau_turb = vadd(V(a.tau), VMUL(nu_eddy, V(3.0f)));
-        omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
-    }
+            const v2 OP1_32 = VMUL(OP1, vsqrt(OP1));
+            const v2 OP2_52 = VMUL(VMUL(OP2, OP2), vsqrt(vmaxs(OP2, 1.0e-12f)));
+            const v2 denom = vadd(OP2_52, VMUL(OP1, vsqrt(vsqrt(vmaxs(OP1, 1.0e-12f)))));
+            const float cw2 = __fmul_rn(a.c_wale, a.c_wale);
+            float ne0 = 0.0f, ne1 = 0.0f;
+            if (OP1.x > 1.0e-12f && denom.x > 1.0e-12f) ne0 = __fdiv_rn(__fmul_rn(cw2, OP1_32.x), denom.x);
+            if (OP1.y > 1.0e-12f && denom.y > 1.0e-12f) ne1 = __fdiv_rn(__fmul_rn(cw2, OP1_32.y), denom.y);
+            const v2 nu_eddy = vmaxs(make_float2(ne0, ne1), a.nu_bg);
+            const v2 tau_turb = vadd(V(a.tau), VMUL(nu_eddy, V(3.0f)));
+            omega = vdiv(V(1.0f), vmaxs(tau_turb, 0.500001f));
+        }
+
+    };
+    if (WALE_FIRST) { load_neighbour_velocities(); relaxation_rate(); }
 
     // ---- pull-stream (:62-149) with the moment sums of :144-148 taken in k order as the values arrive; combo (jy,jz) yields the
     // three consecutive directions k0-1, k0, k0+1 and the combos are visited in ascending k0
@@ -285,6 +290,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         }
     }
 
+    if (!WALE_FIRST) load_neighbour_velocities();
+
     rho = vmaxs(rho, 0.01f);                                          // :172
     const v2 inv_rho = vdiv(V(1.0f), rho);
     v2 ux = VMUL(jx, inv_rho), uy = VMUL(jy, inv_rho), uz = VMUL(jz, inv_rho);
@@ -331,6 +338,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
     } else {
         st2(vout, ux); st2(vout + BS3, uy); st2(vout + 2 * BS3, uz); st2(rout, rho);
     }
+
+    if (!WALE_FIRST) relaxation_rate();
 
     // ---- Pi loop (:308-322): the stored f_k is replaced by feq_k
     const v2 usq15 = VMUL(V(1.5f), usq);
@@ -408,7 +417,8 @@ __global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT)
     const int b = a.list[blockIdx.x / PARTS];
     if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
     __syncthreads();
-    strict_block<FULL, VELFB, MISS, STASH>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo, s_stash);
+    prefetch_block_part<NT>(a, (int)(blockIdx.x / PARTS), (int)(blockIdx.x % PARTS));
+    strict_block<FULL, VELFB, MISS, STASH, (OCC > 4)>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo, s_stash);
 }
 
 // ---- TMA variant: persistent CTAs, the block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the block-major
@@ -460,7 +470,7 @@ __global__ void __launch_bounds__(256, 2) k1_strict_tma_kernel(const __grid_cons
             }
         }
         mbar_wait(&s_bar[cur], (uint32_t)((it >> 1) & 1));
-        strict_block<FULL, VELFB, MISS, false>(a, b, t, fbase, s_fo[cur], s_vo[cur], nullptr);
+        strict_block<FULL, VELFB, MISS, false, false>(a, b, t, fbase, s_fo[cur], s_vo[cur], nullptr);
     }
 }
 
