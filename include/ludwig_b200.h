@@ -313,6 +313,7 @@ int ludwig_multi_compute_aerodynamics(ludwig_multi* m, int32_t handle, int32_t l
 int ludwig_multi_forces_download_maps(ludwig_multi* m, int32_t handle, float* p, float* sx, float* sy, float* sz);
 int ludwig_multi_output_valid_blocks(ludwig_multi* m, int32_t* n_valid, int32_t* blocks);                               /* io_vtk.jl:17-46 */
 int ludwig_multi_output_export(ludwig_multi* m, int64_t t_step, float* rho_arr, float* vel_mat, uint8_t* obst_arr, int32_t* level_arr);   /* io_vtk.jl:52-111 */
+int64_t ludwig_multi_self_check(ludwig_multi* m);                                                   /* ludwig_ctx_self_check on every rank */
 int64_t ludwig_multi_device_bytes(const ludwig_multi* m);
 
 /* -- domain build on the device (N2: the step BEFORE the hot path; the kept Julia driver's setup code calls these instead of its
@@ -339,6 +340,11 @@ int64_t ludwig_domain_qmap(int device, const double* tris, int64_t n_tri, const 
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a host framework can
  * record its own events on it or order other work against it.  NULL for a CPU backend. */
 void* ludwig_ctx_stream(ludwig_ctx* ctx);
+/* Bounds checks of the library's own (compute-sanitizer is not available on the target pool): every index table the kernels turn into
+ * addresses — neighbour tables, remote-block tables against the owners' block counts, peer offsets against offsets recomputed from
+ * the mapped base pointers, the rank-encoded block pointer, the K1 work lists, the Bouzidi cells — is range-checked / re-derived on
+ * the host.  Returns the number of violations (0 = clean; the first one is described by ludwig_last_error) or a negative error code. */
+int64_t ludwig_ctx_self_check(ludwig_ctx* ctx);
 /* Number of kernels this library has launched on the context since creation (kernels inside a replayed CUDA graph included). */
 int64_t ludwig_launch_count(const ludwig_ctx* ctx);
 /* Number of coarse steps executed by replaying a captured CUDA graph (option graphs). */

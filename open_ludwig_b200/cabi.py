@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_multi_flow_stats", "ludwig_multi_forces_create", "ludwig_multi_compute_aerodynamics",
     "ludwig_multi_forces_download_maps", "ludwig_multi_device_bytes",
     "ludwig_domain_last_error", "ludwig_domain_voxelize", "ludwig_domain_wall_distance", "ludwig_domain_qmap",
+    "ludwig_ctx_self_check", "ludwig_multi_self_check",
     "ludwig_graph_replays", "ludwig_init_uniform_flow", "ludwig_multi_init_uniform_flow",
     "ludwig_output_valid_blocks", "ludwig_output_export", "ludwig_multi_output_valid_blocks", "ludwig_multi_output_export",
 )
@@ -154,6 +155,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_domain_voxelize": (C.c_int, [C.c_int, vp, i64, vp, f64, vp, i32, vp, i32, i32, i32, vp]),
         "ludwig_domain_wall_distance": (C.c_int64, [C.c_int, vp, i32, vp, f64, vp]),
         "ludwig_domain_qmap": (C.c_int64, [C.c_int, vp, i64, vp, f64, vp, i32, vp, i32, i32, i32, i64, vp, vp, vp]),
+        "ludwig_ctx_self_check": (C.c_int64, [vp]),
+        "ludwig_multi_self_check": (C.c_int64, [vp]),
         "ludwig_graph_replays": (C.c_int64, [vp]),
         "ludwig_init_uniform_flow": (C.c_int, [vp, f32]),
         "ludwig_multi_init_uniform_flow": (C.c_int, [vp, f32]),
@@ -306,6 +309,13 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ludwig_launch_count(self._h))
+
+    def self_check(self) -> int:
+        """ludwig_ctx_self_check: number of index-table violations (0 = clean)."""
+        n = int(self.lib.ludwig_ctx_self_check(self._h))
+        if n < 0:
+            self._check(n, "ludwig_ctx_self_check")
+        return n
 
     def graph_replays(self) -> int:
         return int(self.lib.ludwig_graph_replays(self._h))
@@ -622,6 +632,12 @@ class MultiContext:
 
     def init_equilibrium(self):
         self._check(self.lib.ludwig_multi_init_equilibrium(self._h), "ludwig_multi_init_equilibrium")
+
+    def self_check(self) -> int:
+        n = int(self.lib.ludwig_multi_self_check(self._h))
+        if n < 0:
+            self._check(n, "ludwig_multi_self_check")
+        return n
 
     def init_uniform_flow(self, ux: float):
         self._check(self.lib.ludwig_multi_init_uniform_flow(self._h, C.c_float(ux)), "ludwig_multi_init_uniform_flow")

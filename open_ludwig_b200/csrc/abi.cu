@@ -948,6 +948,84 @@ int ludwig_num_levels(const ludwig_ctx* ctx) { return ctx ? (int)ctx->levels.siz
 int64_t ludwig_device_bytes(const ludwig_ctx* ctx) { return ctx ? ctx->bytes : 0; }
 
 void* ludwig_ctx_stream(ludwig_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+// Bounds checks of our own (compute-sanitizer is not available on the target pool): every index table the kernels turn into
+// addresses is re-derived / range-checked on the host.  All in-block offsets are bounded by construction (direction * 512 + cell
+// < 27 * 512), so a kernel can only leave its buffers through a wrong BLOCK index or a wrong peer offset — exactly what is
+// checked here: the neighbour tables (local / ghost / remote ranges), the remote tables against the owners' block counts, the
+// peer offsets against offsets recomputed from the mapped base pointers, the rank-encoded block pointer, the work lists and the
+// Bouzidi cells.  Returns the number of violations (0 = clean) or a negative error code; the first violation is in last_error.
+int64_t ludwig_ctx_self_check(ludwig_ctx* ctx) {
+    if (!ctx) return LUDWIG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int64_t bad = 0;
+    auto flag = [&](const std::string& what) { if (bad++ == 0) ctx->err = "self-check: " + what; };
+    auto fetch_i32 = [&](const int32_t* d, size_t n, std::vector<int32_t>& h) -> bool {
+        h.resize(n);
+        return n == 0 || memcpy_sync(ctx->stream, h.data(), d, n * sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        Level& L = *ctx->levels[l];
+        const std::string at = " (level " + std::to_string(l + 1) + ")";
+        if ((int)L.part_starts.size() != ctx->world + 1 || L.part_starts[ctx->rank + 1] - L.part_starts[ctx->rank] != L.nb) flag("partition ranges" + at);
+        for (int i = 0; i < L.n_remote; ++i) {
+            const int ow = L.remote_owner[i];
+            if (ow < 0 || ow >= ctx->world || ow == ctx->rank) { flag("remote owner out of range" + at); continue; }
+            if (L.remote_local[i] < 0 || L.remote_local[i] >= L.part_starts[ow + 1] - L.part_starts[ow]) flag("remote block index beyond the owner's blocks" + at);
+        }
+        std::vector<int32_t> h;
+        const int32_t* tabs[2] = {L.d_nbr, L.d_nbr_fast};
+        for (int ti = 0; ti < 2; ++ti) {
+            if (!tabs[ti]) continue;
+            if (!fetch_i32(tabs[ti], (size_t)L.nb * 27, h)) return fail(ctx, LUDWIG_ECUDA, "self-check: table download failed");
+            for (size_t i = 0; i < h.size(); ++i) {
+                const int32_t v = h[i];
+                const bool ok = v == -1 || (v >= 0 && v < L.nb) || (ti == 1 && v >= L.nb && v < L.nb + L.n_ghost) || (v >= REMOTE_BASE && v - REMOTE_BASE < L.n_remote);
+                if (!ok) { flag("neighbour table entry out of range" + at); break; }
+                if (i % 27 == 13 && v != (int32_t)(i / 27)) { flag("neighbour table: direction 13 is not the block itself" + at); break; }
+            }
+        }
+        if (ctx->peers_attached && L.n_remote > 0)
+            for (int par = 0; par < 2; ++par) {
+                std::vector<long long> of(L.n_remote), ov(L.n_remote);
+                if (memcpy_sync(ctx->stream, of.data(), L.d_roff_f[par], of.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                    memcpy_sync(ctx->stream, ov.data(), L.d_roff_v[par], ov.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+                    return fail(ctx, LUDWIG_ECUDA, "self-check: offset download failed");
+                for (int i = 0; i < L.n_remote; ++i) {
+                    const int ow = L.remote_owner[i];
+                    if (ow < 0 || ow >= ctx->world || !L.peer_f[par][ow] || !L.peer_vel[par][ow]) { flag("peer buffer not mapped" + at); break; }
+                    if (of[i] != (long long)((L.peer_f[par][ow] + (size_t)L.remote_local[i] * Q * BS3) - L.d_f[par]) ||
+                        ov[i] != (long long)((L.peer_vel[par][ow] + (size_t)L.remote_local[i] * 3 * BS3) - L.d_vel[par])) { flag("peer offset does not address the remote block" + at); break; }
+                }
+            }
+        if (!fetch_i32(L.d_ptr, (size_t)L.dimx * L.dimy * L.dimz, h)) return fail(ctx, LUDWIG_ECUDA, "self-check: pointer download failed");
+        size_t n_ptr = 0;
+        for (int32_t v : h) {
+            if (v < 0) continue;
+            ++n_ptr;
+            const int ow = v >> PTR_RANK_SHIFT, loc = v & PTR_LOCAL_MASK;
+            if (ow >= ctx->world || loc >= L.part_starts[ow + 1] - L.part_starts[ow]) { flag("block pointer entry out of range" + at); break; }
+        }
+        if (n_ptr != (size_t)L.nb_global) flag("block pointer does not hold every block once" + at);
+        if (L.fast_ready) {
+            const int32_t* lists[4] = {L.d_list_plain, L.d_list_plain_g, L.d_list_feat, L.d_list_full};
+            const int counts[4] = {L.n_plain, L.n_plain_g, L.n_feat, L.n_full};
+            std::vector<uint8_t> seen(L.nb, 0);
+            for (int li = 0; li < 4; ++li) {
+                if (!fetch_i32(lists[li], (size_t)counts[li], h)) return fail(ctx, LUDWIG_ECUDA, "self-check: list download failed");
+                for (int32_t b : h) { if (b < 0 || b >= L.nb || seen[b]++) { flag("work lists are not a partition of the blocks" + at); break; } }
+            }
+            if (L.n_plain + L.n_plain_g + L.n_feat + L.n_full != L.nb) flag("work lists do not cover every block" + at);
+        }
+        for (int32_t c : L.h_bc_cell) if (c < 0 || c >= L.nb * BS3) { flag("Bouzidi cell out of range" + at); break; }
+        if (L.n_links > 0) {
+            if (!fetch_i32(L.d_link_cell, (size_t)L.n_links, h)) return fail(ctx, LUDWIG_ECUDA, "self-check: link download failed");
+            for (int32_t c : h) if (c < 0 || c >= L.nb * BS3) { flag("Bouzidi link cell out of range" + at); break; }
+        }
+    }
+    return bad;
+}
+
 int64_t ludwig_launch_count(const ludwig_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t ludwig_graph_replays(const ludwig_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 int ludwig_profile_enable(ludwig_ctx* ctx, int32_t on) {
@@ -2047,6 +2125,13 @@ int ludwig_multi_output_export(ludwig_multi* m, int64_t t_step, float* rho_arr, 
     if (!m) return LUDWIG_EINVAL;
     for (ludwig_ctx* c : m->ctx) { int rc = ludwig_output_export(c, t_step, rho_arr, vel_mat, obst_arr, level_arr); if (rc) return mpass(m, c, rc); }
     return LUDWIG_OK;
+}
+
+int64_t ludwig_multi_self_check(ludwig_multi* m) {
+    if (!m) return LUDWIG_EINVAL;
+    int64_t bad = 0;
+    for (ludwig_ctx* c : m->ctx) { const int64_t r = ludwig_ctx_self_check(c); if (r < 0) return mpass(m, c, (int)r); if (r > 0 && bad == 0) m->err = c->err; bad += r; }
+    return bad;
 }
 
 int64_t ludwig_multi_device_bytes(const ludwig_multi* m) {

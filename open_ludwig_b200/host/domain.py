@@ -175,6 +175,12 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
     levels: List[BlockLevel] = []
     reports: List[LevelReport] = []
     prev_active = None
+    import time as _time
+    phase_s: dict = {}
+
+    def timed(name, fn, *a):
+        t0 = _time.time(); r = fn(*a); phase_s[name] = phase_s.get(name, 0.0) + _time.time() - t0
+        return r
     for lvl in range(1, num_levels + 1):
         scale = 2 ** (lvl - 1)
         dx = params.dx_coarse / scale
@@ -188,7 +194,7 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
             if cfg.refinement_strategy != "geometry_first":
                 raise NotImplementedError("only the geometry_first refinement strategy (all shipped cases) is restated")
             grid = np.zeros(dims, np.uint8)
-            lib.ludwig_host_mark_surface_blocks(_p(tris), n_tri, _p(off), dx, dims[0], dims[1], dims[2], _p(grid))
+            timed("mark_surface_blocks", lib.ludwig_host_mark_surface_blocks, _p(tris), n_tri, _p(off), dx, dims[0], dims[1], dims[2], _p(grid))
             active = grid.astype(bool)
             if cfg.wake_enabled:                      # domain.jl:88-112
                 pc = levels[-1].active_block_coords.astype(np.float64)
@@ -206,7 +212,7 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
         n_after = int(active.sum())
         coords = (np.argwhere(active) + 1).astype(np.int32)      # lexicographic, 1-based
         nb = coords.shape[0]
-        nt, full_ptr = build_neighbor_table(coords, dims)
+        nt, full_ptr = timed("neighbor_table", build_neighbor_table, coords, dims)
         full_ptr_cm = np.ascontiguousarray(full_ptr.transpose(2, 1, 0))   # Julia [bx,by,bz] column-major bytes
 
         obstacle = np.zeros((nb, 8, 8, 8), np.uint8)
@@ -215,21 +221,21 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
         cflat = np.ascontiguousarray(coords)
         grid_ptr = np.ascontiguousarray(full_ptr, np.int32)       # [bx][by][bz], 1-based block index, 0 = none
         if glib is not None:
-            gcheck(glib.ludwig_domain_voxelize(gpu_device, _p(tris), n_tri, _p(off), dx, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1], dims[2],
-                                               _p(obstacle)), "ludwig_domain_voxelize")
+            gcheck(timed("voxelize", glib.ludwig_domain_voxelize, gpu_device, _p(tris), n_tri, _p(off), dx, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1], dims[2],
+                         _p(obstacle)), "ludwig_domain_voxelize")
         else:
-            lib.ludwig_host_voxelize(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), _p(obstacle))
+            timed("voxelize", lib.ludwig_host_voxelize, _p(tris), n_tri, _p(cflat), nb, dx, _p(off), _p(obstacle))
         shell = int(obstacle.sum())
-        filled = int(lib.ludwig_host_flood_fill(_p(obstacle), _p(cflat), nb, _p(full_ptr_cm), dims[0], dims[1], dims[2]))
-        lib.ludwig_host_sponge(_p(cflat), nb, dx, params.domain_size[0], params.domain_size[1], params.domain_size[2],
-                               float(cfg.sponge_thickness), int(cfg.symmetric), _p(sponge))
+        filled = int(timed("flood_fill", lib.ludwig_host_flood_fill, _p(obstacle), _p(cflat), nb, _p(full_ptr_cm), dims[0], dims[1], dims[2]))
+        timed("sponge", lib.ludwig_host_sponge, _p(cflat), nb, dx, params.domain_size[0], params.domain_size[1], params.domain_size[2],
+              float(cfg.sponge_thickness), int(cfg.symmetric), _p(sponge))
         near = 0
         if cfg.wall_model_enabled:
             if glib is not None:
                 nt_c = np.ascontiguousarray(nt, np.int32)
-                near = int(gcheck(glib.ludwig_domain_wall_distance(gpu_device, _p(nt_c), nb, _p(obstacle), dx, _p(wall_dist)), "ludwig_domain_wall_distance"))
+                near = int(gcheck(timed("wall_distance", glib.ludwig_domain_wall_distance, gpu_device, _p(nt_c), nb, _p(obstacle), dx, _p(wall_dist)), "ludwig_domain_wall_distance"))
             else:
-                near = int(lib.ludwig_host_wall_distance(_p(cflat), nb, _p(obstacle), dx, _p(wall_dist)))
+                near = int(timed("wall_distance", lib.ludwig_host_wall_distance, _p(cflat), nb, _p(obstacle), dx, _p(wall_dist)))
 
         use_bouzidi = cfg.boundary_method == "bouzidi" and lvl > (num_levels - cfg.bouzidi_levels)   # bouzidi_common.jl:28-34
         q_map = tri_map = cell_block = cell_x = cell_y = cell_z = None
@@ -240,11 +246,11 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
                     return int(gcheck(glib.ludwig_domain_qmap(gpu_device, _p(tris), n_tri, _p(off), dx, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1],
                                                               dims[2], cap, c_, q_, t_), "ludwig_domain_qmap"))
                 return int(lib.ludwig_host_qmap(_p(tris), n_tri, _p(cflat), nb, dx, _p(off), cap, c_, q_, t_))
-            n_bc = qmap(0, None, None, None)
+            n_bc = timed("qmap", qmap, 0, None, None, None)
             cells = np.zeros((max(n_bc, 1), 4), np.int32)
             qv = np.zeros((max(n_bc, 1), 27), np.float64)
             tv = np.zeros((max(n_bc, 1), 27), np.int32)
-            got = qmap(n_bc, _p(cells), _p(qv), _p(tv))
+            got = timed("qmap", qmap, n_bc, _p(cells), _p(qv), _p(tv))
             assert got == n_bc
             cells, qv, tv = cells[:n_bc], qv[:n_bc], tv[:n_bc]
             q_map = np.zeros((27, nb, 8, 8, 8), np.float16)
@@ -252,8 +258,8 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
             tri_map = np.zeros((27, nb, 8, 8, 8), np.int32) if build_tri_map else None
             q16 = qv.astype(np.float16)               # Float16(q) round-to-nearest-even (bouzidi_setup.jl:128)
             cells_c, qv_c, q16_c, tv_c = (np.ascontiguousarray(a) for a in (cells, qv, q16, tv))
-            lib.ludwig_host_scatter_qmap(_p(cells_c), _p(qv_c), _p(q16_c), _p(tv_c) if tri_map is not None else None, n_bc, nb,
-                                         _p(q_map), _p(tri_map) if tri_map is not None else None)
+            timed("scatter_qmap", lib.ludwig_host_scatter_qmap, _p(cells_c), _p(qv_c), _p(q16_c), _p(tv_c) if tri_map is not None else None, n_bc, nb,
+                  _p(q_map), _p(tri_map) if tri_map is not None else None)
             cell_block = cells[:, 0].astype(np.int32)
             cell_x, cell_y, cell_z = (cells[:, i].astype(np.int8) for i in (1, 2, 3))
             qf = q16.astype(np.float32)
@@ -273,7 +279,11 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
             print(f"--- Level {lvl} --- blocks {nb} (+{n_after - n_before} halo) shell {shell} filled {filled} near-wall {near} "
                   f"boundary cells {n_bc} links {links}", flush=True)
         prev_active = active
-    return Domain(cfg, params, mesh, levels, reports)
+    if verbose:
+        print("domain build phases [s]: " + ", ".join(f"{k} {v:.2f}" for k, v in phase_s.items()), flush=True)
+    dom = Domain(cfg, params, mesh, levels, reports)
+    dom.phase_s = phase_s
+    return dom
 
 
 def load_case(case_dir: str, overrides: Optional[dict] = None, verbose: bool = False, build_tri_map: bool = True,

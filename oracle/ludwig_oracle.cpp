@@ -962,6 +962,8 @@ int ludwig_ipc_attach(ludwig_ctx* ctx, const void*, int64_t) { return fail(ctx, 
 void* ludwig_ctx_stream(ludwig_ctx*) { return nullptr; }
 int64_t ludwig_launch_count(const ludwig_ctx*) { return 0; }
 int64_t ludwig_graph_replays(const ludwig_ctx*) { return 0; }
+int64_t ludwig_ctx_self_check(ludwig_ctx*) { return 0; }
+int64_t ludwig_multi_self_check(ludwig_multi*) { return LUDWIG_ESTATE; }
 // N2 device entry points: the host restatement (open_ludwig_b200/host/domain_build.cpp) is their CPU counterpart, not this oracle
 const char* ludwig_domain_last_error(void) { return "not part of the CPU oracle"; }
 int ludwig_domain_voxelize(int, const double*, int64_t, const double*, double, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t, uint8_t*) { return LUDWIG_ESTATE; }

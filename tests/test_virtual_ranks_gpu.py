@@ -44,6 +44,7 @@ def run_two_level(n_ranks, steps, strict, options=None, plan=False, levels=None)
         maps = m.download_force_maps(h, len(areas))
         stats = [m.flow_stats(i) for i in range(len(levels))]
         owners = [[len(m.rank_ctx(r).local_blocks(i)) for r in range(n_ranks)] for i in range(len(levels))]
+        assert m.self_check() == 0          # every index table / peer offset the kernels dereference is in range (host-side bounds checks)
     return out, aero, maps, stats, mid, owners
 
 

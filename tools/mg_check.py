@@ -77,6 +77,7 @@ def run_two_level(partitioned, steps=40, plan=False, strict=0):
     mesh = ctx.create_mesh(centers, nrm, areas)
     forces = ctx.create_forces(mesh, 1.225, 10.0, 1.0, 1.0, (20.0, 16.0, 16.0), False)
     ctx.step_batch(1, steps, 0.02, p); ctx.sync(); dist.barrier()
+    assert ctx.self_check() == 0, "index-table self-check failed"
     aero = ctx.compute_aerodynamics(forces, 1, (0.0, 0.0, 0.0), 300.0, 1.225, 5)
     if partitioned:
         aero = mg.reduce_aero(aero, dev)
