@@ -60,6 +60,13 @@ inline uint64_t spread3(uint32_t v) {   // 21 bits -> every third bit
     return x;
 }
 inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
+inline uint64_t morton2(uint32_t x, uint32_t y) {   // 16 bits each
+    auto s2 = [](uint64_t v) {
+        v &= 0xffff; v = (v | v << 8) & 0x00ff00ffULL; v = (v | v << 4) & 0x0f0f0f0fULL; v = (v | v << 2) & 0x33333333ULL; v = (v | v << 1) & 0x55555555ULL;
+        return v;
+    };
+    return s2(x) | (s2(y) << 1);
+}
 
 void free_level(Level* L) {
     if (!L) return;
@@ -422,7 +429,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.prefetch_distance = ctx->opt_prefetch_distance; a.strict_occ = ctx->opt_strict_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
+    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.prefetch_distance = ctx->opt_prefetch_distance; a.strict_occ = ctx->opt_strict_occ; a.strict_loop = ctx->opt_strict_loop; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -918,6 +925,15 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         const int n = atoi(value);
         if (n != 4 && n != 5 && n != 6) return fail(ctx, LUDWIG_EINVAL, "strict_occupancy: 4 | 5 | 6");
         ctx->opt_strict_occ = n;
+    } else if (k == "l2_fetch") {               // cudaLimitMaxL2FetchGranularity of the device: 32 | 64 | 128 bytes (a hint to the L2)
+        const int n = atoi(value);
+        if (n != 32 && n != 64 && n != 128) return fail(ctx, LUDWIG_EINVAL, "l2_fetch: 32 | 64 | 128");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)n));
+    } else if (k == "strict_loop") {            // strict plain K1 (64-thread CTAs, strict_occupancy 5): z-plane pairs of a block one CTA works through
+        const int n = atoi(value);
+        if (n != 1 && n != 2 && n != 4) return fail(ctx, LUDWIG_EINVAL, "strict_loop: 1 | 2 | 4");
+        ctx->opt_strict_loop = n;
     } else if (k == "cta_threads") {            // threads per CTA of the non-persistent K1 kernels: a CTA takes 8 / 4 / 2 z-planes of a block
         const int n = v == "auto" ? 0 : atoi(value);
         if (n != 0 && n != 256 && n != 128 && n != 64) return fail(ctx, LUDWIG_EINVAL, "cta_threads: auto | 256 | 128 | 64");
@@ -935,6 +951,11 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         if (!before_levels) return need_early();
         if (v == "morton") ctx->partition_mode = 0; else if (v == "rcb") ctx->partition_mode = 1; else if (v == "rcb_yz") ctx->partition_mode = 2;
         else return fail(ctx, LUDWIG_EINVAL, "partition: morton | rcb | rcb_yz");
+    } else if (k == "block_order") {            // internal block order within a rank: "morton" | "xslab<T>" (T = 2..64, default xslab8)
+        if (!before_levels) return need_early();
+        if (v == "morton") ctx->opt_block_order = 0;
+        else if (v.rfind("xslab", 0) == 0 && atoi(value + 5) >= 2 && atoi(value + 5) <= 64) ctx->opt_block_order = atoi(value + 5);
+        else return fail(ctx, LUDWIG_EINVAL, "block_order: morton | xslab<T> with T = 2..64");
     } else if (k == "remote_order") {           // where the blocks that pull from a peer sit in the plain launch
         if (v != "morton" && v != "first" && v != "last" && v != "interleave") return fail(ctx, LUDWIG_EINVAL, "remote_order: morton | first | last | interleave");
         for (Level* L : ctx->levels) if (L->fast_ready) return fail(ctx, LUDWIG_ESTATE, "remote_order must be set before the first step");
@@ -1150,6 +1171,23 @@ int ludwig_level_create(ludwig_ctx* ctx, const ludwig_level_desc* d, int32_t* ou
             L.part_starts[r] = cut;
         }
         L.part_starts[ctx->world] = nbg;
+    }
+    // --- order WITHIN each rank's range ("block_order").  In the block-major layout an x-face halo layer costs a full 32-byte
+    // sector per 4 useful bytes (8x), a y- or z-face layer 1x, so the x neighbours of a block must still be in L2 when it runs:
+    // x-slab order = tiles of T x T blocks in (y, z), Morton order over the tiles, and inside a tile x-slices one after the other
+    // (x-neighbour distance T^2 blocks, always an L2 hit; only the tile faces in y / z can miss).  Measured on the 512^3 box:
+    // profiles/README.md.  The owner of every block is unchanged (the ranges were cut on the Morton / RCB order above).
+    if (ctx->opt_block_order > 0) {
+        const uint32_t T = (uint32_t)ctx->opt_block_order;
+        std::vector<uint64_t> k2(nbg);
+        for (int i = 0; i < nbg; ++i) {
+            const uint32_t bx = (uint32_t)(d->map_x[i] - 1), by = (uint32_t)(d->map_y[i] - 1), bz = (uint32_t)(d->map_z[i] - 1);
+            const uint64_t tile = morton2(by / T, bz / T);
+            k2[i] = ((tile * (uint64_t)(d->dim_x + 1) + bx) * T + (by % T)) * T + (bz % T);
+        }
+        for (int r = 0; r < ctx->world; ++r)
+            std::sort(L.int2ref.begin() + L.part_starts[r], L.int2ref.begin() + L.part_starts[r + 1], [&](int32_t a, int32_t b) { return k2[a] < k2[b]; });
+        for (int i = 0; i < nbg; ++i) L.ref2int[L.int2ref[i]] = i;
     }
     L.part_start = L.part_starts[ctx->rank];
     const int nb = L.part_starts[ctx->rank + 1] - L.part_start;

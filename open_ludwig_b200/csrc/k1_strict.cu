@@ -408,17 +408,22 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
 // resident per SM and their load and compute phases interleave (the register-limited occupancy is the same number of warps).
 // OCC: resident warps per SM in units of four (16 / 20 / 24 warps -> 128 / 96 / 80 registers per thread).  With the relaxation rate
 // computed before the pull (see strict_block) 96 registers cost 32 bytes of spills and 80 registers 112 bytes.
-template <bool FULL, bool VELFB, bool MISS, bool STASH, int NT, int OCC = 4>
+// LOOP: consecutive parts of ONE block a CTA works through (64-thread CTAs, LOOP = 4: the CTA walks up the block's four z-plane
+// pairs): list entry -> neighbour table -> offsets (two dependent memory round trips and a barrier before the first useful load)
+// are paid once per block instead of once per part, and the z-halo planes of one part are the own planes of the next (L1).
+template <bool FULL, bool VELFB, bool MISS, bool STASH, int NT, int OCC = 4, int LOOP = 1>
 __global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT) k1_strict_kernel(const __grid_constant__ K1Args a) {
     extern __shared__ float2 s_stash[];
     __shared__ long long s_fo[27];   // element offset of each neighbour block relative to f_in (MISSING: no block)
     __shared__ long long s_vo[27];   // ... relative to vel_in (MISSING for ghost blocks: they carry populations only)
-    constexpr int PARTS = 256 / NT;
-    const int b = a.list[blockIdx.x / PARTS];
+    constexpr int CTAS = 256 / (NT * LOOP);   // CTAs per block
+    const int b = a.list[blockIdx.x / CTAS];
     if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
     __syncthreads();
-    prefetch_block_part<NT>(a, (int)(blockIdx.x / PARTS), (int)(blockIdx.x % PARTS));
-    strict_block<FULL, VELFB, MISS, STASH, (OCC > 4)>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo, s_stash);
+    if (LOOP == 1) prefetch_block_part<NT>(a, (int)(blockIdx.x / CTAS), (int)(blockIdx.x % CTAS));
+#pragma unroll 1
+    for (int l = 0; l < LOOP; ++l)
+        strict_block<FULL, VELFB, MISS, STASH, (OCC > 4)>(a, b, (int)threadIdx.x + ((int)(blockIdx.x % CTAS) * LOOP + l) * NT, a.f_in, s_fo, s_vo, s_stash);
 }
 
 // ---- TMA variant: persistent CTAs, the block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the block-major
@@ -496,6 +501,8 @@ void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
     else if (a.cta_threads == 64) {
         // (the feature / domain-face instantiations would spill ~0.5-1 KB per thread at 96 / 80 registers: plain classes only)
         if constexpr (!FULL) {
+            if (a.strict_loop == 4 && a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5, 4><<<a.n_list, 64, 0, s>>>(a); return; }
+            if (a.strict_loop == 2 && a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5, 2><<<2 * a.n_list, 64, 0, s>>>(a); return; }
             if (a.strict_occ == 6) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 6><<<4 * a.n_list, 64, 0, s>>>(a); return; }
             if (a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5><<<4 * a.n_list, 64, 0, s>>>(a); return; }
         }

@@ -150,7 +150,7 @@ def load_domain_shared(name: str, log=None):
 
 def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = False, options: dict | None = None, plan: bool = False,
                     ramp_steps: int | None = None, profile_steps: int = 0, log=None, dom=None, all_ranks_levels: bool = False,
-                    uniform_start: bool = False) -> dict:
+                    uniform_start: bool = False, param_overrides: dict | None = None) -> dict:
     """One strong-scaling measurement of a named case (open_ludwig_b200.host.cases) over the ranks of the current process
     group (or a single GPU when torch.distributed is not initialised): every rank creates its partitioned context from the
     shared domain (load_domain_shared), attaches the peers and steps `steps` coarse steps along the driver's cosine ramp
@@ -188,6 +188,8 @@ def run_case_strong(name: str, steps: int, local_rank: int, *, strict: bool = Fa
         else:
             ctx.init_equilibrium()
         params = make_params(dom, strict=strict)
+        for k, v in (param_overrides or {}).items():              # experiments only (e.g. wall_model_active=0 to time a feature alone)
+            setattr(params, k, type(getattr(params, k))(v))
         ctx.sync()
         upload_s = time.time() - t0
         ramp = 1 if uniform_start else (ramp_steps or dom.cfg.ramp_steps)

@@ -25,6 +25,19 @@ def morton_order(coords_1based: np.ndarray) -> np.ndarray:
     return np.argsort(key, kind="stable").astype(np.int32)
 
 
+BLOCK_ORDER_DEFAULT = 12   # the library's default "block_order" option (csrc/ludwig_internal.h: opt_block_order)
+
+
+def xslab_key(coords_1based: np.ndarray, tile: int) -> np.ndarray:
+    """Mirror of the library's "block_order = xslab<T>" key (csrc/abi.cu, ludwig_level_create): T x T tiles in (y, z) along a
+    Morton curve of the tiles, x-slices one after the other inside a tile."""
+    c = np.asarray(coords_1based, np.int64) - 1
+    t = np.uint64(tile)
+    bx, by, bz = (c[:, i].astype(np.uint64) for i in range(3))
+    tile_key = _spread3(by // t) | (_spread3(bz // t) << np.uint64(1))        # same ORDER as the library's 2-D interleave
+    return ((tile_key * np.uint64(int(c[:, 0].max()) + 2) + bx) * t + by % t) * t + bz % t
+
+
 def partition_starts(n_blocks: int, world: int) -> np.ndarray:
     return np.array([(n_blocks * r) // world for r in range(world + 1)], np.int32)
 
@@ -73,11 +86,25 @@ def _starts(coords_1based, world, level=None):
     return order, weighted_starts(block_costs(level)[order], world)
 
 
-def local_blocks(coords_1based: np.ndarray, rank: int, world: int, level=None) -> np.ndarray:
+def internal_order(coords_1based: np.ndarray, world: int, level=None, block_order: int = BLOCK_ORDER_DEFAULT) -> np.ndarray:
+    """Reference indices (0-based) in the library's internal order: the owners' ranges are cut on the Morton order, then every
+    range is walked in `block_order` (0: Morton, T: x-slab order with T x T tiles)."""
+    order, st = _starts(coords_1based, world, level)
+    if block_order <= 0:
+        return order
+    key = xslab_key(coords_1based, block_order)
+    out = order.copy()
+    for r in range(world):
+        seg = order[st[r]:st[r + 1]]
+        out[st[r]:st[r + 1]] = seg[np.argsort(key[seg], kind="stable")]
+    return out
+
+
+def local_blocks(coords_1based: np.ndarray, rank: int, world: int, level=None, block_order: int = BLOCK_ORDER_DEFAULT) -> np.ndarray:
     """0-based reference indices of the blocks rank `rank` owns, in internal order.  With `level` the cut is
     cost-weighted exactly as the library does it; without, equal block counts."""
-    order, st = _starts(coords_1based, world, level)
-    return order[st[rank]:st[rank + 1]]
+    _, st = _starts(coords_1based, world, level)
+    return internal_order(coords_1based, world, level, block_order)[st[rank]:st[rank + 1]]
 
 
 def owner_of_ref(coords_1based: np.ndarray, world: int, level=None) -> np.ndarray:

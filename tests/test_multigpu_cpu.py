@@ -88,7 +88,8 @@ def _worker(rank, world, tmp):
             dist.all_gather(allb, buf)
             cat = np.concatenate([b.numpy()[:int(s.item())] for b, s in zip(allb, sizes)])
             assert sorted(cat.tolist()) == list(range(lv.n_blocks))
-            assert np.array_equal(cat, partition.morton_order(lv.active_block_coords))
+            assert np.array_equal(cat, partition.internal_order(lv.active_block_coords, world, level=lv))
+            assert np.array_equal(np.sort(cat), np.sort(partition.morton_order(lv.active_block_coords)))
             # 2. halo symmetry: every remote block I pull from is owned by the peer, and the peer pulls from me too
             rem = partition.remote_neighbours(lv.neighbor_table, lv.active_block_coords, rank, world, level=lv)
             own = partition.owner_of_ref(lv.active_block_coords, world, level=lv)

@@ -44,9 +44,10 @@ for v in (args.variant or [""]):
     items = [x for x in v.split(",") if x]
     plan = "plan" in items
     opts = dict(x.split("=", 1) for x in items if x != "plan")
+    pov = {k[2:]: float(opts.pop(k)) for k in [k for k in opts if k.startswith("p.")]}   # "p.wall_model_active=0": ludwig_params override (experiments)
     fp = opts.pop("fp", args.fp_mode)                      # "fp=fast" / "fp=strict" inside a variant overrides --fp-mode
     rec = mg.run_case_strong(args.case, args.steps, lr, strict=fp == "strict", options=opts, plan=plan, ramp_steps=args.ramp,
-                             profile_steps=args.profile, log=log, dom=dom, all_ranks_levels=args.profile > 0, uniform_start=args.uniform_start)
+                             profile_steps=args.profile, log=log, dom=dom, all_ranks_levels=args.profile > 0, uniform_start=args.uniform_start, param_overrides=pov)
     rec["variant"] = v or "default"; rec["domain_build_s"] = build_s
     records.append(rec)
     if rank == 0:
