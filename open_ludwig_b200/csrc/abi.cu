@@ -506,13 +506,19 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
         const bool fork = ctx->use_side_streams && L.nb <= ctx->fork_max_blocks;
         // LUDWIG_FORK_FULL=1 (experiment for large levels, unmeasured): the domain-face blocks (128 registers, latency-bound,
         // 8 GLUPS on the bench box's inlet / outlet faces) run on a side stream UNDER the HBM-bound plain launch
-        const bool fork_full = !fork && ctx->fork_full && ctx->use_side_streams && L.n_full > 0 && L.n_plain > 0;
+        // face_persist: on a level whose plain launch dwarfs its domain-face class (the bench box: 3 % of the cells on the inlet / outlet
+        // planes) that class runs as a few persistent CTAs per SM launched BEFORE the plain kernel, so that it shares every SM with
+        // the HBM-bound plain launch for its whole run instead of trailing it as waves of latency-bound CTAs on an otherwise idle GPU
+        const bool persist_full = ctx->opt_face_persist > 0 && ctx->use_side_streams && L.n_full > 0 && (long long)L.n_plain > 15LL * L.n_full &&
+                                  (long long)L.n_full * 4 > 2LL * ctx->opt_face_persist * ctx->num_sms;
+        const bool fork_full = persist_full || (!fork && ctx->fork_full && ctx->use_side_streams && L.n_full > 0 && L.n_plain > 0);
         int used = 0;
         if (fork || fork_full) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         auto launch_on = [&](void (*fn)(const K1Args&, cudaStream_t), const int32_t* list, int n, bool main_stream, bool ghosts) -> int {
             if (n <= 0) return LUDWIG_OK;
             a.list = list; a.n_list = n;
-            if ((strict ? a.strict_stash : a.fast_variant) == 2) {   // persistent variant: its ticket counter (one per launch class)
+            a.persist_grid = (persist_full && fn == k_full) ? ctx->opt_face_persist * ctx->num_sms : 0;
+            if ((strict ? a.strict_stash : a.fast_variant) == 2 && !a.persist_grid) {   // persistent variant: its ticket counter (one per launch class)
                 const int cls = fn == k_plain ? 0 : fn == k_plain_g ? 1 : fn == k_feat ? 2 : 3;
                 const int grid = n < 2 * ctx->num_sms ? n : 2 * ctx->num_sms;
                 a.ticket = ctx->d_ticket + cls; a.ticket_base = ctx->ticket_base[cls];
@@ -930,6 +936,10 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         if (n != 32 && n != 64 && n != 128) return fail(ctx, LUDWIG_EINVAL, "l2_fetch: 32 | 64 | 128");
         CU(cudaSetDevice(ctx->device));
         CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)n));
+    } else if (k == "face_persist") {           // persistent CTAs per SM of the domain-face K1 class beside a much larger plain launch (0 = off)
+        const int n = atoi(value);
+        if (n < 0 || n > 8) return fail(ctx, LUDWIG_EINVAL, "face_persist: 0..8");
+        ctx->opt_face_persist = n;
     } else if (k == "strict_loop") {            // strict plain K1 (64-thread CTAs, strict_occupancy 5): z-plane pairs of a block one CTA works through
         const int n = atoi(value);
         if (n != 1 && n != 2 && n != 4) return fail(ctx, LUDWIG_EINVAL, "strict_loop: 1 | 2 | 4");

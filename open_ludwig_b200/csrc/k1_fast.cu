@@ -430,6 +430,20 @@ __global__ void __launch_bounds__(NT, MINB * (256 / NT)) k1_fast_kernel(const __
     fast_block<FULL, VELFB, MISS>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo);
 }
 
+// Persistent form for a small latency-bound class beside the plain launch (see k1_strict.cu / abi.cu, option face_persist).
+template <bool FULL, bool VELFB, bool MISS>
+__global__ void __launch_bounds__(64, 8) k1_fast_persist_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27], s_vo[27];
+    const int total = a.n_list * 4;
+    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+        const int b = a.list[e >> 2];
+        __syncthreads();
+        if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
+        __syncthreads();
+        fast_block<FULL, VELFB, MISS>(a, b, (int)threadIdx.x + (e & 3) * 64, a.f_in, s_fo, s_vo);
+    }
+}
+
 // TMA variant (option fast_kernel = tma): persistent CTAs, the block's own populations staged into shared memory by one
 // cp.async.bulk per block, double-buffered (see k1_strict.cu for the full description).  north_star asks for this form
 // ("block tiles plus halo staged into shared memory with TMA, or cp.async where measured faster"); the measured A/B against the
@@ -486,6 +500,9 @@ __global__ void __launch_bounds__(256, 2) k1_fast_tma_kernel(const __grid_consta
 template <bool FULL, bool VELFB, bool MISS, int MINB>
 void launch_fast(const K1Args& a, cudaStream_t s) {
     if (a.n_list <= 0) return;
+    if (a.persist_grid > 0) {
+        if constexpr (FULL && MISS) { k1f::k1_fast_persist_kernel<FULL, VELFB, MISS><<<a.persist_grid, 64, 0, s>>>(a); return; }
+    }
     if (a.fast_variant == 2) {
         static const cudaError_t once = cudaFuncSetAttribute(k1f::k1_fast_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)k1f::TILE_BYTES);
         static const cudaError_t once2 = cudaFuncSetAttribute(k1f::k1_fast_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

@@ -127,7 +127,7 @@ template <> struct FStore<true> {
 // One 8^3 block: 256 threads, two x-adjacent cells per thread.  fbase + s_fo[d] is neighbour block d's populations (fbase is
 // a.f_in, or — TMA variant — the same address with its global provenance hidden, because s_fo[13] then points into shared memory
 // and the loads must be generic).
-template <bool FULL, bool VELFB, bool MISS, bool STASH, bool WALE_FIRST>
+template <bool FULL, bool VELFB, bool MISS, bool STASH, bool WALE_FIRST, bool MISS_UNIFORM = true>
 __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const int t, const float* __restrict__ fbase, const long long* s_fo,
                                              const long long* s_vo, float2* s_stash) {
     const v2 NZ = V(a.negzero);
@@ -230,7 +230,7 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
             const int k0 = 1 + 3 * jyc + 9 * jzc, kp = k0 + 1, km = k0 - 1;
             const long long o0 = s_fo[dir + 1], oM = s_fo[dir + dM], oP = s_fo[dir + dP];
             v2 fm, f0, fp;
-            if (!MISS || (o0 != MISSING && oM != MISSING && oP != MISSING)) {
+            if (!MISS || (!MISS_UNIFORM && o0 != MISSING && oM != MISSING && oP != MISSING)) {
                 const float* __restrict__ P0 = fbase + o0 + (loc + x0);
                 const float* __restrict__ PM = fbase + oM + (loc + xM);
                 const float* __restrict__ PP = fbase + oP + (loc + xP);
@@ -238,7 +238,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
                 f0 = ld2(P0 + k0 * BS3);
                 fp = make_float2(PM[kp * BS3], P0[kp * BS3]);       // cx=+1: sources x0-1, x0
             } else {
-                // some source block is missing: domain face (rare path)
+                // some source block may be missing (domain face).  MISS_UNIFORM: every thread of a domain-face block takes this path, so
+                // that the lanes on the face (a quarter of every warp at an x face) do not make the warp execute both paths
                 if (o0 != MISSING) {
                     const float* __restrict__ P0 = fbase + o0 + (loc + x0);
                     f0 = ld2(P0 + k0 * BS3); fp.y = P0[kp * BS3]; fm.x = P0[km * BS3 + 1];
@@ -423,7 +424,24 @@ __global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT)
     if (LOOP == 1) prefetch_block_part<NT>(a, (int)(blockIdx.x / CTAS), (int)(blockIdx.x % CTAS));
 #pragma unroll 1
     for (int l = 0; l < LOOP; ++l)
-        strict_block<FULL, VELFB, MISS, STASH, (OCC > 4)>(a, b, (int)threadIdx.x + ((int)(blockIdx.x % CTAS) * LOOP + l) * NT, a.f_in, s_fo, s_vo, s_stash);
+        strict_block<FULL, VELFB, MISS, STASH, (OCC > 4 || FULL)>(a, b, (int)threadIdx.x + ((int)(blockIdx.x % CTAS) * LOOP + l) * NT, a.f_in, s_fo, s_vo, s_stash);
+}
+
+// Persistent form for a SMALL latency-bound class (the domain-face blocks of a large level): a few 64-thread CTAs per SM stride over
+// the (block, z-plane pair) parts of the list.  Launched BEFORE the plain kernel on a side stream they keep a fixed, small share of
+// every SM (2 CTAs = 16 K registers) for their whole run, the HBM-bound plain launch fills the rest, and the class costs no tail of
+// half-empty waves after it (abi.cu, option face_persist).  Same strict_block body, same bits.
+template <bool FULL, bool VELFB, bool MISS>
+__global__ void __launch_bounds__(64, 8) k1_strict_persist_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27], s_vo[27];
+    const int total = a.n_list * 4;
+    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+        const int b = a.list[e >> 2];
+        __syncthreads();                       // every warp is done with the previous part's tables
+        if (threadIdx.x < 27) neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo);
+        __syncthreads();
+        strict_block<FULL, VELFB, MISS, false, true>(a, b, (int)threadIdx.x + (e & 3) * 64, a.f_in, s_fo, s_vo, nullptr);
+    }
 }
 
 // ---- TMA variant: persistent CTAs, the block's own 27 x 2 KiB population planes (one contiguous 54 KiB run in the block-major
@@ -486,6 +504,9 @@ constexpr int STASH_BYTES = 27 * 256 * (int)sizeof(float2);   // 55 296
 template <bool FULL, bool VELFB, bool MISS>
 void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
     if (a.n_list <= 0) return;
+    if (a.persist_grid > 0) {
+        if constexpr (FULL && MISS) { k1s::k1_strict_persist_kernel<FULL, VELFB, MISS><<<a.persist_grid, 64, 0, s>>>(a); return; }
+    }
     if (variant == 2) {
         static const cudaError_t once = cudaFuncSetAttribute(k1s::k1_strict_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)k1s::TILE_BYTES);
         static const cudaError_t once2 = cudaFuncSetAttribute(k1s::k1_strict_tma_kernel<FULL, VELFB, MISS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
