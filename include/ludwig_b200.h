@@ -325,6 +325,10 @@ const char* ludwig_domain_last_error(void);
 /* domain_generation.jl:34-112  build_block_triangle_map + voxelize_blocks!: sets obstacle[b][z][y][x] = 1 for the shell cells */
 int ludwig_domain_voxelize(int device, const double* tris, int64_t n_tri, const double offset[3], double dx, const int32_t* coords, int32_t nb,
                            const int32_t* grid_ptr, int32_t dimx, int32_t dimy, int32_t dimz, uint8_t* obstacle /* in/out [nb][512] */);
+/* domain_generation.jl:114-203  perform_flood_fill!: every non-obstacle cell that cannot be reached from the non-obstacle cells of
+ * the min-bx blocks through 6-connected non-obstacle cells of existing blocks becomes solid; returns the number of filled cells */
+int64_t ludwig_domain_flood_fill(int device, const int32_t* coords, int32_t nb, const int32_t* grid_ptr, int32_t dimx, int32_t dimy, int32_t dimz,
+                                 uint8_t* obstacle /* in/out [nb][512] */);
 /* domain_generation.jl:371-431  compute_wall_distances!: neighbor_table as in ludwig_level_desc; returns the number of near-wall cells */
 int64_t ludwig_domain_wall_distance(int device, const int32_t* neighbor_table, int32_t nb, const uint8_t* obstacle, double dx,
                                     float* wall_dist /* in/out [nb][512], 100 = far */);

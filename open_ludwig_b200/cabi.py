@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "ludwig_multi_level_download", "ludwig_multi_init_equilibrium", "ludwig_multi_step_batch", "ludwig_multi_sync",
     "ludwig_multi_flow_stats", "ludwig_multi_forces_create", "ludwig_multi_compute_aerodynamics",
     "ludwig_multi_forces_download_maps", "ludwig_multi_device_bytes",
-    "ludwig_domain_last_error", "ludwig_domain_voxelize", "ludwig_domain_wall_distance", "ludwig_domain_qmap",
+    "ludwig_domain_last_error", "ludwig_domain_voxelize", "ludwig_domain_flood_fill", "ludwig_domain_wall_distance", "ludwig_domain_qmap",
     "ludwig_ctx_self_check", "ludwig_multi_self_check",
     "ludwig_graph_replays", "ludwig_init_uniform_flow", "ludwig_multi_init_uniform_flow",
     "ludwig_output_valid_blocks", "ludwig_output_export", "ludwig_multi_output_valid_blocks", "ludwig_multi_output_export",
@@ -153,6 +153,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "ludwig_multi_device_bytes": (C.c_int64, [vp]),
         "ludwig_domain_last_error": (C.c_char_p, []),
         "ludwig_domain_voxelize": (C.c_int, [C.c_int, vp, i64, vp, f64, vp, i32, vp, i32, i32, i32, vp]),
+        "ludwig_domain_flood_fill": (C.c_int64, [C.c_int, vp, i32, vp, i32, i32, i32, vp]),
         "ludwig_domain_wall_distance": (C.c_int64, [C.c_int, vp, i32, vp, f64, vp]),
         "ludwig_domain_qmap": (C.c_int64, [C.c_int, vp, i64, vp, f64, vp, i32, vp, i32, i32, i32, i64, vp, vp, vp]),
         "ludwig_ctx_self_check": (C.c_int64, [vp]),

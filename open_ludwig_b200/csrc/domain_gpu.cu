@@ -339,6 +339,88 @@ bool args_ok(const double* tris, int64_t n_tri, const double* off, double dx, co
     return true;
 }
 
+// ---- flood fill (domain_generation.jl:114-203 perform_flood_fill!) ------------------------------------------------------------
+// The reference walks a cell-by-cell FIFO from the non-obstacle cells of the min-bx blocks through 6-connected non-obstacle cells of
+// existing blocks and then marks every cell it never reached as solid.  The reachable set does not depend on the visiting order, so
+// the device computes the same set as a frontier of BLOCKS: one CTA per frontier block (a thread per cell) imports the visited
+// cells of the six facing neighbour layers, propagates inside the block in shared memory until nothing changes, and queues the
+// neighbours behind every face on which one of its cells became visited.  Visited flags only ever go 0 -> 1, a block is re-queued
+// whenever a neighbour face changes after (or while) it was processed, so concurrent CTAs need no ordering; the host launches
+// one kernel per frontier (its size is the only thing read back) until the frontier is empty.
+__device__ inline int ff_neighbour(const int32_t* __restrict__ grid, int dimx, int dimy, int dimz, int bx, int by, int bz) {
+    if (bx < 1 || bx > dimx || by < 1 || by > dimy || bz < 1 || bz > dimz) return -1;
+    return grid[((size_t)(bx - 1) * dimy + (by - 1)) * dimz + (bz - 1)] - 1;   // [bx][by][bz] C order, 1-based, 0 = none
+}
+__global__ void __launch_bounds__(512) flood_fill_kernel(const int32_t* __restrict__ coords, const int32_t* __restrict__ grid, int dimx, int dimy, int dimz,
+                                                         const uint8_t* __restrict__ obstacle, uint8_t* visited, const int32_t* __restrict__ frontier,
+                                                         int32_t* next, int32_t* next_count, int32_t* queued, int seed_min_x) {
+    __shared__ uint8_t s_v[512];
+    __shared__ int s_face[6];
+    const int b = frontier[blockIdx.x], c = threadIdx.x;
+    const int lx = c & 7, ly = (c >> 3) & 7, lz = c >> 6;
+    const int bx = coords[3 * b], by = coords[3 * b + 1], bz = coords[3 * b + 2];
+    if (c < 6) s_face[c] = 0;
+    // From now on a neighbour may queue this block again.  The reset comes BEFORE the reads of the neighbours' layers (fence +
+    // barrier): a neighbour that finds the flag still set has published its cells before this CTA looks at them, one that
+    // finds it cleared appends the block to the next frontier.  (A block can therefore enter a list twice per launch: the
+    // lists hold 2 nb entries.)  Other CTAs' flags are read past the non-coherent L1 (__ldcg).
+    if (c == 0) { atomicExch(&queued[b], 0); __threadfence(); }
+    __syncthreads();
+    const bool solid = obstacle[(size_t)b * 512 + c] != 0;
+    const bool v0 = __ldcg(visited + (size_t)b * 512 + c) != 0;
+    bool v = v0;
+    if (seed_min_x >= 0 && bx == seed_min_x && !solid) v = true;            // the reference's seeds (first launch only)
+    if (!solid && !v) {                                                    // import the facing layers of the six neighbours
+        const int ddx[6] = {1, -1, 0, 0, 0, 0}, ddy[6] = {0, 0, 1, -1, 0, 0}, ddz[6] = {0, 0, 0, 0, 1, -1};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int nx = lx + ddx[i], ny = ly + ddy[i], nz = lz + ddz[i];
+            if (nx >= 0 && nx < BS && ny >= 0 && ny < BS && nz >= 0 && nz < BS) continue;
+            const int t = ff_neighbour(grid, dimx, dimy, dimz, bx + ddx[i], by + ddy[i], bz + ddz[i]);
+            if (t >= 0 && __ldcg(visited + (size_t)t * 512 + ((nz + BS) % BS) * 64 + ((ny + BS) % BS) * 8 + ((nx + BS) % BS))) v = true;
+        }
+    }
+    // a block without obstacle cells is internally connected: reached anywhere, it is reached everywhere
+    if (!__syncthreads_or(solid) && __syncthreads_or(v)) v = true;
+    s_v[c] = v;
+    __syncthreads();
+    for (;;) {                                                              // in-block propagation to the fixed point
+        bool grow = false;
+        if (!solid && !v)
+            grow = (lx > 0 && s_v[c - 1]) || (lx < 7 && s_v[c + 1]) || (ly > 0 && s_v[c - 8]) || (ly < 7 && s_v[c + 8]) || (lz > 0 && s_v[c - 64]) || (lz < 7 && s_v[c + 64]);
+        __syncthreads();
+        if (grow) { v = true; s_v[c] = 1; }
+        if (!__syncthreads_or(grow)) break;
+    }
+    if (v && !v0) {
+        visited[(size_t)b * 512 + c] = 1;
+        if (lx == 7) s_face[0] = 1;
+        if (lx == 0) s_face[1] = 1;
+        if (ly == 7) s_face[2] = 1;
+        if (ly == 0) s_face[3] = 1;
+        if (lz == 7) s_face[4] = 1;
+        if (lz == 0) s_face[5] = 1;
+    }
+    __threadfence();
+    __syncthreads();
+    if (c < 6 && s_face[c]) {
+        const int ddx[6] = {1, -1, 0, 0, 0, 0}, ddy[6] = {0, 0, 1, -1, 0, 0}, ddz[6] = {0, 0, 0, 0, 1, -1};
+        const int t = ff_neighbour(grid, dimx, dimy, dimz, bx + ddx[c], by + ddy[c], bz + ddz[c]);
+        if (t >= 0 && atomicExch(&queued[t], 1) == 0) next[atomicAdd(next_count, 1)] = t;
+    }
+}
+__global__ void ff_seed_kernel(const int32_t* __restrict__ coords, int nb, int min_x, int32_t* frontier, int32_t* count, int32_t* queued) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb && coords[3 * b] == min_x) { queued[b] = 1; frontier[atomicAdd(count, 1)] = b; }
+}
+__global__ void __launch_bounds__(512) ff_finish_kernel(uint8_t* obstacle, const uint8_t* __restrict__ visited, unsigned long long* filled) {
+    const size_t i = (size_t)blockIdx.x * 512 + threadIdx.x;
+    const bool fill = !obstacle[i] && !visited[i];
+    if (fill) obstacle[i] = 1;
+    const int n = __syncthreads_count(fill);
+    if (threadIdx.x == 0 && n) atomicAdd(filled, (unsigned long long)n);
+}
+
 // the q-map is asked for twice (count, then fill): the device state of the counting call is kept for the fill call
 struct QmapState {
     TriMap M;
@@ -369,6 +451,44 @@ int ludwig_domain_voxelize(int device, const double* tris, int64_t n_tri, const 
     DCU(cudaGetLastError());
     DCU(cudaMemcpy(obstacle, obs.p, (size_t)nb * 512, cudaMemcpyDeviceToHost));
     return LUDWIG_OK;
+}
+
+int64_t ludwig_domain_flood_fill(int device, const int32_t* coords, int32_t nb, const int32_t* grid_ptr, int32_t dimx, int32_t dimy, int32_t dimz,
+                                 uint8_t* obstacle) {
+    if (!coords || nb <= 0 || !grid_ptr || dimx <= 0 || dimy <= 0 || dimz <= 0 || !obstacle) { g_err = "bad flood-fill arguments"; return LUDWIG_EINVAL; }
+    DCU(cudaSetDevice(device));
+    const size_t nc = (size_t)nb * 512, ngrid = (size_t)dimx * dimy * dimz;
+    DevBuf dco, dgrid, obs, vis, lists, counts, queued, filled;
+    DCU(dco.alloc((size_t)nb * 3 * sizeof(int32_t))); DCU(dgrid.alloc(ngrid * sizeof(int32_t))); DCU(obs.alloc(nc)); DCU(vis.alloc(nc));
+    DCU(lists.alloc((size_t)nb * 4 * sizeof(int32_t))); DCU(counts.alloc(2 * sizeof(int32_t))); DCU(queued.alloc((size_t)nb * sizeof(int32_t)));
+    DCU(filled.alloc(sizeof(unsigned long long)));
+    DCU(cudaMemcpy(dco.p, coords, (size_t)nb * 3 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    DCU(cudaMemcpy(dgrid.p, grid_ptr, ngrid * sizeof(int32_t), cudaMemcpyHostToDevice));
+    DCU(cudaMemcpy(obs.p, obstacle, nc, cudaMemcpyHostToDevice));
+    DCU(cudaMemset(vis.p, 0, nc)); DCU(cudaMemset(counts.p, 0, 2 * sizeof(int32_t))); DCU(cudaMemset(queued.p, 0, (size_t)nb * sizeof(int32_t)));
+    DCU(cudaMemset(filled.p, 0, sizeof(unsigned long long)));
+    int min_x = coords[0];
+    for (int i = 1; i < nb; ++i) min_x = std::min(min_x, coords[3 * i]);
+    int32_t* list[2] = {lists.as<int32_t>(), lists.as<int32_t>() + 2 * (size_t)nb};
+    int32_t* cnt = counts.as<int32_t>();
+    ff_seed_kernel<<<(nb + 255) / 256, 256>>>(dco.as<int32_t>(), nb, min_x, list[0], cnt, queued.as<int32_t>());
+    int32_t n = 0;
+    DCU(cudaMemcpy(&n, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int cur = 0, seed = min_x;
+    while (n > 0) {
+        DCU(cudaMemset(cnt + (cur ^ 1), 0, sizeof(int32_t)));
+        flood_fill_kernel<<<n, 512>>>(dco.as<int32_t>(), dgrid.as<int32_t>(), dimx, dimy, dimz, obs.as<uint8_t>(), vis.as<uint8_t>(), list[cur], list[cur ^ 1],
+                                      cnt + (cur ^ 1), queued.as<int32_t>(), seed);
+        seed = -1;
+        cur ^= 1;
+        DCU(cudaMemcpy(&n, cnt + cur, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    ff_finish_kernel<<<nb, 512>>>(obs.as<uint8_t>(), vis.as<uint8_t>(), filled.as<unsigned long long>());
+    DCU(cudaGetLastError());
+    unsigned long long f = 0;
+    DCU(cudaMemcpy(&f, filled.p, sizeof(f), cudaMemcpyDeviceToHost));
+    DCU(cudaMemcpy(obstacle, obs.p, nc, cudaMemcpyDeviceToHost));
+    return (int64_t)f;
 }
 
 int64_t ludwig_domain_wall_distance(int device, const int32_t* neighbor_table, int32_t nb, const uint8_t* obstacle, double dx, float* wall_dist) {

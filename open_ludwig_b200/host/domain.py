@@ -140,7 +140,7 @@ def build_neighbor_table(coords: np.ndarray, dims) -> tuple:
 
 def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, verbose: bool = False,
                             build_tri_map: bool = True, gpu_device: Optional[int] = None) -> Domain:
-    """domain.jl:20-280.  gpu_device: run the three brute-force phases (voxelisation, wall distance, q-map ray casting) on that
+    """domain.jl:20-280.  gpu_device: run voxelisation, flood fill, wall distance and q-map ray casting on that
     CUDA device through libludwig_b200.so's ludwig_domain_* entry points (N2) instead of the host threads; the tables are
     byte-identical either way (tests/test_domain_gpu.py)."""
     lib = host_lib()
@@ -226,7 +226,11 @@ def setup_multilevel_domain(cfg: CaseConfig, mesh: Optional[SolverMesh] = None, 
         else:
             timed("voxelize", lib.ludwig_host_voxelize, _p(tris), n_tri, _p(cflat), nb, dx, _p(off), _p(obstacle))
         shell = int(obstacle.sum())
-        filled = int(timed("flood_fill", lib.ludwig_host_flood_fill, _p(obstacle), _p(cflat), nb, _p(full_ptr_cm), dims[0], dims[1], dims[2]))
+        if glib is not None:
+            filled = int(gcheck(timed("flood_fill", glib.ludwig_domain_flood_fill, gpu_device, _p(cflat), nb, _p(grid_ptr), dims[0], dims[1], dims[2], _p(obstacle)),
+                                "ludwig_domain_flood_fill"))
+        else:
+            filled = int(timed("flood_fill", lib.ludwig_host_flood_fill, _p(obstacle), _p(cflat), nb, _p(full_ptr_cm), dims[0], dims[1], dims[2]))
         timed("sponge", lib.ludwig_host_sponge, _p(cflat), nb, dx, params.domain_size[0], params.domain_size[1], params.domain_size[2],
               float(cfg.sponge_thickness), int(cfg.symmetric), _p(sponge))
         near = 0

@@ -169,6 +169,10 @@ end
 voxelize!(device, tris, offset, dx, coords, grid_ptr, dims, obstacle::Array{UInt8,4}) =
     domain_check(ccall((:ludwig_domain_voxelize, LIB), Cint, (Cint, Ptr{Float64}, Int64, Ptr{Float64}, Float64, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{UInt8}),
                        device, tris, size(tris, 3), Float64[offset...], dx, coords, size(coords, 2), grid_ptr, dims[1], dims[2], dims[3], obstacle), "ludwig_domain_voxelize")
+# domain_generation.jl:114-203  perform_flood_fill!  (returns the number of filled voxels)
+flood_fill!(device, coords, grid_ptr, dims, obstacle::Array{UInt8,4}) =
+    domain_check(ccall((:ludwig_domain_flood_fill, LIB), Int64, (Cint, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{UInt8}),
+                       device, coords, size(coords, 2), grid_ptr, dims[1], dims[2], dims[3], obstacle), "ludwig_domain_flood_fill")
 # domain_generation.jl:371-431  compute_wall_distances!  (returns the number of near-wall cells)
 wall_distance!(device, neighbor_table::Matrix{Int32}, obstacle::Array{UInt8,4}, dx, wall_dist::Array{Float32,4}) =
     domain_check(ccall((:ludwig_domain_wall_distance, LIB), Int64, (Cint, Ptr{Int32}, Int32, Ptr{UInt8}, Float64, Ptr{Float32}),

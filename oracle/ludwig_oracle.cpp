@@ -967,6 +967,7 @@ int64_t ludwig_multi_self_check(ludwig_multi*) { return LUDWIG_ESTATE; }
 // N2 device entry points: the host restatement (open_ludwig_b200/host/domain_build.cpp) is their CPU counterpart, not this oracle
 const char* ludwig_domain_last_error(void) { return "not part of the CPU oracle"; }
 int ludwig_domain_voxelize(int, const double*, int64_t, const double*, double, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t, uint8_t*) { return LUDWIG_ESTATE; }
+int64_t ludwig_domain_flood_fill(int, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t, uint8_t*) { return LUDWIG_ESTATE; }
 int64_t ludwig_domain_wall_distance(int, const int32_t*, int32_t, const uint8_t*, double, float*) { return LUDWIG_ESTATE; }
 int64_t ludwig_domain_qmap(int, const double*, int64_t, const double*, double, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t, int64_t, int32_t*, double*, int32_t*) { return LUDWIG_ESTATE; }
 int ludwig_multi_init_uniform_flow(ludwig_multi*, float) { return LUDWIG_ESTATE; }
