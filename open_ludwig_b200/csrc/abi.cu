@@ -429,7 +429,7 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
 
     a.roff_f = L.d_roff_f[in]; a.roff_v = L.d_roff_v[in];
     if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: call ludwig_ipc_attach before stepping");
-    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.prefetch_distance = ctx->opt_prefetch_distance; a.strict_occ = ctx->opt_strict_occ; a.strict_loop = ctx->opt_strict_loop; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
+    a.negzero = -0.0f; a.wm_c166 = ctx->wm_c166; a.strict_stash = ctx->opt_strict_variant; a.fast_variant = ctx->opt_fast_variant; a.num_sms = ctx->num_sms; a.prefetch_distance = ctx->opt_prefetch_distance; a.strict_occ = ctx->opt_strict_occ; a.strict_loop = ctx->opt_strict_loop; a.strict_feat_occ = ctx->opt_strict_feat_occ; a.cta_threads = ctx->opt_cta_threads ? ctx->opt_cta_threads : (p.strict_fp ? 64 : 128);   // measured best (profiles/README.md)
     const bool strict = p.strict_fp != 0;
     if (strict && ctx->opt_strict_generic) {
         // cross-check path (option "strict_generic"): the one-thread-per-cell kernel with every branch of the reference
@@ -936,6 +936,10 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         if (n != 32 && n != 64 && n != 128) return fail(ctx, LUDWIG_EINVAL, "l2_fetch: 32 | 64 | 128");
         CU(cudaSetDevice(ctx->device));
         CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)n));
+    } else if (k == "strict_feature_occupancy") {   // strict feature / domain-face K1: resident warps per SM / 4 -> 128 / 96 registers
+        const int n = atoi(value);
+        if (n != 3 && n != 4 && n != 5) return fail(ctx, LUDWIG_EINVAL, "strict_feature_occupancy: 3 | 4 | 5");
+        ctx->opt_strict_feat_occ = n;
     } else if (k == "face_persist") {           // persistent CTAs per SM of the domain-face K1 class beside a much larger plain launch (0 = off)
         const int n = atoi(value);
         if (n < 0 || n > 8) return fail(ctx, LUDWIG_EINVAL, "face_persist: 0..8");

@@ -216,7 +216,13 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         }
 
     };
-    if (WALE_FIRST) { load_neighbour_velocities(); relaxation_rate(); }
+    // obstacle flags first: a thread whose two cells are solid only bounces its populations back (:154-166) and needs no relaxation rate
+    bool obsA = false, obsB = false;
+    if (FULL && (bflags & BF_OBSTACLE)) {
+        const uchar2 o = *reinterpret_cast<const uchar2*>(a.obstacle + (size_t)b * BS3 + c0);
+        obsA = o.x != 0; obsB = o.y != 0;
+    }
+    if (WALE_FIRST && !(FULL && obsA && obsB)) { load_neighbour_velocities(); relaxation_rate(); }
 
     // ---- pull-stream (:62-149) with the moment sums of :144-148 taken in k order as the values arrive; combo (jy,jz) yields the
     // three consecutive directions k0-1, k0, k0+1 and the combos are visited in ascending k0
@@ -267,11 +273,6 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         }
     }
 
-    bool obsA = false, obsB = false;
-    if (FULL && (bflags & BF_OBSTACLE)) {
-        const uchar2 o = *reinterpret_cast<const uchar2*>(a.obstacle + (size_t)b * BS3 + c0);
-        obsA = o.x != 0; obsB = o.y != 0;
-    }
     float* __restrict__ fout = a.f_out + (size_t)b * (Q * BS3) + c0;
     float* __restrict__ vout = a.vel_out + (size_t)b * (3 * BS3) + c0;
     float* __restrict__ rout = a.rho_out + (size_t)b * BS3 + c0;
@@ -526,6 +527,10 @@ void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
             if (a.strict_loop == 2 && a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5, 2><<<2 * a.n_list, 64, 0, s>>>(a); return; }
             if (a.strict_occ == 6) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 6><<<4 * a.n_list, 64, 0, s>>>(a); return; }
             if (a.strict_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5><<<4 * a.n_list, 64, 0, s>>>(a); return; }
+        }
+        if constexpr (FULL) {
+            if (a.strict_feat_occ == 5) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 5><<<4 * a.n_list, 64, 0, s>>>(a); return; }
+            if (a.strict_feat_occ == 3) { k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 3><<<4 * a.n_list, 64, 0, s>>>(a); return; }
         }
         k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 64, 4><<<4 * a.n_list, 64, 0, s>>>(a);
     } else k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 256><<<a.n_list, 256, 0, s>>>(a);

@@ -208,6 +208,7 @@ struct ludwig_ctx {
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
     int opt_strict_occ = 5;                  // "strict_occupancy" = 4 | 5 | 6 (5: measured best, profiles/README.md)
     int opt_face_persist = 0;                // "face_persist": persistent CTAs per SM of the domain-face K1 class beside the plain launch (0 = off: measured slower, profiles/README.md)
+    int opt_strict_feat_occ = 4;             // "strict_feature_occupancy" = 4 | 5 (128 / 96 registers for the feature and domain-face classes)
     int opt_strict_loop = 1;                 // "strict_loop" = 1 | 2 | 4: z-plane pairs of a block one 64-thread CTA works through
     int opt_block_order = 12;                // "block_order": 0 Morton, T > 0: x-slab order with T x T tiles in (y, z) (12: measured, profiles/README.md)
     int opt_prefetch_distance = 0;           // "prefetch_distance" = blocks
@@ -290,6 +291,7 @@ struct K1Args {
     int num_sms;
     int strict_occ;         // strict K1 at 64 threads per CTA: resident warps per SM / 4 (4, 5 or 6)
     int persist_grid;       // > 0: this launch runs as that many persistent CTAs striding over the list's parts (see abi.cu, "face_persist")
+    int strict_feat_occ;    // strict feature / domain-face K1 at 64 threads per CTA: resident warps per SM / 4 (4 or 5)
     int strict_loop;        // strict K1 at 64 threads per CTA: z-plane pairs of a block per CTA (1, 2 or 4)
     int prefetch_distance;  // blocks ahead whose lines a CTA prefetches into L2 (0 = off)
     int cta_threads;        // 256 (one CTA per block), 128 or 64 (a CTA takes 4 / 2 z-planes of a block)

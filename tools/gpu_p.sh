@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_abi_and_oracle_units.py tests/test_k1_single_level_gpu.py tests/test_large_sizes_gpu.py tests/test_virtual_ranks_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -3
-timeout 900 python tools/ab_box.py --nb 64 --steps 40 --repeat 2 "base|strict|" "base|fast|" > gpurun_out/p_ab.log 2>&1; echo "ab exit $?" >> gpurun_out/p_ab.log
-grep -E "^AB|exit|Error" gpurun_out/p_ab.log | cut -c1-360
+timeout 600 python -m pytest tests/test_k1_features_gpu.py tests/test_bunny_small_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -3
+timeout 1200 python tools/run_case_mg.py bunny 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_bunny.log 2>&1
+grep -E "RESULT|exit|Error" gpurun_out/p_bunny.log | cut -c1-200
+timeout 1200 python tools/run_case_mg.py wing5 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_wing.log 2>&1
+grep -E "RESULT|exit|Error" gpurun_out/p_wing.log | cut -c1-200
