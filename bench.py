@@ -11,7 +11,7 @@ ms per coarse step, true MLUPS, Cd / Cl after the (shortened) ramp and rank 0's 
 A "step" is one coarse time step of the whole hot path (K1 on every block of the level; the synthetic box has
 no Bouzidi cells or refinement) over a 512^3 single-level box with open x faces and periodic y/z — the
 configuration BASELINE.json's metric is quoted on.  Multi-GPU (N>1): one process per GPU, weak scaling: the box grows
-to (512 N) x 512 x 512 cells, the library partitions its blocks along a Morton curve and K1 pulls the halo blocks of
+to (512 N) x 512 x 512 cells, the library cuts the Morton curve of its blocks into N ranges and K1 pulls the halo blocks of
 other GPUs through NVLink peer mappings.  See DESIGN.md "Multi-GPU".
 
 Prints ONE JSON line (rank 0).
@@ -33,15 +33,15 @@ import numpy as np  # noqa: E402
 
 BYTES_PER_LU = 216  # 27 x 4 B read + 27 x 4 B write
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per lattice update, from ncu captures under profiles/
-# (captured at the benched size, 512^3: 253 952 plain blocks per launch)
-TRAFFIC_BYTES_PER_LU = {"fast": (17274605312 + 16087857920) / (253952 * 512), "strict": (17255133696 + 16074985984) / (253952 * 512)}
-TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<plain> at 512^3 (profiles/r2a_dram_traffic_k1_512cube_fast.csv) per LU x LU per launch",
-                  "strict": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_strict_kernel<plain> at 512^3 (profiles/r2a_dram_traffic_k1_512cube_strict.csv) per LU x LU per launch"}
+# (captured at the benched size, 512^3: 253 952 plain blocks per launch, the library's default block order)
+TRAFFIC_BYTES_PER_LU = {"fast": (16460977664 + 16092003584) / (253952 * 512), "strict": (16460049152 + 16093137152) / (253952 * 512)}
+TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<plain> at 512^3 (profiles/r2q_dram_traffic_fast_plain_l2fetch_and_xslab_512cube.csv, launch 20: block_order xslab12) per LU x LU per launch",
+                  "strict": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_strict_kernel<plain> at 512^3 (profiles/r2w_dram_traffic_k1_512cube_strict_xslab12.csv) per LU x LU per launch"}
 DEFAULT_FP_MODE = "strict"          # the mode whose results are bit-identical to the reference restatement; fast is reported beside it
 DEFAULT_STRONG_PARTITION = "rcb_yz"
 # 1-GPU time per coarse step of the strong-scaling case measured by this file's own strong record (profiles/), for the
 # efficiency shown at N > 1: (case, fp_mode) -> ms
-T1_MS_COMMITTED = {("bunny_fine", "fast"): 495.6, ("bunny_fine", "strict"): 588.0}   # profiles/r2e_bunny_fine_1gpu_*.log
+T1_MS_COMMITTED = {("bunny_fine", "fast"): 495.6, ("bunny_fine", "strict"): 575.0}   # profiles/r2e_bunny_fine_1gpu_fast.log, r2s_bench_default_1gpu_xslab12.json (this file's strong record at N = 1)
 
 
 def measured_peaks():
