@@ -119,6 +119,14 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   prefetch_distance = N             K1 CTAs prefetch the lines of the block N list entries ahead into L2 (0 = off)
  *   fast_kernel = direct | tma        fast K1 variant: direct loads, or the persistent TMA-staged form (identical bits either way)
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
+ *   block_order = morton | xslab<T>   internal block order within a rank (before the first level): Morton curve, or T x T tiles in (y, z)
+ *                                     with the x-slices of a tile one after the other (default xslab12: x-face halo sectors stay in L2)
+ *   merge_face = auto | 0 | 1         plain and domain-face K1 classes in ONE launch on levels without an interface pre-pass
+ *                                     (auto: fast mode only - measured)
+ *   face_persist = N                  domain-face K1 class as N persistent CTAs per SM beside the plain launch (0 = off: measured slower)
+ *   strict_loop = 1 | 2 | 4           z-plane pairs of a block one 64-thread strict K1 CTA works through (1: measured best)
+ *   strict_feature_occupancy = 3 | 4 | 5   register budget of the strict feature / domain-face classes (166 / 128 / 96; 4: measured best)
+ *   l2_fetch = 32 | 64 | 128          cudaLimitMaxL2FetchGranularity of the device (a hint; measured: no effect on DRAM bytes)
  *   partition = morton | rcb | rcb_yz multi-GPU block partition (before the first level)
  *   halo_mirror = 0 | 1               packed halo exchange into local mirrors instead of in-kernel NVLink pulls (before the first level)
  *   remote_order = morton | first | last | interleave   place of the blocks that pull from a peer in the plain launch

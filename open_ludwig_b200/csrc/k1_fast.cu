@@ -430,6 +430,18 @@ __global__ void __launch_bounds__(NT, MINB * (256 / NT)) k1_fast_kernel(const __
     fast_block<FULL, VELFB, MISS>(a, b, (int)threadIdx.x + (int)(blockIdx.x % PARTS) * NT, a.f_in, s_fo, s_vo);
 }
 
+// Merged launch of the plain and the domain-face class (see k1_strict.cu / abi.cu, option merge_face); register budget of the plain kernel.
+__global__ void __launch_bounds__(128, 6) k1_fast_mixed_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27], s_vo[27];
+    const int b = a.list[blockIdx.x >> 1];
+    bool miss = false;
+    if (threadIdx.x < 27) { neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo); miss = s_fo[threadIdx.x] == MISSING; }
+    const bool face = __syncthreads_or(miss) != 0;
+    const int t = (int)threadIdx.x + (int)(blockIdx.x & 1) * 128;
+    if (face) fast_block<true, true, true>(a, b, t, a.f_in, s_fo, s_vo);
+    else fast_block<false, false, false>(a, b, t, a.f_in, s_fo, s_vo);
+}
+
 // Persistent form for a small latency-bound class beside the plain launch (see k1_strict.cu / abi.cu, option face_persist).
 template <bool FULL, bool VELFB, bool MISS>
 __global__ void __launch_bounds__(64, 8) k1_fast_persist_kernel(const __grid_constant__ K1Args a) {
@@ -514,6 +526,7 @@ void launch_fast(const K1Args& a, cudaStream_t s) {
     else k1f::k1_fast_kernel<FULL, VELFB, MISS, MINB, 256><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1_plain(const K1Args& a, cudaStream_t s) { launch_fast<false, false, false, 3>(a, s); }
+void launch_k1_mixed(const K1Args& a, cudaStream_t s) { if (a.n_list > 0) k1f::k1_fast_mixed_kernel<<<2 * a.n_list, 128, 0, s>>>(a); }
 void launch_k1_plain_ghost(const K1Args& a, cudaStream_t s) { launch_fast<false, true, false, 3>(a, s); }
 // feature blocks: 80 registers / 3 CTAs per SM measured +12 % over 127 registers / 2 CTAs on Wing_5_deg (A/B on one box)
 void launch_k1_feat(const K1Args& a, cudaStream_t s) { launch_fast<true, true, false, 3>(a, s); }

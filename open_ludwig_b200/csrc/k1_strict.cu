@@ -428,6 +428,25 @@ __global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT)
         strict_block<FULL, VELFB, MISS, STASH, (OCC > 4 || FULL)>(a, b, (int)threadIdx.x + ((int)(blockIdx.x % CTAS) * LOOP + l) * NT, a.f_in, s_fo, s_vo, s_stash);
 }
 
+// Merged launch of the plain and the domain-face class (abi.cu, option merge_face): one grid over both lists in spatial order, a
+// CTA-uniform branch picks the body.  The face blocks (3 % of the bench box) then run BETWEEN plain CTAs on the same SMs instead of as
+// 28 half-empty waves of latency-bound CTAs after the plain launch; the register budget is the plain kernel's (96), the face body
+// spills into it, which only the face CTAs pay.  Same bodies, same bits.
+// (out of line: ptxas then allocates the plain body's registers exactly as in the plain kernel; the face body keeps its own frame)
+__device__ __noinline__ void strict_face_part(const K1Args& a, int b, int t, const long long* s_fo, const long long* s_vo) {
+    strict_block<true, true, true, false, true>(a, b, t, a.f_in, s_fo, s_vo, nullptr);
+}
+__global__ void __launch_bounds__(64, 10) k1_strict_mixed_kernel(const __grid_constant__ K1Args a) {
+    __shared__ long long s_fo[27], s_vo[27];
+    const int b = a.list[blockIdx.x >> 2];
+    bool miss = false;
+    if (threadIdx.x < 27) { neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo); miss = s_fo[threadIdx.x] == MISSING; }
+    const bool face = __syncthreads_or(miss) != 0;
+    const int t = (int)threadIdx.x + (int)(blockIdx.x & 3) * 64;
+    if (face) strict_face_part(a, b, t, s_fo, s_vo);
+    else strict_block<false, false, false, false, true>(a, b, t, a.f_in, s_fo, s_vo, nullptr);
+}
+
 // Persistent form for a SMALL latency-bound class (the domain-face blocks of a large level): a few 64-thread CTAs per SM stride over
 // the (block, z-plane pair) parts of the list.  Launched BEFORE the plain kernel on a side stream they keep a fixed, small share of
 // every SM (2 CTAs = 16 K registers) for their whole run, the HBM-bound plain launch fills the rest, and the class costs no tail of
@@ -536,6 +555,7 @@ void launch_strict(const K1Args& a, int variant, cudaStream_t s) {
     } else k1s::k1_strict_kernel<FULL, VELFB, MISS, false, 256><<<a.n_list, 256, 0, s>>>(a);
 }
 void launch_k1s_plain(const K1Args& a, cudaStream_t s) { launch_strict<false, false, false>(a, a.strict_stash, s); }
+void launch_k1s_mixed(const K1Args& a, cudaStream_t s) { if (a.n_list > 0) k1s::k1_strict_mixed_kernel<<<4 * a.n_list, 64, 0, s>>>(a); }
 void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s) { launch_strict<false, true, false>(a, a.strict_stash, s); }
 void launch_k1s_feat(const K1Args& a, cudaStream_t s) { launch_strict<true, true, false>(a, a.strict_stash, s); }
 void launch_k1s_full(const K1Args& a, cudaStream_t s) { launch_strict<true, true, true>(a, a.strict_stash, s); }

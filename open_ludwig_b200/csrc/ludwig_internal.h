@@ -135,6 +135,7 @@ struct Level {
     int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
     int32_t* d_list_feat = nullptr;      // all 26 neighbours present, some feature flag
     int32_t* d_list_full = nullptr;      // some neighbour missing (domain face)
+    int32_t* d_list_plain_full = nullptr; // plain + full in internal (spatial) order: the merged launch (option merge_face)
     int32_t* d_list_nonplain = nullptr;  // plain_g + feat + full (strict mode: the generic strict kernel)
     int n_plain = 0, n_plain_g = 0, n_feat = 0, n_full = 0;
 
@@ -207,6 +208,7 @@ struct ludwig_ctx {
     int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
     int opt_strict_occ = 5;                  // "strict_occupancy" = 4 | 5 | 6 (5: measured best, profiles/README.md)
+    int opt_merge_face = -1;                 // "merge_face": plain and domain-face K1 classes in one launch on levels without an interface pre-pass: auto (fast mode only: measured) | 0 | 1
     int opt_face_persist = 0;                // "face_persist": persistent CTAs per SM of the domain-face K1 class beside the plain launch (0 = off: measured slower, profiles/README.md)
     int opt_strict_feat_occ = 4;             // "strict_feature_occupancy" = 4 | 5 (128 / 96 registers for the feature and domain-face classes)
     int opt_strict_loop = 1;                 // "strict_loop" = 1 | 2 | 4: z-plane pairs of a block one 64-thread CTA works through
@@ -333,6 +335,8 @@ void launch_ghost_interp(const GhostArgs& g, bool block_variant, cudaStream_t s)
 // k1_strict.cu (-fmad=false): the same four classes and the pre-pass in the reference's operation order (bit-exact
 // against the CPU oracle), packed FP32x2
 void launch_k1s_plain(const K1Args& a, cudaStream_t s);
+void launch_k1s_mixed(const K1Args& a, cudaStream_t s);   // plain + domain-face blocks in one grid (option merge_face)
+void launch_k1_mixed(const K1Args& a, cudaStream_t s);
 void launch_k1s_plain_ghost(const K1Args& a, cudaStream_t s);
 void launch_k1s_feat(const K1Args& a, cudaStream_t s);
 void launch_k1s_full(const K1Args& a, cudaStream_t s);

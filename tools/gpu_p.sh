@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_k1_features_gpu.py tests/test_bunny_small_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -3
-timeout 1200 python tools/run_case_mg.py bunny 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_bunny.log 2>&1
-grep -E "RESULT|exit|Error" gpurun_out/p_bunny.log | cut -c1-200
-timeout 1200 python tools/run_case_mg.py wing5 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_wing.log 2>&1
-grep -E "RESULT|exit|Error" gpurun_out/p_wing.log | cut -c1-200
+timeout 300 python tools/check_options.py "merge_face=0" > gpurun_out/p_check.log 2>&1; echo "check exit $?" >> gpurun_out/p_check.log
+grep -E "CHECK|exit|Error" gpurun_out/p_check.log | cut -c1-300
+timeout 900 python tools/ab_box.py --nb 64 --steps 40 --repeat 3 "merge1|strict|merge_face=1" "merge0|strict|merge_face=0" "merge1|fast|merge_face=1" "merge0|fast|merge_face=0" > gpurun_out/p_ab.log 2>&1; echo "ab exit $?" >> gpurun_out/p_ab.log
+grep -E "^AB|exit|Error" gpurun_out/p_ab.log | cut -c1-330
