@@ -32,11 +32,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BYTES_PER_LU = 216  # 27 x 4 B read + 27 x 4 B write
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per lattice update, from ncu captures under profiles/
-# (captured at the benched size, 512^3: 253 952 plain blocks per launch, the library's default block order)
-TRAFFIC_BYTES_PER_LU = {"fast": (16460977664 + 16092003584) / (253952 * 512), "strict": (16460049152 + 16093137152) / (253952 * 512)}
-TRAFFIC_SOURCE = {"fast": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_fast_kernel<plain> at 512^3 (profiles/r2q_dram_traffic_fast_plain_l2fetch_and_xslab_512cube.csv, launch 20: block_order xslab12) per LU x LU per launch",
-                  "strict": "ncu dram__bytes_read.sum + dram__bytes_write.sum of k1_strict_kernel<plain> at 512^3 (profiles/r2w_dram_traffic_k1_512cube_strict_xslab12.csv) per LU x LU per launch"}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per lattice update, from the ncu capture under profiles/
+# (at the benched size, 512^3; since the domain-face blocks ride in the plain launch one launch covers all 262 144 blocks)
+TRAFFIC_BYTES_PER_LU = {"fast": (16863751680 + 17040579328) / (262144 * 512), "strict": (16778522112 + 16629274880) / (262144 * 512)}
+TRAFFIC_SOURCE = {m: f"ncu dram__bytes_read.sum + dram__bytes_write.sum of {k} at 512^3 (profiles/r2y_dram_traffic_k1_512cube_merged.csv) per LU x LU per launch"
+                  for m, k in (("fast", "k1_fast_mixed_kernel"), ("strict", "k1_strict_mixed_kernel"))}
 DEFAULT_FP_MODE = "strict"          # the mode whose results are bit-identical to the reference restatement; fast is reported beside it
 DEFAULT_STRONG_PARTITION = "rcb_yz"
 # 1-GPU time per coarse step of the strong-scaling case measured by this file's own strong record (profiles/), for the
@@ -319,7 +319,8 @@ def run_ours(args, rank, local_rank, world):
         k_avg_ms = k_ms / max(k_launches, 1)
         achieved = (k_cells / max(k_launches, 1)) * BYTES_PER_LU / (k_avg_ms * 1e-3) / 1e9 if k_launches else None
         stats_parts = min(4096, max(1, min(148 * 8, (cells_per_rank + 255) // 256)))
-        kname = "k1_strict_kernel<plain>" if strict else "k1_fast_kernel<PLAIN>"
+        # (single GPU: the x-only inlet / outlet blocks ride in the plain launch, csrc/abi.cu "merge_face")
+        kname = "k1_strict_mixed_kernel (plain + inlet / outlet blocks)" if strict else "k1_fast_mixed_kernel (plain + domain-face blocks)"
         line = {
             "metric": "MLUPS (D3Q27 FP32)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",

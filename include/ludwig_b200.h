@@ -121,8 +121,8 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *   strict_generic = 0 | 1            strict_fp through the one-thread-per-cell cross-check kernel (single GPU)
  *   block_order = morton | xslab<T>   internal block order within a rank (before the first level): Morton curve, or T x T tiles in (y, z)
  *                                     with the x-slices of a tile one after the other (default xslab12: x-face halo sectors stay in L2)
- *   merge_face = auto | 0 | 1         plain and domain-face K1 classes in ONE launch on levels without an interface pre-pass
- *                                     (auto: fast mode only - measured)
+ *   merge_face = 0 | 1                domain-face blocks ride in the plain K1 launch on levels without an interface pre-pass (default 1;
+ *                                     strict mode: only the blocks that lack nothing but what lies beyond the inlet / outlet plane)
  *   face_persist = N                  domain-face K1 class as N persistent CTAs per SM beside the plain launch (0 = off: measured slower)
  *   strict_loop = 1 | 2 | 4           z-plane pairs of a block one 64-thread strict K1 CTA works through (1: measured best)
  *   strict_feature_occupancy = 3 | 4 | 5   register budget of the strict feature / domain-face classes (166 / 128 / 96; 4: measured best)

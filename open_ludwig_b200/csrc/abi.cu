@@ -70,7 +70,7 @@ inline uint64_t morton2(uint32_t x, uint32_t y) {   // 16 bits each
 
 void free_level(Level* L) {
     if (!L) return;
-    void* ptrs[] = {L->d_pack, L->d_unpack, L->d_export, L->d_fmirror, L->d_vmirror, L->d_moff_f[0], L->d_moff_f[1], L->d_moff_v[0], L->d_moff_v[1], L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_gstart, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain, L->d_list_plain_full,
+    void* ptrs[] = {L->d_pack, L->d_unpack, L->d_export, L->d_fmirror, L->d_vmirror, L->d_moff_f[0], L->d_moff_f[1], L->d_moff_v[0], L->d_moff_v[1], L->d_roff_f[0], L->d_roff_f[1], L->d_roff_v[0], L->d_roff_v[1], L->d_link_cell, L->d_link_k, L->d_link_q, L->d_link_tmp, L->d_gstart, L->d_int2ref, L->d_nbr, L->d_bcoord, L->d_ptr, L->d_nbr_fast, L->d_gcoord, L->d_fghost, L->d_gcell, L->d_gmask, L->d_gcells8, L->d_list_plain, L->d_list_plain_g, L->d_list_feat, L->d_list_full, L->d_list_nonplain, L->d_list_plain_full, L->d_list_plain_xface, L->d_list_full_rest,
                     L->d_obstacle, L->d_sponge, L->d_wall_dist, L->d_f[0], L->d_f[1], L->d_vel[0], L->d_vel[1], L->d_rho[0],
                     L->d_rho[1], L->d_f_old, L->d_vel_old, L->d_rho_old};
     for (void* p : ptrs)
@@ -161,10 +161,10 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     if (L.fast_ready && L.fast_dom[0] == p.domain_nx && L.fast_dom[1] == p.domain_ny && L.fast_dom[2] == p.domain_nz) return LUDWIG_OK;
     CU(cudaStreamSynchronize(ctx->stream));
     for (void* q : {(void*)L.d_gstart, (void*)L.d_nbr_fast, (void*)L.d_gcoord, (void*)L.d_fghost, (void*)L.d_gcell, (void*)L.d_gmask, (void*)L.d_gcells8, (void*)L.d_list_plain,
-                    (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full, (void*)L.d_list_nonplain, (void*)L.d_list_plain_full})
+                    (void*)L.d_list_plain_g, (void*)L.d_list_feat, (void*)L.d_list_full, (void*)L.d_list_nonplain, (void*)L.d_list_plain_full, (void*)L.d_list_plain_xface, (void*)L.d_list_full_rest})
         if (q) cudaFree(q);
     L.d_gstart = nullptr; L.d_nbr_fast = nullptr; L.d_gcoord = nullptr; L.d_fghost = nullptr; L.d_gcell = nullptr; L.d_gmask = nullptr; L.d_gcells8 = nullptr;
-    L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = L.d_list_nonplain = L.d_list_plain_full = nullptr;
+    L.d_list_plain = L.d_list_plain_g = L.d_list_feat = L.d_list_full = L.d_list_nonplain = L.d_list_plain_full = L.d_list_plain_xface = L.d_list_full_rest = nullptr;
     const int nb = L.nb;
     const int scale = 1 << (L.level_id - 1);
     const int ext[3] = {p.domain_nx * scale / BS, p.domain_ny * scale / BS, p.domain_nz * scale / BS};   // blocks per axis
@@ -218,17 +218,23 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         gstart.push_back((int32_t)gcell.size());
     }
     // K1 work lists
-    std::vector<int32_t> lp, lg, le, lf;
+    std::vector<int32_t> lp, lg, le, lf, lx, lfr;   // lx: x-only face blocks (subset of lf), lfr = lf without them
+    const int nxg_level = p.domain_nx << (L.level_id - 1);
     for (int b = 0; b < nb; ++b) {
-        bool all = true, ghost = false;
+        bool all = true, ghost = false, xonly = true;
+        const int bx = L.h_bcoord[(size_t)b * 4];
         for (int d = 0; d < 27; ++d) {
             int v = nbrf[(size_t)b * 27 + d];
-            if (v < 0) all = false; else if (v >= nb && v < REMOTE_BASE) ghost = true;
+            if (v < 0) {
+                all = false;
+                const int dx = d % 3 - 1;   // missing only beyond the inlet plane (block at x = 0) or the outlet plane (block ends at nx)
+                if (dx == 0 || (dx < 0 && bx != 0) || (dx > 0 && (bx + 1) * BS != nxg_level)) xonly = false;
+            } else if (v >= nb && v < REMOTE_BASE) ghost = true;
         }
         const uint32_t feat = (uint32_t)L.h_bcoord[(size_t)b * 4 + 3] & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
         if (all && !feat) (ghost ? lg : lp).push_back(b);
         else if (all) le.push_back(b);
-        else lf.push_back(b);
+        else { lf.push_back(b); (xonly && !feat && !ghost ? lx : lfr).push_back(b); }
     }
     // plain blocks without a remote neighbour first: they can run while the halo import is still in flight
     auto has_remote = [&](int32_t b) {
@@ -281,7 +287,12 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
     std::vector<int32_t> lpf(lp);
     lpf.insert(lpf.end(), lf.begin(), lf.end());
     std::sort(lpf.begin(), lpf.end());   // internal = spatial order
-    struct { std::vector<int32_t>* v; int32_t** d; } lists[6] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}, {&ln, &L.d_list_nonplain}, {&lpf, &L.d_list_plain_full}};
+    std::vector<int32_t> lpx(lp);
+    lpx.insert(lpx.end(), lx.begin(), lx.end());
+    std::sort(lpx.begin(), lpx.end());
+    L.n_xface = (int)lx.size();
+    struct { std::vector<int32_t>* v; int32_t** d; } lists[8] = {{&lp, &L.d_list_plain}, {&lg, &L.d_list_plain_g}, {&le, &L.d_list_feat}, {&lf, &L.d_list_full}, {&ln, &L.d_list_nonplain}, {&lpf, &L.d_list_plain_full},
+                                                                 {&lpx, &L.d_list_plain_xface}, {&lfr, &L.d_list_full_rest}};
     for (auto& l : lists) {
         CU(dalloc(ctx, l.d, l.v->size()));
         if (!l.v->empty()) CU(memcpy_sync(ctx->stream, *l.d, l.v->data(), l.v->size() * 4, cudaMemcpyHostToDevice));
@@ -542,22 +553,27 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
             ctx->launches += 1;
             return LUDWIG_OK;
         };
-        // merge_face: on a level without an interface pre-pass (level 1, the bench box) the domain-face blocks ride in the plain launch
+        // merge_face: on a level without an interface pre-pass (level 1, the bench box) domain-face blocks ride in the plain launch
         // (a CTA-uniform branch picks the body) instead of trailing it as waves of latency-bound CTAs on an otherwise idle GPU.
-        // Measured on the 512^3 box: fast mode -2...5 % per step; strict mode +2.5 % (its face CTAs live ~4x longer under the plain
-        // CTAs' memory traffic and hold a third of the CTA slots meanwhile), hence auto = fast mode only.
-        const bool merged = (ctx->opt_merge_face == 1 || (ctx->opt_merge_face < 0 && !strict)) && !wait_halo && !fork_full && L.n_gcell == 0 && L.n_full > 0 && L.n_plain > 0 &&
+        // Fast mode merges the whole class.  Strict mode merges only the X-ONLY face blocks (nothing missing but beyond the inlet /
+        // outlet plane, no feature: k1_strict.cu), whose body is as lean as the plain one, and keeps a separate launch for the rest:
+        // with the general strict face body in the mix the step got 2.5 % SLOWER (its CTAs live ~4x longer under the plain CTAs'
+        // memory traffic and hold a third of the CTA slots meanwhile).  Numbers: profiles/README.md.
+        const int n_face_merged = strict ? L.n_xface : L.n_full;
+        const bool merged = ctx->opt_merge_face != 0 && !wait_halo && !fork_full && L.n_gcell == 0 && n_face_merged > 0 && L.n_plain > 0 &&
                             (strict ? a.strict_stash == 0 && a.cta_threads == 64 && a.strict_occ == 5 && a.strict_loop == 1 : a.fast_variant == 0 && a.cta_threads == 128);
+        const int32_t* list_full = merged && strict ? L.d_list_full_rest : L.d_list_full;
+        const int n_full_left = merged ? L.n_full - n_face_merged : L.n_full;
         if (fork_full && (rc = launch_on(k_full, L.d_list_full, L.n_full, false, true))) return rc;
         if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
         if (merged) {
-            if ((rc = launch_on(strict ? launch_k1s_mixed : launch_k1_mixed, L.d_list_plain_full, L.n_plain + L.n_full, true, false))) return rc;
+            if ((rc = launch_on(strict ? launch_k1s_mixed : launch_k1_mixed, strict ? L.d_list_plain_xface : L.d_list_plain_full, L.n_plain + n_face_merged, true, false))) return rc;
         } else if (wait_halo) {
             if ((rc = launch_on(k_plain, L.d_list_plain, L.n_plain_int, true, false))) return rc;
             CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
             if ((rc = launch_on(k_plain, L.d_list_plain + L.n_plain_int, L.n_plain - L.n_plain_int, true, false))) return rc;
         } else if ((rc = launch_on(k_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
-        if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)(L.n_plain + (merged ? L.n_full : 0)) * BS3))) return rc;
+        if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)(L.n_plain + (merged ? n_face_merged : 0)) * BS3))) return rc;
         // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
         const bool pc = ctx->profiling && !fork && !fork_full;
         if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
@@ -566,9 +582,9 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
         if ((rc = prof_begin(ctx, 2, pc && L.n_feat > 0))) return rc;
         if ((rc = launch_on(k_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
-        if ((rc = prof_begin(ctx, 3, pc && L.n_full > 0))) return rc;
-        if (!fork_full && !merged && (rc = launch_on(k_full, L.d_list_full, L.n_full, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
-        if ((rc = prof_end(ctx, pc && L.n_full > 0, 0))) return rc;
+        if ((rc = prof_begin(ctx, 3, pc && n_full_left > 0))) return rc;
+        if (!fork_full && (rc = launch_on(k_full, list_full, n_full_left, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
+        if ((rc = prof_end(ctx, pc && n_full_left > 0, 0))) return rc;
         for (int i = 0; i < used; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         if (overlap_pre) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pre, 0));   // nothing on the main stream consumed it yet
     }
@@ -951,7 +967,7 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         const int n = atoi(value);
         if (n != 3 && n != 4 && n != 5) return fail(ctx, LUDWIG_EINVAL, "strict_feature_occupancy: 3 | 4 | 5");
         ctx->opt_strict_feat_occ = n;
-    } else if (k == "merge_face") ctx->opt_merge_face = v == "auto" ? -1 : (on ? 1 : 0);   // plain + domain-face K1 classes in one launch (levels without a pre-pass): auto = fast mode only
+    } else if (k == "merge_face") ctx->opt_merge_face = on ? 1 : 0;   // domain-face blocks ride in the plain K1 launch (levels without a pre-pass)
     else if (k == "face_persist") {           // persistent CTAs per SM of the domain-face K1 class beside a much larger plain launch (0 = off)
         const int n = atoi(value);
         if (n < 0 || n > 8) return fail(ctx, LUDWIG_EINVAL, "face_persist: 0..8");

@@ -127,7 +127,10 @@ template <> struct FStore<true> {
 // One 8^3 block: 256 threads, two x-adjacent cells per thread.  fbase + s_fo[d] is neighbour block d's populations (fbase is
 // a.f_in, or — TMA variant — the same address with its global provenance hidden, because s_fo[13] then points into shared memory
 // and the loads must be generic).
-template <bool FULL, bool VELFB, bool MISS, bool STASH, bool WALE_FIRST, bool MISS_UNIFORM = true>
+// XONLY (with MISS): the only neighbours the block lacks lie beyond the domain's inlet / outlet plane and it has no feature (the host
+// checks both when it builds the work lists): the closed-form x-face populations are all that is needed - no out-of-line boundary code,
+// the register budget of the plain kernel.
+template <bool FULL, bool VELFB, bool MISS, bool STASH, bool WALE_FIRST, bool MISS_UNIFORM = true, bool XONLY = false>
 __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const int t, const float* __restrict__ fbase, const long long* s_fo,
                                              const long long* s_vo, float2* s_stash) {
     const v2 NZ = V(a.negzero);
@@ -136,9 +139,9 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
     const int x0 = 2 * p, c0 = 2 * t;
     uint32_t bflags = BF_INTERIOR;
     int gx = 0, gy = 0, gz = 0;   // 1-based global coords of cell A (MISS only)
-    if (FULL) {
+    if (FULL || MISS) {
         const int4 bc = *reinterpret_cast<const int4*>(a.bcoord + (size_t)b * 4);
-        bflags = (uint32_t)bc.w;
+        if (FULL) bflags = (uint32_t)bc.w;
         if (MISS) { gx = bc.x * BS + x0 + 1; gy = bc.y * BS + y + 1; gz = bc.z * BS + z + 1; }
     }
     // domain x faces in closed form (cell A on the inlet plane / cell B on the outlet plane; an inlet source wins over y / z faces
@@ -246,7 +249,7 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
             } else {
                 // some source block may be missing (domain face).  MISS_UNIFORM: every thread of a domain-face block takes this path, so
                 // that the lanes on the face (a quarter of every warp at an x face) do not make the warp execute both paths
-                if (o0 != MISSING) {
+                if (XONLY || o0 != MISSING) {
                     const float* __restrict__ P0 = fbase + o0 + (loc + x0);
                     f0 = ld2(P0 + k0 * BS3); fp.y = P0[kp * BS3]; fm.x = P0[km * BS3 + 1];
                 } else {
@@ -254,8 +257,8 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
                     fp.y = pull_missing(a, fin_own + 1, kp, gx + 1, gy, gz);
                     fm.x = pull_missing(a, fin_own, km, gx, gy, gz);
                 }
-                fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : at_inlet ? lat_w_of(kp) * xf.p_in : pull_missing(a, fin_own, kp, gx, gy, gz);
-                fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : at_outlet ? lat_w_of(km) * xf.p_out : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
+                fp.x = oM != MISSING ? fbase[oM + (loc + xM) + kp * BS3] : (XONLY || at_inlet) ? lat_w_of(kp) * xf.p_in : pull_missing(a, fin_own, kp, gx, gy, gz);
+                fm.y = oP != MISSING ? fbase[oP + (loc + xP) + km * BS3] : (XONLY || at_outlet) ? lat_w_of(km) * xf.p_out : pull_missing(a, fin_own + 1, km, gx + 1, gy, gz);
             }
             f.set(km, fm); f.set(k0, f0); f.set(kp, fp);
             // rho += f_k; j += f_k c_k  (k = km: cx = -1, k0: cx = 0, kp: cx = +1; cy = jyc - 1, cz = jzc - 1)
@@ -432,10 +435,8 @@ __global__ void __launch_bounds__(NT, STASH ? 3 * (256 / NT) : (OCC * 128) / NT)
 // CTA-uniform branch picks the body.  The face blocks (3 % of the bench box) then run BETWEEN plain CTAs on the same SMs instead of as
 // 28 half-empty waves of latency-bound CTAs after the plain launch; the register budget is the plain kernel's (96), the face body
 // spills into it, which only the face CTAs pay.  Same bodies, same bits.
-// (out of line: ptxas then allocates the plain body's registers exactly as in the plain kernel; the face body keeps its own frame)
-__device__ __noinline__ void strict_face_part(const K1Args& a, int b, int t, const long long* s_fo, const long long* s_vo) {
-    strict_block<true, true, true, false, true>(a, b, t, a.f_in, s_fo, s_vo, nullptr);
-}
+// strict mode: the face blocks of the merged list are the X-ONLY ones (see strict_block), whose body is as lean as the plain one; the
+// general domain-face class (y / z faces, features, anything that needs pull_missing) keeps its own launch.
 __global__ void __launch_bounds__(64, 10) k1_strict_mixed_kernel(const __grid_constant__ K1Args a) {
     __shared__ long long s_fo[27], s_vo[27];
     const int b = a.list[blockIdx.x >> 2];
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(64, 10) k1_strict_mixed_kernel(const __grid_co
     if (threadIdx.x < 27) { neighbour_offsets(a, b, threadIdx.x, (long long)b * (Q * BS3), s_fo, s_vo); miss = s_fo[threadIdx.x] == MISSING; }
     const bool face = __syncthreads_or(miss) != 0;
     const int t = (int)threadIdx.x + (int)(blockIdx.x & 3) * 64;
-    if (face) strict_face_part(a, b, t, s_fo, s_vo);
+    if (face) strict_block<false, true, true, false, true, true, true>(a, b, t, a.f_in, s_fo, s_vo, nullptr);
     else strict_block<false, false, false, false, true>(a, b, t, a.f_in, s_fo, s_vo, nullptr);
 }
 

@@ -135,7 +135,10 @@ struct Level {
     int32_t* d_list_plain_g = nullptr;   // all 26 neighbours real or ghost, no feature flag
     int32_t* d_list_feat = nullptr;      // all 26 neighbours present, some feature flag
     int32_t* d_list_full = nullptr;      // some neighbour missing (domain face)
-    int32_t* d_list_plain_full = nullptr; // plain + full in internal (spatial) order: the merged launch (option merge_face)
+    int32_t* d_list_plain_full = nullptr; // plain + full in internal (spatial) order: the merged launch (option merge_face), fast mode
+    int32_t* d_list_plain_xface = nullptr; // plain + x-only face blocks (no feature, nothing missing but beyond the inlet / outlet plane): merged launch, strict mode
+    int32_t* d_list_full_rest = nullptr;  // full minus the x-only face blocks
+    int n_xface = 0;
     int32_t* d_list_nonplain = nullptr;  // plain_g + feat + full (strict mode: the generic strict kernel)
     int n_plain = 0, n_plain_g = 0, n_feat = 0, n_full = 0;
 
@@ -208,7 +211,7 @@ struct ludwig_ctx {
     int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
     int opt_strict_occ = 5;                  // "strict_occupancy" = 4 | 5 | 6 (5: measured best, profiles/README.md)
-    int opt_merge_face = -1;                 // "merge_face": plain and domain-face K1 classes in one launch on levels without an interface pre-pass: auto (fast mode only: measured) | 0 | 1
+    int opt_merge_face = 1;                  // "merge_face": domain-face blocks ride in the plain K1 launch on levels without an interface pre-pass (strict: the x-only ones)
     int opt_face_persist = 0;                // "face_persist": persistent CTAs per SM of the domain-face K1 class beside the plain launch (0 = off: measured slower, profiles/README.md)
     int opt_strict_feat_occ = 4;             // "strict_feature_occupancy" = 4 | 5 (128 / 96 registers for the feature and domain-face classes)
     int opt_strict_loop = 1;                 // "strict_loop" = 1 | 2 | 4: z-plane pairs of a block one 64-thread CTA works through

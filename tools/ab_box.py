@@ -15,6 +15,7 @@ ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--warmup", type=int, default=6)
 ap.add_argument("--repeat", type=int, default=2)
 ap.add_argument("--profile-steps", type=int, default=6)
+ap.add_argument("--e2e-steps", type=int, default=20)
 ap.add_argument("variants", nargs="+")
 a = ap.parse_args()
 lv = syn.make_box_level(a.nb, a.nb, a.nb)
@@ -44,9 +45,9 @@ for early, vs in by_ctx.items():
                     c.profile_enable(True); c.step_batch(t, a.profile_steps, 0.03, p); t += a.profile_steps
                     k_ms, k_l, k_cells = c.profile_read(); classes = {k: round(v / a.profile_steps, 3) for k, v in c.profile_classes().items() if v}; c.profile_enable(False)
                 t0 = time.perf_counter()
-                for _ in range(20):
+                for _ in range(a.e2e_steps):
                     c.step_batch(t, 1, 0.03, p); t += 1; st = c.flow_stats(0)
-                e2e = (time.perf_counter() - t0) / 20
+                e2e = (time.perf_counter() - t0) / max(a.e2e_steps, 1)
                 print(f"AB {name:28s} {fp:6s} early={dict(early)} opts={o} rep={rep} ms/step={dt / a.steps * 1e3:.3f} MLUPS={lv.n_cells * a.steps / dt / 1e6:.0f} "
                       f"plain_kernel_ms={k_ms / max(k_l, 1):.3f} frac216={(k_cells / max(k_l, 1)) * 216 / (max(k_ms, 1e-9) / max(k_l, 1) * 1e-3) / 1e9 / 6456.5:.3f} classes={classes} e2e_ms={e2e * 1e3:.3f}", flush=True)
         print("stats", c.flow_stats(0), flush=True)
