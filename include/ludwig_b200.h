@@ -123,6 +123,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx);
  *                                     with the x-slices of a tile one after the other (default xslab12: x-face halo sectors stay in L2)
  *   merge_face = 0 | 1                domain-face blocks ride in the plain K1 launch on levels without an interface pre-pass (default 1;
  *                                     strict mode: only the blocks that lack nothing but what lies beyond the inlet / outlet plane)
+ *   feature_first = 0 | 1             feature blocks without a ghost neighbour before the plain launch, beside the pre-pass (measured: no effect, off)
  *   face_persist = N                  domain-face K1 class as N persistent CTAs per SM beside the plain launch (0 = off: measured slower)
  *   strict_loop = 1 | 2 | 4           z-plane pairs of a block one 64-thread strict K1 CTA works through (1: measured best)
  *   strict_feature_occupancy = 3 | 4 | 5   register budget of the strict feature / domain-face classes (166 / 128 / 96; 4: measured best)

@@ -218,7 +218,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         gstart.push_back((int32_t)gcell.size());
     }
     // K1 work lists
-    std::vector<int32_t> lp, lg, le, lf, lx, lfr;   // lx: x-only face blocks (subset of lf), lfr = lf without them
+    std::vector<int32_t> lp, lg, le, le_g, lf, lx, lfr;   // lx: x-only face blocks (subset of lf), lfr = lf without them; le_g: feature blocks with a ghost neighbour
     const int nxg_level = p.domain_nx << (L.level_id - 1);
     for (int b = 0; b < nb; ++b) {
         bool all = true, ghost = false, xonly = true;
@@ -233,7 +233,7 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         }
         const uint32_t feat = (uint32_t)L.h_bcoord[(size_t)b * 4 + 3] & (BF_OBSTACLE | BF_SPONGE | BF_WALLDIST);
         if (all && !feat) (ghost ? lg : lp).push_back(b);
-        else if (all) le.push_back(b);
+        else if (all) (ghost ? le_g : le).push_back(b);
         else { lf.push_back(b); (xonly && !feat && !ghost ? lx : lfr).push_back(b); }
     }
     // plain blocks without a remote neighbour first: they can run while the halo import is still in flight
@@ -265,6 +265,8 @@ int ensure_fast_tables(ludwig_ctx* ctx, Level& L, const ludwig_params& p) {
         if (order != "last") L.n_plain_int = 0;   // only the mirror mode splits the launch
     }
     L.n_ghost = ng; L.n_gcell = (int)gcell.size();
+    L.n_feat_nog = (int)le.size();
+    le.insert(le.end(), le_g.begin(), le_g.end());   // feature list = [no ghost neighbour ..., with ghost neighbour ...]
     L.n_plain = (int)lp.size(); L.n_plain_g = (int)lg.size(); L.n_feat = (int)le.size(); L.n_full = (int)lf.size();
     CU(dalloc(ctx, &L.d_nbr_fast, nbrf.size()));
     CU(memcpy_sync(ctx->stream, L.d_nbr_fast, nbrf.data(), nbrf.size() * 4, cudaMemcpyHostToDevice));
@@ -565,6 +567,18 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
         const int32_t* list_full = merged && strict ? L.d_list_full_rest : L.d_list_full;
         const int n_full_left = merged ? L.n_full - n_face_merged : L.n_full;
         if (fork_full && (rc = launch_on(k_full, L.d_list_full, L.n_full, false, true))) return rc;
+        // feature_first (option, off): while the interface pre-pass runs on its own stream, the feature blocks that pull from no ghost
+        // block go first — they are compute-bound, so the latency-bound pre-pass would get the memory system it crawls without beside
+        // the plain launch.  Measured on the shipped bunny and wing (both FP modes): no effect (65.4 / 65.5 vs 65.3 / 65.8 ms): the GPU
+        // is busy either way, the pre-pass is work, not a wait; reordering launches cannot remove it.
+        const bool pc = ctx->profiling && !fork && !fork_full;   // (with profiling on and no forking, classes 1..3 are bracketed too)
+        // (not with the persistent ticket-scheduled variants: two launches of one class would share a ticket counter)
+        const int n_feat_first = (ctx->opt_feature_first && overlap_pre && L.n_plain > 0 && (strict ? a.strict_stash : a.fast_variant) != 2) ? L.n_feat_nog : 0;
+        if (n_feat_first > 0) {   // main stream, no wait for the pre-pass: no entry of this part of the list has a ghost neighbour
+            if ((rc = prof_begin(ctx, 2, pc))) return rc;
+            if ((rc = launch_on(k_feat, L.d_list_feat, n_feat_first, true, false))) return rc;
+            if ((rc = prof_end(ctx, pc, 0))) return rc;
+        }
         if ((rc = prof_begin(ctx, 0, L.n_plain > 0))) return rc;
         if (merged) {
             if ((rc = launch_on(strict ? launch_k1s_mixed : launch_k1_mixed, strict ? L.d_list_plain_xface : L.d_list_plain_full, L.n_plain + n_face_merged, true, false))) return rc;
@@ -574,14 +588,12 @@ int step_level_phase(ludwig_ctx* ctx, Level& L, const ParentView* pv, int64_t t_
             if ((rc = launch_on(k_plain, L.d_list_plain + L.n_plain_int, L.n_plain - L.n_plain_int, true, false))) return rc;
         } else if ((rc = launch_on(k_plain, L.d_list_plain, L.n_plain, true, false))) return rc;
         if ((rc = prof_end(ctx, L.n_plain > 0, (int64_t)(L.n_plain + (merged ? n_face_merged : 0)) * BS3))) return rc;
-        // (with profiling on and no forking, classes 1..3 are bracketed too: per-class device time of this rank)
-        const bool pc = ctx->profiling && !fork && !fork_full;
         if ((rc = prof_begin(ctx, 1, pc && L.n_plain_g > 0))) return rc;
         if ((rc = launch_on(k_plain_g, L.d_list_plain_g, L.n_plain_g, L.n_plain == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && L.n_plain_g > 0, 0))) return rc;
-        if ((rc = prof_begin(ctx, 2, pc && L.n_feat > 0))) return rc;
-        if ((rc = launch_on(k_feat, L.d_list_feat, L.n_feat, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
-        if ((rc = prof_end(ctx, pc && L.n_feat > 0, 0))) return rc;
+        if ((rc = prof_begin(ctx, 2, pc && L.n_feat > n_feat_first))) return rc;
+        if ((rc = launch_on(k_feat, L.d_list_feat + n_feat_first, L.n_feat - n_feat_first, L.n_plain == 0 && L.n_plain_g == 0, true))) return rc;
+        if ((rc = prof_end(ctx, pc && L.n_feat > n_feat_first, 0))) return rc;
         if ((rc = prof_begin(ctx, 3, pc && n_full_left > 0))) return rc;
         if (!fork_full && (rc = launch_on(k_full, list_full, n_full_left, L.n_plain == 0 && L.n_plain_g == 0 && L.n_feat == 0, true))) return rc;
         if ((rc = prof_end(ctx, pc && n_full_left > 0, 0))) return rc;
@@ -967,7 +979,8 @@ int ludwig_ctx_set_option(ludwig_ctx* ctx, const char* key, const char* value) {
         const int n = atoi(value);
         if (n != 3 && n != 4 && n != 5) return fail(ctx, LUDWIG_EINVAL, "strict_feature_occupancy: 3 | 4 | 5");
         ctx->opt_strict_feat_occ = n;
-    } else if (k == "merge_face") ctx->opt_merge_face = on ? 1 : 0;   // domain-face blocks ride in the plain K1 launch (levels without a pre-pass)
+    } else if (k == "feature_first") ctx->opt_feature_first = on;         // feature blocks without a ghost neighbour before the plain launch, beside the pre-pass
+    else if (k == "merge_face") ctx->opt_merge_face = on ? 1 : 0;   // domain-face blocks ride in the plain K1 launch (levels without a pre-pass)
     else if (k == "face_persist") {           // persistent CTAs per SM of the domain-face K1 class beside a much larger plain launch (0 = off)
         const int n = atoi(value);
         if (n < 0 || n > 8) return fail(ctx, LUDWIG_EINVAL, "face_persist: 0..8");

@@ -141,6 +141,7 @@ struct Level {
     int n_xface = 0;
     int32_t* d_list_nonplain = nullptr;  // plain_g + feat + full (strict mode: the generic strict kernel)
     int n_plain = 0, n_plain_g = 0, n_feat = 0, n_full = 0;
+    int n_feat_nog = 0;                    // the first n_feat_nog entries of d_list_feat have no ghost-block neighbour (they need no pre-pass)
 
     // static fields (device)
     uint8_t* d_obstacle = nullptr;  // [nb][512]
@@ -211,6 +212,7 @@ struct ludwig_ctx {
     int opt_strict_variant = 0;              // "strict_kernel" = reg | stash | tma
     int opt_fast_variant = 0;                // "fast_kernel" = direct | tma
     int opt_strict_occ = 5;                  // "strict_occupancy" = 4 | 5 | 6 (5: measured best, profiles/README.md)
+    bool opt_feature_first = false;          // "feature_first": feature blocks without a ghost neighbour run BEFORE the plain launch, beside the interface pre-pass (measured: no effect, off)
     int opt_merge_face = 1;                  // "merge_face": domain-face blocks ride in the plain K1 launch on levels without an interface pre-pass (strict: the x-only ones)
     int opt_face_persist = 0;                // "face_persist": persistent CTAs per SM of the domain-face K1 class beside the plain launch (0 = off: measured slower, profiles/README.md)
     int opt_strict_feat_occ = 4;             // "strict_feature_occupancy" = 4 | 5 (128 / 96 registers for the feature and domain-face classes)
