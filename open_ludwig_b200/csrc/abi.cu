@@ -1748,12 +1748,15 @@ int ludwig_block_costs(const ludwig_level_desc* d, float* cost) {
             const float w = d->wall_dist[i];
             wd |= (w > 0.0f && w < 10.0f);
         }
-        bool miss = false;
-        for (int dir = 0; dir < 27; ++dir) miss |= d->neighbor_table[b + (size_t)nb * dir] == 0;
+        bool miss = false, miss_x_only = true;   // x-only: nothing missing but beyond the inlet / outlet plane (level 1)
+        for (int dir = 0; dir < 27; ++dir)
+            if (d->neighbor_table[b + (size_t)nb * dir] == 0) { miss = true; if (dir % 3 == 1) miss_x_only = false; }
+        const bool feat = n_obs > 0 || sp || wd;
         float c = 1.0f;
         if (n_obs == BS3) c = 0.6f;
-        else if (n_obs > 0 || sp || wd) c += 1.0f;
-        if (miss) c += 1.0f;
+        else if (feat) c += 1.0f;
+        // (a feature-less inlet / outlet block of level 1 rides in the plain launch with a body as lean as the plain one: merge_face)
+        if (miss && !(miss_x_only && !feat && d->level_id == 1)) c += 1.0f;
         cost[b] = c;
     }
     if (d->bouzidi_enabled && d->cell_block)

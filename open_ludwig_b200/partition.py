@@ -50,11 +50,15 @@ def block_costs(level) -> np.ndarray:
     sp = (np.asarray(level.sponge).reshape(nb, 512) > 0).any(axis=1)
     wdv = np.asarray(level.wall_dist).reshape(nb, 512)
     wd = ((wdv > 0) & (wdv < 10)).any(axis=1)
-    miss = (np.asarray(level.neighbor_table) == 0).any(axis=0)
+    nt0 = np.asarray(level.neighbor_table) == 0
+    miss = nt0.any(axis=0)
+    miss_dx0 = nt0[np.arange(27) % 3 == 1].any(axis=0)                 # something missing that is not beyond an x face
+    feat = (n_obs > 0) | sp | wd
     c = np.ones(nb, np.float32)
-    c[(n_obs > 0) | sp | wd] += np.float32(1.0)
+    c[feat] += np.float32(1.0)
     c[n_obs == 512] = np.float32(0.6)
-    c[miss] += np.float32(1.0)
+    lean = ~miss_dx0 & ~feat & (level.level_id == 1)                    # feature-less inlet / outlet block: rides in the plain launch
+    c[miss & ~lean] += np.float32(1.0)
     if level.bouzidi_enabled and level.cell_block is not None:
         for b in np.asarray(level.cell_block) - 1:          # sequential float32 adds, like the library
             c[b] = np.float32(c[b] + np.float32(0.004))
