@@ -70,22 +70,21 @@ def attach_peers(ctx: cabi.Context, device: torch.device, barrier: str | None = 
 
 
 def reduce_stats(stats: dict, device: torch.device) -> dict:
-    """Combine per-rank ludwig_flow_stats results (diagnostics.jl:56-94 over the whole level)."""
+    """Combine per-rank ludwig_flow_stats results (diagnostics.jl:56-94 over the whole level): ONE all-gather of the six partial
+    values per rank and a host-side reduction in rank order (sums are deterministic; a NaN density / velocity stays NaN as in the
+    library and in Julia's minimum / maximum, which MIN / MAX all-reduces would drop)."""
     device = _comm_device(device)
-    s = torch.tensor([stats["n_fluid"], stats["rho_mean"] * stats["n_fluid"], stats["kinetic_energy"]], dtype=torch.float64, device=device)
-    mn = torch.tensor([stats["rho_min"]], dtype=torch.float64, device=device)
-    mx = torch.tensor([stats["rho_max"], stats["v_max"]], dtype=torch.float64, device=device)
-    dist.all_reduce(s); dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    n = float(s[0])
-    # torch's MIN / MAX all-reduce drop NaN like fminf; the library reports a NaN density / velocity as NaN min / max, keep it
-    bad = torch.tensor([float(np.isnan(stats["rho_min"]) or np.isnan(stats["rho_max"])), float(np.isnan(stats["v_max"]))], dtype=torch.float64, device=device)
-    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-    if float(bad[0]) > 0:
-        mn[0] = float("nan"); mx[0] = float("nan")
-    if float(bad[1]) > 0:
-        mx[1] = float("nan")
-    return {"n_fluid": n, "rho_mean": float(s[1]) / max(n, 1.0), "rho_min": float(mn[0]), "rho_max": float(mx[0]),
-            "v_max": float(mx[1]), "kinetic_energy": float(s[2])}
+    mine = torch.tensor([stats["n_fluid"], stats["rho_mean"] * stats["n_fluid"], stats["kinetic_energy"], stats["rho_min"], stats["rho_max"],
+                         stats["v_max"]], dtype=torch.float64, device=device)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    a = torch.stack(parts).cpu().numpy()
+    n = float(a[:, 0].sum())
+    nan_rho = bool(np.isnan(a[:, 3]).any() or np.isnan(a[:, 4]).any())
+    nan_v = bool(np.isnan(a[:, 5]).any())
+    return {"n_fluid": n, "rho_mean": float(a[:, 1].sum()) / max(n, 1.0), "rho_min": float("nan") if nan_rho else float(a[:, 3].min()),
+            "rho_max": float("nan") if nan_rho else float(a[:, 4].max()), "v_max": float("nan") if nan_v else float(a[:, 5].max()),
+            "kinetic_energy": float(a[:, 2].sum())}
 
 
 def reduce_aero(aero: dict, device: torch.device) -> dict:
