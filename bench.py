@@ -41,7 +41,7 @@ DEFAULT_FP_MODE = "strict"          # the mode whose results are bit-identical t
 DEFAULT_STRONG_PARTITION = "rcb_yz"
 # 1-GPU time per coarse step of the strong-scaling case measured by this file's own strong record (profiles/), for the
 # efficiency shown at N > 1: (case, fp_mode) -> ms
-T1_MS_COMMITTED = {("bunny_fine", "fast"): 495.6, ("bunny_fine", "strict"): 575.0}   # profiles/r2e_bunny_fine_1gpu_fast.log, r2s_bench_default_1gpu_xslab12.json (this file's strong record at N = 1)
+T1_MS_COMMITTED = {("bunny_fine", "fast"): 495.6, ("bunny_fine", "strict"): 552.4}   # profiles/r2e_bunny_fine_1gpu_fast.log, r2y_bench_default_1gpu.json (this file's strong record at N = 1; 552-575 ms from box to box)
 
 
 def measured_peaks():
