@@ -325,7 +325,11 @@ __device__ __forceinline__ void strict_block(const K1Args& a, const int b, const
         const v2 dw = ld2(a.wall_dist + (size_t)b * BS3 + c0);
         if (dw.x > 0.0f && dw.x < 10.0f && !obsA) { float3 F = wall_force(dw.x, rho.x, ux.x, uy.x, uz.x, a.tau, a.wm_c166); Fx.x = F.x; Fy.x = F.y; Fz.x = F.z; }
         if (dw.y > 0.0f && dw.y < 10.0f && !obsB) { float3 F = wall_force(dw.y, rho.y, ux.y, uy.y, uz.y, a.tau, a.wm_c166); Fx.y = F.x; Fy.y = F.y; Fz.y = F.z; }
-        has_force = true;
+        // The force enters u_eq and the force term of the collision loop only through sums and products in which a zero force
+        // contributes +-0 (u + 0.5 * 0 / rho, out + hw * w * (a . 0)): where no cell of the warp's z-plane carries a force — the outer
+        // part of the 10-cell near-wall shell, cells the law of the wall leaves alone — both are skipped, as in blocks without wall distance.
+        const bool nz = Fx.x != 0.0f || Fx.y != 0.0f || Fy.x != 0.0f || Fy.y != 0.0f || Fz.x != 0.0f || Fz.y != 0.0f;
+        has_force = __any_sync(__activemask(), nz) != 0;
     }
     // u_eq = u + 0.5 F inv_rho with the PRE-sponge 1/rho (:238); without a force it is u (+0 changes no value)
     v2 uxe = ux, uye = uy, uze = uz;

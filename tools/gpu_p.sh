@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/mg_check.py > gpurun_out/p_mg_check.log 2>&1; echo "exit $?" >> gpurun_out/p_mg_check.log
-grep -E "MG_CHECK|exit|Error|identical" gpurun_out/p_mg_check.log | tail -5 | cut -c1-200
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 40 --warmup 5 --strong-case none --no-cpu --fast-init 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value',round(d['value']),'e2e',round(d['e2e']['value']),'ms',round(d['ms_per_step'],3))"
+timeout 900 python -m pytest tests/test_k1_features_gpu.py tests/test_bunny_small_gpu.py tests/test_full_size_cases_gpu.py tests/test_cases_gpu.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -4
+timeout 1200 python tools/run_case_mg.py bunny 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_bunny.log 2>&1
+grep -E "RESULT|exit|Error" gpurun_out/p_bunny.log | cut -c1-200
+timeout 1200 python tools/run_case_mg.py wing5 8 --fp-mode strict --uniform-start --variant "verbose=0" --variant "verbose=0" > gpurun_out/p_wing.log 2>&1
+grep -E "RESULT|exit|Error" gpurun_out/p_wing.log | cut -c1-200
