@@ -170,3 +170,29 @@ def test_rcb_partition_is_balanced_compact_and_deterministic(cuda_lib):
     small = syn.make_box_level(1, 1, 2)
     d2, keep2 = cabi.Context.make_desc(small)
     assert lib.ludwig_partition_rcb(C.byref(d2), 4, own_bad.ctypes.data_as(C.c_void_p)) != 0      # fewer blocks than ranks
+
+
+def test_xslab_order_keeps_x_neighbours_close():
+    """The library's default internal order (x-slab, T = 12: DESIGN.md section 4): inside a rank every block's x neighbour is at most
+    T * T positions away (its x-face halo sectors — 8x as expensive as a y / z face — are still in L2 when it runs), the order is a
+    permutation, and it is the Morton order when block_order = 0."""
+    lv = syn.make_box_level(20, 30, 26)
+    co = lv.active_block_coords
+    for T in (2, 5, 12):
+        order = partition.internal_order(co, 1, block_order=T)
+        assert sorted(order.tolist()) == list(range(lv.n_blocks))
+        pos = np.empty(lv.n_blocks, np.int64); pos[order] = np.arange(lv.n_blocks)
+        index = {tuple(c): i for i, c in enumerate(co.tolist())}
+        worst = 0
+        for i, (x, y, z) in enumerate(co.tolist()):
+            j = index.get((x + 1, y, z))
+            if j is not None:
+                worst = max(worst, abs(int(pos[j]) - int(pos[i])))
+        assert worst <= T * T, (T, worst)
+    assert np.array_equal(partition.internal_order(co, 1, block_order=0), partition.morton_order(co))
+    # partitioned: the owners are cut on the Morton order, only the order INSIDE a rank changes
+    for world in (2, 3):
+        own_m = partition.owner_of_ref(co, world, level=lv)
+        for r in range(world):
+            mine = partition.local_blocks(co, r, world, level=lv)
+            assert np.all(own_m[mine] == r) and len(mine) == int((own_m == r).sum())
