@@ -92,32 +92,47 @@ PeerPtrs peers_of(const float* const (&tab)[MAX_RANKS]) {
 
 // Upload one reference-layout field [ncomp][nb_ref][512] into the internal layout [nb_int][ncomp][512],
 // one component at a time through a 2 KiB-per-block staging buffer.
+// Staging buffer of the level uploads / downloads: one component of a level in the caller's order.  Kept between calls, grown on
+// demand, released by release_stage() when stepping starts (a 339 M-cell case would otherwise hold 1 GB for nothing).
+int ensure_stage(ludwig_ctx* ctx, size_t n) {
+    if (ctx->stage_floats >= n) return LUDWIG_OK;
+    if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_floats = 0; }
+    CU(cudaMalloc((void**)&ctx->d_stage, n * sizeof(float)));
+    ctx->stage_floats = n;
+    return LUDWIG_OK;
+}
+void release_stage(ludwig_ctx* ctx) {
+    if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_floats = 0; }
+}
 int upload_field(ludwig_ctx* ctx, Level& L, const float* h_src, float* d_dst, int ncomp, bool local_order = false) {
-    float* stage = nullptr;
     // global: the host array covers the whole level in reference order, d_int2ref picks the local blocks;
     // local_order: the host array holds only this rank's blocks, already in the library's internal order
-    size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;
-    CU(cudaMalloc((void**)&stage, n * 4));
+    const size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;
+    int rc = ensure_stage(ctx, n);
+    if (rc) return rc;
+    // stream order keeps component k's scatter ahead of component k + 1's copy into the same buffer: no host synchronisation per
+    // component (a copy from pageable memory returns once the source has been read), one at the end to report errors
     for (int k = 0; k < ncomp; ++k) {
-        cudaError_t e = cudaMemcpyAsync(stage, h_src + n * k, n * 4, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) { launch_ref_to_int(stage, d_dst, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream); e = cudaStreamSynchronize(ctx->stream); }
-        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("upload_field: ") + cudaGetErrorString(e)); }
+        CU(cudaMemcpyAsync(ctx->d_stage, h_src + n * k, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        launch_ref_to_int(ctx->d_stage, d_dst, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream);
     }
-    cudaFree(stage);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, std::string("upload_field: ") + cudaGetErrorString(e));
     return LUDWIG_OK;
 }
 int download_field(ludwig_ctx* ctx, Level& L, const float* d_src, float* h_dst, int ncomp, bool local_order = false) {
-    float* stage = nullptr;
-    size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;   // global: blocks owned by other ranks are returned as zeros
-    CU(cudaMalloc((void**)&stage, n * 4));
-    for (int k = 0; k < ncomp; ++k) {
-        if (!local_order && L.nb != L.nb_global) CU(cudaMemsetAsync(stage, 0, n * 4, ctx->stream));
-        launch_int_to_ref(d_src, stage, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream);
-        cudaError_t e = cudaMemcpyAsync(h_dst + n * k, stage, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFree(stage); return fail(ctx, LUDWIG_ECUDA, std::string("download_field: ") + cudaGetErrorString(e)); }
+    const size_t n = (size_t)(local_order ? L.nb : L.nb_global) * BS3;   // global: blocks owned by other ranks are returned as zeros
+    int rc = ensure_stage(ctx, n);
+    if (rc) return rc;
+    for (int k = 0; k < ncomp; ++k) {   // (a copy to pageable memory returns when it is complete: the buffer is free for the next component)
+        if (!local_order && L.nb != L.nb_global) CU(cudaMemsetAsync(ctx->d_stage, 0, n * 4, ctx->stream));
+        launch_int_to_ref(d_src, ctx->d_stage, local_order ? nullptr : L.d_int2ref, L.nb, ncomp, k, ctx->stream);
+        CU(cudaMemcpyAsync(h_dst + n * k, ctx->d_stage, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    cudaFree(stage);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LUDWIG_ECUDA, std::string("download_field: ") + cudaGetErrorString(e));
     return LUDWIG_OK;
 }
 
@@ -803,6 +818,7 @@ int group_step_batch(Group& g, int64_t t_start, int32_t batch_size, float u_curr
     for (ludwig_ctx* ctx : g.c) {
         if (g.c.size() > 1) CU(cudaSetDevice(ctx->device));
         if (ctx->world > 1 && !ctx->peers_attached) return fail(ctx, LUDWIG_ESTATE, "multi-GPU context: attach the peers first");
+        release_stage(ctx);   // the upload / download staging buffer is not held while the case steps
         int rcp = prepare_tables(ctx, p);
         if (rcp) return rcp;
         // export the halo layers of the CURRENT state (it may have been uploaded or initialised since the last batch): level l's
@@ -932,6 +948,7 @@ int ludwig_ctx_destroy(ludwig_ctx* ctx) {
     if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->h_bar_err) cudaFreeHost(ctx->h_bar_err);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
+    release_stage(ctx);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

@@ -229,6 +229,8 @@ struct ludwig_ctx {
     unsigned long long* d_ticket = nullptr;   // [4] ticket counters of the persistent K1 variants, one per launch class
     unsigned long long ticket_base[4] = {0, 0, 0, 0};
     double* d_stats = nullptr;   // flow-stats partials
+    float* d_stage = nullptr;    // one component of a whole level in reference order: staging of ludwig_level_upload / download, kept
+    size_t stage_floats = 0;     // between calls (a case uploads ~30 components per level) and released when stepping starts
     double* h_stats = nullptr;   // pinned
     int num_sms = 148;
     int rank = 0, world = 1;
